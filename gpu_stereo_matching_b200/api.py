@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference interface for the BlockMatching hot path.
+
+Reference interface (C++, OpenCV types)                      this module
+  blockMatching_gpu(Mat&, Mat&, Mat&, int, int)                blockMatching_gpu(left, right, SADWindowSize, searchRange)
+      BlockMatching/Device.cuh:50, Device.cu:173-301
+  singleFrame()  BlockMatching/Caller.cpp:9-25                 singleFrame(left_gray, right_gray)  (imread/imshow decoupled)
+  PreCal / getAllSAD / compareDiff / compareSAD / compareDisp   StereoContext.ad_volume / all_sad / compare_disp
+      BlockMatching/BlockMatching.h:8-15
+Same argument meaning (SADWindowSize is a radius, searchRange the number of disparities) and the
+same result (u8 disparity, rows x cols).  Errors raise GsmError instead of being ignored.
+
+Everything computes in libgsm.so (CUDA, sm_100a) through the C ABI of include/gsm.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import lib as _l
+from .lib import GSM_MODE_GF, GSM_MODE_SAD, GsmError, GsmParams  # noqa: F401
+
+GF_EPS_DEFAULT = 6.5025  # 1e-4 * 255^2
+
+
+def make_params(mode="sad", radius=5, num_disp=64, eps=0.0, lr_check=False, median_radius=0, row_bands=0,
+                d_begin=0, d_end=0) -> GsmParams:
+    m = {"sad": GSM_MODE_SAD, "gf": GSM_MODE_GF}[mode] if isinstance(mode, str) else int(mode)
+    return GsmParams(m, int(radius), int(num_disp), float(eps), int(bool(lr_check)), int(median_radius),
+                     int(row_bands), int(d_begin), int(d_end))
+
+
+def _u8c(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError(f"{name}: expected uint8 (CV_8UC1), got {a.dtype}")
+    return np.ascontiguousarray(a)  # the reference requires continuous Mats (Device.cu:213-214)
+
+
+def _ptr(a) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
+
+
+class StereoContext:
+    """Owns one gsm_ctx (device buffers, stream) on one GPU.  One host thread at a time."""
+
+    def __init__(self, max_rows: int, max_cols: int, max_disp: int = 256, max_batch: int = 1, device: int = 0):
+        self._lib = _l.load()
+        self._h = C.c_void_p(None)
+        _l.check(self._lib.gsm_create(C.byref(self._h), device, max_rows, max_cols, max_disp, max_batch))
+        self.device = device
+        self.max_rows, self.max_cols, self.max_disp, self.max_batch = max_rows, max_cols, max_disp, max_batch
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.gsm_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- reference entry point -------------------------------------------------------------
+    def block_matching(self, left, right, radius: int, num_disp: int) -> np.ndarray:
+        """== blockMatching_gpu / getDisp (bit-exact), host arrays."""
+        L, R = _u8c(left, "left"), _u8c(right, "right")
+        if L.ndim != 2 or L.shape != R.shape:
+            raise ValueError("left/right must be 2-D and the same size")
+        out = np.empty_like(L)
+        _l.check(self._lib.gsm_block_matching(self._h, _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1],
+                                              radius, num_disp))
+        return out
+
+    # ---- full path -------------------------------------------------------------------------
+    def stereo_batch(self, left, right, params: GsmParams, out: Optional[np.ndarray] = None,
+                     mask_out: Optional[np.ndarray] = None) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        """n frames [n, rows, cols] (or one frame [rows, cols]) of host u8 -> (disparity, mask|None)."""
+        L, R = _u8c(left, "left"), _u8c(right, "right")
+        single = L.ndim == 2
+        if single:
+            L, R = L[None], R[None]
+        if L.ndim != 3 or L.shape != R.shape:
+            raise ValueError("left/right must be [n, rows, cols] and the same size")
+        n, rows, cols = L.shape
+        disp = out if out is not None else np.empty_like(L)
+        mask = None
+        if params.lr_check:
+            mask = mask_out if mask_out is not None else np.empty_like(L)
+        _l.check(self._lib.gsm_stereo_batch(self._h, C.byref(params), n, _ptr(L), _ptr(R), _ptr(disp), _ptr(mask),
+                                            rows, cols))
+        if single and out is None:
+            return disp[0], (mask[0] if mask is not None else None)
+        return disp, mask
+
+    def stereo(self, left, right, **kw):
+        return self.stereo_batch(left, right, make_params(**kw))
+
+    def stereo_device(self, left_ptr: int, right_ptr: int, disp_ptr: int, mask_ptr: int, n: int, rows: int,
+                      cols: int, params: GsmParams, stream: int = 0) -> None:
+        """Device-resident buffers (raw device pointers, e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
+        _l.check(self._lib.gsm_stereo_device(self._h, C.byref(params), n, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                             C.c_void_p(disp_ptr), C.c_void_p(mask_ptr or None), rows, cols,
+                                             C.c_void_p(stream or None)))
+
+    def sync(self):
+        _l.check(self._lib.gsm_sync(self._h))
+
+    # ---- multi-GPU disparity split -----------------------------------------------------------
+    def partial_keys_device(self, left_ptr, right_ptr, keys_ptr, rows, cols, params: GsmParams, view=0, stream=0):
+        _l.check(self._lib.gsm_partial_keys_device(self._h, C.byref(params), view, C.c_void_p(left_ptr),
+                                                   C.c_void_p(right_ptr), C.c_void_p(keys_ptr), rows, cols,
+                                                   C.c_void_p(stream or None)))
+
+    def finalize_keys_device(self, keys_left_ptr, keys_right_ptr, disp_ptr, mask_ptr, rows, cols, params: GsmParams,
+                             stream=0):
+        _l.check(self._lib.gsm_finalize_keys_device(self._h, C.byref(params), C.c_void_p(keys_left_ptr),
+                                                    C.c_void_p(keys_right_ptr or None), C.c_void_p(disp_ptr),
+                                                    C.c_void_p(mask_ptr or None), rows, cols,
+                                                    C.c_void_p(stream or None)))
+
+    # ---- cost-stage exports ------------------------------------------------------------------
+    def ad_volume(self, left, right, num_disp: int) -> np.ndarray:
+        """== PreCal (BlockMatching.cpp:89-109): u8 [D][rows][cols]."""
+        L, R = _u8c(left, "left"), _u8c(right, "right")
+        out = np.empty((num_disp,) + L.shape, np.uint8)
+        _l.check(self._lib.gsm_ad_volume(self._h, _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1], num_disp))
+        return out
+
+    def cost_slices(self, left, right, params: GsmParams, d0: int, nd: int, view: int = 0) -> np.ndarray:
+        """Aggregated cost for d in [d0, d0+nd): int32 SAD (mode sad) or float32 q (mode gf), [nd][rows][cols]."""
+        L, R = _u8c(left, "left"), _u8c(right, "right")
+        dt = np.int32 if params.mode == GSM_MODE_SAD else np.float32
+        out = np.empty((nd,) + L.shape, dt)
+        _l.check(self._lib.gsm_cost_slices(self._h, C.byref(params), view, _ptr(L), _ptr(R), d0, nd, _ptr(out),
+                                           L.shape[0], L.shape[1]))
+        return out
+
+    def all_sad(self, left, right, radius: int, num_disp: int) -> np.ndarray:
+        """== getAllSAD (BlockMatching.cpp:191-261): u8 [rows*cols][D]."""
+        L, R = _u8c(left, "left"), _u8c(right, "right")
+        out = np.empty((L.size, num_disp), np.uint8)
+        _l.check(self._lib.gsm_all_sad(self._h, _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1], radius,
+                                       num_disp))
+        return out
+
+    def median(self, img, radius: int) -> np.ndarray:
+        a = _u8c(img, "img")
+        out = np.empty_like(a)
+        _l.check(self._lib.gsm_median(self._h, _ptr(a), _ptr(out), a.shape[0], a.shape[1], radius))
+        return out
+
+    def lr_check(self, disp_left, disp_right):
+        a, b = _u8c(disp_left, "disp_left"), _u8c(disp_right, "disp_right")
+        occ, mask = np.empty_like(a), np.empty_like(a)
+        _l.check(self._lib.gsm_lr_check(self._h, _ptr(a), _ptr(b), _ptr(occ), _ptr(mask), a.shape[0], a.shape[1]))
+        return occ, mask
+
+    # ---- introspection -----------------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gsm_launch_count(self._h))
+
+    def set_kernel_timing(self, on: bool):
+        _l.check(self._lib.gsm_set_kernel_timing(self._h, int(on)))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.gsm_last_kernel_ms(self._h))
+
+    def measure_alu_peak(self) -> float:
+        v = C.c_double(0.0)
+        _l.check(self._lib.gsm_measure_alu_peak(self._h, C.byref(v)))
+        return v.value
+
+
+# ---- free functions with the reference's names ---------------------------------------------------
+_default_ctx: Optional[StereoContext] = None
+
+
+def _ctx_for(rows: int, cols: int, num_disp: int) -> StereoContext:
+    global _default_ctx
+    c = _default_ctx
+    if c is None or rows > c.max_rows or cols > c.max_cols or num_disp > c.max_disp:
+        if c is not None:
+            c.close()
+        _default_ctx = c = StereoContext(max(rows, 1080), max(cols, 1920), 256, 1)
+    return c
+
+
+def blockMatching_gpu(h_left, h_right, SADWindowSize: int, searchRange: int) -> np.ndarray:
+    """Drop-in for blockMatching_gpu(h_left, h_right, h_disparity, SADWindowSize, searchRange)
+    (BlockMatching/Device.cuh:50): returns h_disparity."""
+    L = _u8c(h_left, "h_left")
+    return _ctx_for(L.shape[0], L.shape[1], searchRange).block_matching(L, h_right, SADWindowSize, searchRange)
+
+
+def singleFrame(left_gray, right_gray) -> np.ndarray:
+    """Compute part of singleFrame() (BlockMatching/Caller.cpp:9-25): blockMatching_gpu(g1, g2, disp, 5, 64).
+    Image loading (imread + cvtColor) and display (imshow/waitKey) stay with the caller."""
+    return blockMatching_gpu(left_gray, right_gray, 5, 64)
+
+
+def compare_disp(reference_disp, gpu_disp):
+    """compareDisp (BlockMatching.cpp:278-293) without the printing: list of (row, col, cpu, gpu) mismatches."""
+    a, b = np.asarray(reference_disp), np.asarray(gpu_disp)
+    ys, xs = np.nonzero(a != b)
+    return [(int(y), int(x), int(a[y, x]), int(b[y, x])) for y, x in zip(ys, xs)]

@@ -1,0 +1,682 @@
+// gsm_api.cu -- host side of libgsm.so: context, launch plans and the C ABI declared in include/gsm.h.
+// Replaces the host "proxy" functions of the reference (BlockMatching/Device.cu:173-367).
+#include "../../include/gsm.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "gsm_common.cuh"
+#include "gsm_gf.cuh"
+#include "gsm_sad.cuh"
+#include "gsm_util.cuh"
+
+using namespace gsm;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(GSM_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct gsm_ctx {
+  int device = 0;
+  int max_rows = 0, max_cols = 0, max_disp = 0, max_batch = 0;
+  cudaStream_t stream = nullptr;
+  // device buffers, each sized for max_batch frames
+  u8 *tightL = nullptr, *tightR = nullptr;                       // uploads on the host path
+  u8 *planeL = nullptr, *planeR = nullptr, *planeLrep = nullptr;  // padded planes
+  float* stats[2] = {nullptr, nullptr};                           // GF guide statistics (left / right guide)
+  i64 *keysL = nullptr, *keysR = nullptr;                         // packed-min planes
+  u8 *dispA = nullptr, *dispB = nullptr, *dispC = nullptr, *dispD = nullptr, *maskD = nullptr;
+  u8* dispOut = nullptr;                                          // final map of the host path before D2H
+  long long stat_key[2] = {-1, -1};                               // geometry the statistic planes were zeroed for
+  void* export_buf = nullptr;
+  size_t export_bytes = 0;
+  u32* peak_buf = nullptr;
+  size_t plane_bytes_per_frame = 0;
+  size_t stats_floats_per_frame = 0;
+  long long launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;  // (start, stop) pairs of the fused kernels of the last device call
+  size_t ev_used = 0;
+};
+
+static int max_pitch(int cols) { return round_up(PADL_BASE + 16 + cols + PADR, 16); }
+
+static PlaneGeom make_plane_geom(int rows, int cols, int hl) {
+  PlaneGeom pg;
+  pg.H = rows;
+  pg.W = cols;
+  pg.pitch = max_pitch(cols);
+  pg.xoff = PADL_BASE + (hl % 16);  // makes (xoff - hl) a multiple of 16: every run starts 16-byte aligned
+  pg.plane_rows = rows + 2 * PADV;
+  pg.plane_stride = (size_t)pg.pitch * pg.plane_rows;
+  return pg;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* gsm_last_error(void) { return g_err; }
+extern "C" const char* gsm_version(void) { return "gsm-b200 0.1 (sm_100a)"; }
+
+extern "C" void gsm_destroy(gsm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  void* bufs[] = {c->tightL, c->tightR, c->planeL, c->planeR, c->planeLrep, c->stats[0], c->stats[1], c->keysL,
+                  c->keysR,  c->dispA,  c->dispB,  c->dispC,  c->dispD,     c->maskD,    c->export_buf, c->peak_buf, c->dispOut};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols, int max_disp, int max_batch) {
+  if (!out) return fail(GSM_ERR_INVALID, "gsm_create: out is null");
+  *out = nullptr;
+  if (max_rows < 1 || max_cols < 1 || max_disp < 1 || max_disp > MAX_DISP || max_batch < 1)
+    return fail(GSM_ERR_INVALID, "gsm_create: bad capacity rows=%d cols=%d disp=%d batch=%d", max_rows, max_cols,
+                max_disp, max_batch);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(GSM_ERR_CUDA, "gsm_create: no CUDA device (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(GSM_ERR_INVALID, "gsm_create: device %d of %d", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(GSM_ERR_UNSUPPORTED, "gsm_create: device %s is sm_%d%d; this library is built for sm_100a only",
+                prop.name, prop.major, prop.minor);
+  gsm_ctx* c = new gsm_ctx();
+  c->device = device;
+  c->max_rows = max_rows;
+  c->max_cols = max_cols;
+  c->max_disp = max_disp;
+  c->max_batch = max_batch;
+  const size_t px = (size_t)max_rows * max_cols * max_batch;
+  c->plane_bytes_per_frame = (size_t)max_pitch(max_cols) * (max_rows + 2 * PADV);
+  c->stats_floats_per_frame = c->plane_bytes_per_frame;  // one float plane with the image's padded geometry
+  const size_t plane = c->plane_bytes_per_frame * max_batch;
+  cudaError_t st = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) {
+    if (st == cudaSuccess) st = cudaMalloc(p, bytes);
+    if (st == cudaSuccess) st = cudaMemset(*p, 0, bytes);
+  };
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) st = cudaErrorUnknown;
+  A((void**)&c->tightL, px);
+  A((void**)&c->tightR, px);
+  A((void**)&c->planeL, plane);
+  A((void**)&c->planeR, plane);
+  A((void**)&c->planeLrep, plane);
+  A((void**)&c->stats[0], plane * sizeof(float) * GF_STAT_PLANES);
+  A((void**)&c->stats[1], plane * sizeof(float) * GF_STAT_PLANES);
+  A((void**)&c->keysL, px * sizeof(i64));
+  A((void**)&c->keysR, px * sizeof(i64));
+  A((void**)&c->dispA, px);
+  A((void**)&c->dispB, px);
+  A((void**)&c->dispC, px);
+  A((void**)&c->dispD, px);
+  A((void**)&c->maskD, px);
+  A((void**)&c->dispOut, px);
+  A((void**)&c->peak_buf, (size_t)prop.multiProcessorCount * 8 * 256 * sizeof(u32));
+  if (st != cudaSuccess) {
+    int rc = fail(GSM_ERR_CUDA, "gsm_create: allocation failed: %s", cudaGetErrorString(st));
+    gsm_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return GSM_OK;
+}
+
+extern "C" long long gsm_launch_count(const gsm_ctx* c) { return c ? c->launches : 0; }
+extern "C" int gsm_set_kernel_timing(gsm_ctx* c, int enabled) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  c->timing = enabled != 0;
+  return GSM_OK;
+}
+extern "C" float gsm_last_kernel_ms(gsm_ctx* c) {
+  if (!c || c->ev_used == 0) return -1.f;
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    if (cudaEventSynchronize(c->ev[i + 1]) != cudaSuccess) return -1.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]) != cudaSuccess) return -1.f;
+    total += ms;
+  }
+  return total;
+}
+extern "C" int gsm_sync(gsm_ctx* c) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return GSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_params(const gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int* d_begin,
+                        int* d_end, float* eps) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  if (!p) return fail(GSM_ERR_INVALID, "null params");
+  if (rows < 1 || cols < 1 || n < 1) return fail(GSM_ERR_INVALID, "bad shape n=%d rows=%d cols=%d", n, rows, cols);
+  if (rows > c->max_rows || cols > c->max_cols || p->num_disp > c->max_disp ||
+      (size_t)rows * cols > (size_t)c->max_rows * c->max_cols)
+    return fail(GSM_ERR_CAPACITY, "request %dx%d D=%d exceeds context capacity %dx%d D=%d", rows, cols, p->num_disp,
+                c->max_rows, c->max_cols, c->max_disp);
+  if (p->num_disp < 1 || p->num_disp > MAX_DISP) return fail(GSM_ERR_INVALID, "num_disp %d not in 1..256", p->num_disp);
+  if (p->mode == GSM_MODE_SAD) {
+    if (p->radius < 1 || p->radius > 12) return fail(GSM_ERR_INVALID, "SAD radius %d not in 1..12", p->radius);
+    if (p->lr_check) return fail(GSM_ERR_INVALID, "lr_check needs mode GF (the reference defines no right-view SAD)");
+  } else if (p->mode == GSM_MODE_GF) {
+    if (p->radius < 1 || p->radius > 9) return fail(GSM_ERR_INVALID, "GF radius %d not in 1..9", p->radius);
+  } else {
+    return fail(GSM_ERR_INVALID, "mode %d", p->mode);
+  }
+  if (p->median_radius < 0 || p->median_radius > MED_MAXR)
+    return fail(GSM_ERR_INVALID, "median_radius %d not in 0..%d", p->median_radius, MED_MAXR);
+  int b = p->d_begin, e = p->d_end;
+  if (b == 0 && e == 0) e = p->num_disp;
+  if (b < 0 || e > p->num_disp || b >= e) return fail(GSM_ERR_INVALID, "d range [%d,%d) not inside [0,%d)", b, e, p->num_disp);
+  *d_begin = b;
+  *d_end = e;
+  *eps = p->eps > 0.f ? p->eps : 6.5025f;
+  return GSM_OK;
+}
+
+// launch plan of a fused kernel
+struct Plan {
+  FusedGeom g;
+  dim3 grid, block;
+  size_t smem;
+};
+
+static Plan make_plan(const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, int view, int K,
+                      int runs, int stage_halo, int exch_planes, int HL4) {
+  Plan pl;
+  const int hl = round_up(stage_halo, 4);
+  const int TWt = runs * K;
+  int TW = (TWt - hl - stage_halo) / 16 * 16;
+  pl.g.pg = make_plane_geom(rows, cols, hl);
+  pl.g.D = p->num_disp;
+  pl.g.d_begin = d_begin;
+  pl.g.d_end = d_end;
+  pl.g.TW = TW;
+  pl.g.hl = hl;
+  pl.g.runs = runs;
+  int bands = p->row_bands;
+  const int strips = (cols + TW - 1) / TW;
+  const int dchunks = (d_end - d_begin + WARP - 1) / WARP;
+  if (bands <= 0) {
+    // automatic: enough CTAs for ~2 waves of 148 SMs, bands no shorter than 64 rows
+    bands = 1;
+    while ((long long)strips * dchunks * n * bands < 2 * 148 && rows / (bands + 1) >= 64) ++bands;
+  }
+  bands = std::max(1, std::min(bands, rows));
+  pl.g.bands = bands;
+  pl.g.band_rows = (rows + bands - 1) / bands;
+  pl.g.view = view;
+  pl.g.export_ptr = nullptr;
+  pl.g.export_d0 = 0;
+  pl.g.export_nd = 0;
+  pl.grid = dim3(strips, dchunks, n * bands);
+  pl.block = dim3(WARP, runs, 1);
+  pl.smem = (size_t)exch_planes * WARP * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+  return pl;
+}
+
+static int timing_begin(gsm_ctx* c, cudaStream_t s) {
+  if (!c->timing) return GSM_OK;
+  while (c->ev.size() < c->ev_used + 2) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    c->ev.push_back(e);
+  }
+  CK(cudaEventRecord(c->ev[c->ev_used], s));
+  return GSM_OK;
+}
+static int timing_end(gsm_ctx* c, cudaStream_t s) {
+  if (!c->timing) return GSM_OK;
+  CK(cudaEventRecord(c->ev[c->ev_used + 1], s));
+  c->ev_used += 2;
+  return GSM_OK;
+}
+
+#define SAD_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+
+template <bool EXPORT>
+static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, int view,
+                      const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0, int end_) {
+  constexpr int K = 16;
+  const int runs = 13;
+  const int R = p->radius;
+  const int HL4 = (R + 3) / 4 * 4;
+  Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, R, 2, HL4);
+  pl.g.export_ptr = export_ptr;
+  pl.g.export_d0 = ed0;
+  pl.g.export_nd = end_;
+  switch (R) {
+#define X(r)                                                                                                \
+  case r: {                                                                                                 \
+    auto kfn = sad_wta_kernel<r, K, EXPORT>;                                                                \
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));               \
+    kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, keys, pl.g);                                               \
+    break;                                                                                                  \
+  }
+    SAD_CASES(X)
+#undef X
+    default:
+      return fail(GSM_ERR_INVALID, "SAD radius %d", R);
+  }
+  c->launches++;
+  CK(cudaGetLastError());
+  return GSM_OK;
+}
+
+#define GF_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
+
+template <bool EXPORT>
+static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, float eps,
+                     int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
+                     int end_) {
+  constexpr int K = 16;
+  const int runs = 12;
+  const int R = p->radius;
+  const int HL4 = (R + 3) / 4 * 4;
+  Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, 2 * R, 6, HL4);
+  pl.g.export_ptr = export_ptr;
+  pl.g.export_d0 = ed0;
+  pl.g.export_nd = end_;
+  const PlaneGeom& pg = pl.g.pg;
+  float* stats = c->stats[view];
+  // the statistic planes must be zero outside the image: re-zero when the padded geometry changes
+  const long long key = ((long long)rows << 40) ^ ((long long)cols << 20) ^ ((long long)pg.xoff << 8) ^ n;
+  if (c->stat_key[view] != key) {
+    CK(cudaMemsetAsync(stats, 0, (size_t)n * GF_STAT_PLANES * pg.plane_stride * sizeof(float), s));
+    c->stat_key[view] = key;
+  }
+  {
+    const int tw = GS_T + 2 * R;
+    const size_t sm = (size_t)((tw * tw + 3) / 4 + 2 * tw * GS_T) * sizeof(int);
+    gf_stats_kernel<<<dim3((cols + GS_T - 1) / GS_T, (rows + GS_T - 1) / GS_T, n), dim3(GS_T, 8), sm, s>>>(G, stats, pg,
+                                                                                                          R, eps);
+    c->launches++;
+    gf_coef_kernel<<<dim3((cols + 255) / 256, rows + 2 * R + 1, n), 256, 0, s>>>(G, stats, pg, R);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  int rc;
+  if ((rc = timing_begin(c, s))) return rc;
+  switch (R) {
+#define X(r)                                                                                  \
+  case r: {                                                                                   \
+    auto kfn = gf_wta_kernel<r, K, EXPORT>;                                                   \
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                          \
+    break;                                                                                    \
+  }
+    GF_CASES(X)
+#undef X
+    default:
+      return fail(GSM_ERR_INVALID, "GF radius %d", R);
+  }
+  c->launches++;
+  CK(cudaGetLastError());
+  if ((rc = timing_end(c, s))) return rc;
+  return GSM_OK;
+}
+
+static int pack_planes(gsm_ctx* c, const PlaneGeom& pg, int n, const u8* src, u8* dst, int fill, cudaStream_t s) {
+  dim3 block(128);
+  dim3 grid((pg.pitch / 4 + 127) / 128, pg.plane_rows, n);
+  pack_plane_kernel<<<grid, block, 0, s>>>(src, dst, pg, fill);
+  c->launches++;
+  CK(cudaGetLastError());
+  return GSM_OK;
+}
+
+static int fill_keys(gsm_ctx* c, i64* keys, size_t npx, i64 v, cudaStream_t s) {
+  fill_keys_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, s>>>(keys, npx, v);
+  c->launches++;
+  CK(cudaGetLastError());
+  return GSM_OK;
+}
+
+static i64 key_init(const gsm_params* p) {
+  if (p->mode == GSM_MODE_SAD) {
+    const int w = 2 * p->radius + 1;
+    return ((i64)(50 * w * w) << 8);  // BlockMatching.cpp:157-158: min = 50 * dNum, dm = -256 -> (uchar)0
+  }
+  return (i64)0x7fffffffffffff00LL;  // +inf cost, d = 0
+}
+
+static int median_launch(gsm_ctx* c, const u8* src, u8* dst, int n, int rows, int cols, int m, cudaStream_t s) {
+  dim3 grid((cols + MED_TX - 1) / MED_TX, (rows + MED_TY - 1) / MED_TY, n);
+  median_kernel<<<grid, dim3(MED_TX, MED_TY), 0, s>>>(src, dst, rows, cols, m);
+  c->launches++;
+  CK(cudaGetLastError());
+  return GSM_OK;
+}
+
+// Fused aggregation + WTA of one view for a sub-batch that fits the context: tight images -> packed keys.
+static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end,
+                         float eps, int view, const u8* Ltight, const u8* Rtight, i64* keys, cudaStream_t s,
+                         void* export_ptr = nullptr, int ed0 = 0, int end_ = 0) {
+  const size_t npx = (size_t)n * rows * cols;
+  const int stage_halo = p->mode == GSM_MODE_SAD ? p->radius : 2 * p->radius;
+  const PlaneGeom pg = make_plane_geom(rows, cols, round_up(stage_halo, 4));
+  int rc;
+  // guide / other planes.  view 0: guide L, other R (zero pad).  view 1: guide R, other L right-replicated.
+  u8* Gp = view == 0 ? c->planeL : c->planeR;
+  u8* Op = view == 0 ? c->planeR : c->planeLrep;
+  if ((rc = pack_planes(c, pg, n, view == 0 ? Ltight : Rtight, Gp, 0, s))) return rc;
+  if ((rc = pack_planes(c, pg, n, view == 0 ? Rtight : Ltight, Op, view == 0 ? 0 : 1, s))) return rc;
+  if ((rc = fill_keys(c, keys, npx, key_init(p), s))) return rc;
+  if (p->mode == GSM_MODE_SAD) {
+    if ((rc = timing_begin(c, s))) return rc;
+    if (export_ptr)
+      rc = launch_sad<true>(c, p, n, rows, cols, d_begin, d_end, view, Gp, Op, keys, s, export_ptr, ed0, end_);
+    else
+      rc = launch_sad<false>(c, p, n, rows, cols, d_begin, d_end, view, Gp, Op, keys, s, nullptr, 0, 0);
+    if (rc) return rc;
+    if ((rc = timing_end(c, s))) return rc;
+  } else {
+    if (export_ptr)
+      rc = launch_gf<true>(c, p, n, rows, cols, d_begin, d_end, eps, view, Gp, Op, keys, s, export_ptr, ed0, end_);
+    else
+      rc = launch_gf<false>(c, p, n, rows, cols, d_begin, d_end, eps, view, Gp, Op, keys, s, nullptr, 0, 0);
+    if (rc) return rc;
+  }
+  return GSM_OK;
+}
+
+// keys (left [, right]) -> disparity [, mask]; order follows STMatching/StereoDisparity.cpp:115-147:
+// WTA -> median on both views -> LR check.
+static int finalize_views(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, const i64* kL, const i64* kR,
+                          u8* disp_out, u8* mask_out, cudaStream_t s) {
+  const size_t npx = (size_t)n * rows * cols;
+  const unsigned gb = (unsigned)((npx + 255) / 256);
+  int rc;
+  const bool lr = p->lr_check && kR;
+  const int m = p->median_radius;
+  u8* dl = (m > 0 || lr) ? c->dispA : disp_out;
+  finalize_keys_kernel<<<gb, 256, 0, s>>>(kL, dl, npx);
+  c->launches++;
+  if (m > 0) {
+    u8* dst = lr ? c->dispB : disp_out;
+    if ((rc = median_launch(c, dl, dst, n, rows, cols, m, s))) return rc;
+    dl = dst;
+  }
+  if (lr) {
+    u8* dr = c->dispC;
+    finalize_keys_kernel<<<gb, 256, 0, s>>>(kR, dr, npx);
+    c->launches++;
+    if (m > 0) {
+      if ((rc = median_launch(c, dr, c->dispD, n, rows, cols, m, s))) return rc;
+      dr = c->dispD;
+    }
+    dim3 grid((cols + 255) / 256, rows, n);
+    lr_check_kernel<<<grid, 256, 0, s>>>(dl, dr, nullptr, mask_out, disp_out, rows, cols, n);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  return GSM_OK;
+}
+
+extern "C" int gsm_stereo_device(gsm_ctx* c, const gsm_params* p, int n, const void* left_dev, const void* right_dev,
+                                 void* disparity_dev, void* mask_dev, int rows, int cols, void* stream) {
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, n, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!left_dev || !right_dev || !disparity_dev) return fail(GSM_ERR_INVALID, "null image pointer");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  c->ev_used = 0;
+  const size_t fpx = (size_t)rows * cols;
+  for (int f0 = 0; f0 < n; f0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, n - f0);
+    const u8* L = (const u8*)left_dev + f0 * fpx;
+    const u8* R = (const u8*)right_dev + f0 * fpx;
+    if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 0, L, R, c->keysL, s))) return rc;
+    if (p->lr_check)
+      if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 1, L, R, c->keysR, s))) return rc;
+    if ((rc = finalize_views(c, p, nb, rows, cols, c->keysL, p->lr_check ? c->keysR : nullptr,
+                             (u8*)disparity_dev + f0 * fpx, mask_dev ? (u8*)mask_dev + f0 * fpx : nullptr, s)))
+      return rc;
+  }
+  return GSM_OK;
+}
+
+extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
+                                uint8_t* disparity, uint8_t* mask, int rows, int cols) {
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, n, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!left || !right || !disparity) return fail(GSM_ERR_INVALID, "null image pointer");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const size_t fpx = (size_t)rows * cols;
+  for (int f0 = 0; f0 < n; f0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, n - f0);
+    CK(cudaMemcpyAsync(c->tightL, left + f0 * fpx, nb * fpx, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->tightR, right + f0 * fpx, nb * fpx, cudaMemcpyHostToDevice, s));
+    u8* dres = c->dispOut;
+    if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 0, c->tightL, c->tightR, c->keysL, s))) return rc;
+    if (p->lr_check)
+      if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 1, c->tightL, c->tightR, c->keysR, s)))
+        return rc;
+    if ((rc = finalize_views(c, p, nb, rows, cols, c->keysL, p->lr_check ? c->keysR : nullptr, dres,
+                             (mask && p->lr_check) ? c->maskD : nullptr, s)))
+      return rc;
+    CK(cudaMemcpyAsync(disparity + f0 * fpx, dres, nb * fpx, cudaMemcpyDeviceToHost, s));
+    if (mask && p->lr_check) CK(cudaMemcpyAsync(mask + f0 * fpx, c->maskD, nb * fpx, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_block_matching(gsm_ctx* c, const uint8_t* left, const uint8_t* right, uint8_t* disparity, int rows,
+                                  int cols, int radius, int num_disp) {
+  gsm_params p;
+  memset(&p, 0, sizeof(p));
+  p.mode = GSM_MODE_SAD;
+  p.radius = radius;
+  p.num_disp = num_disp;
+  return gsm_stereo_batch(c, &p, 1, left, right, disparity, nullptr, rows, cols);
+}
+
+extern "C" int gsm_partial_keys_device(gsm_ctx* c, const gsm_params* p, int view, const void* left_dev,
+                                       const void* right_dev, void* keys_dev, int rows, int cols, void* stream) {
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!left_dev || !right_dev || !keys_dev) return fail(GSM_ERR_INVALID, "null pointer");
+  if (view != 0 && view != 1) return fail(GSM_ERR_INVALID, "view %d", view);
+  if (view == 1 && p->mode != GSM_MODE_GF) return fail(GSM_ERR_INVALID, "right view needs mode GF");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  c->ev_used = 0;
+  return run_view_keys(c, p, 1, rows, cols, d_begin, d_end, eps, view, (const u8*)left_dev, (const u8*)right_dev,
+                       (i64*)keys_dev, s);
+}
+
+extern "C" int gsm_finalize_keys_device(gsm_ctx* c, const gsm_params* p, const void* keys_left_dev,
+                                        const void* keys_right_dev, void* disparity_dev, void* mask_dev, int rows,
+                                        int cols, void* stream) {
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!keys_left_dev || !disparity_dev) return fail(GSM_ERR_INVALID, "null pointer");
+  if (p->lr_check && !keys_right_dev) return fail(GSM_ERR_INVALID, "lr_check needs right-view keys");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  return finalize_views(c, p, 1, rows, cols, (const i64*)keys_left_dev, (const i64*)keys_right_dev, (u8*)disparity_dev,
+                        (u8*)mask_dev, s);
+}
+
+// ---- cost-stage exports ------------------------------------------------------------------------
+static int ensure_export(gsm_ctx* c, size_t bytes) {
+  if (c->export_bytes >= bytes) return GSM_OK;
+  if (c->export_buf) cudaFree(c->export_buf);
+  c->export_buf = nullptr;
+  c->export_bytes = 0;
+  CK(cudaMalloc(&c->export_buf, bytes));
+  c->export_bytes = bytes;
+  return GSM_OK;
+}
+
+extern "C" int gsm_ad_volume(gsm_ctx* c, const uint8_t* left, const uint8_t* right, uint8_t* volume, int rows,
+                             int cols, int num_disp) {
+  gsm_params p;
+  memset(&p, 0, sizeof(p));
+  p.mode = GSM_MODE_SAD;
+  p.radius = 1;
+  p.num_disp = num_disp;
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, &p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!left || !right || !volume) return fail(GSM_ERR_INVALID, "null pointer");
+  CK(cudaSetDevice(c->device));
+  const size_t fpx = (size_t)rows * cols;
+  if ((rc = ensure_export(c, fpx * num_disp))) return rc;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(c->tightL, left, fpx, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->tightR, right, fpx, cudaMemcpyHostToDevice, s));
+  ad_volume_kernel<<<dim3((cols + 255) / 256, rows, num_disp), 256, 0, s>>>(c->tightL, c->tightR, (u8*)c->export_buf,
+                                                                              rows, cols);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(volume, c->export_buf, fpx * num_disp, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_cost_slices(gsm_ctx* c, const gsm_params* p, int view, const uint8_t* left, const uint8_t* right,
+                               int d0, int nd, void* out, int rows, int cols) {
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!left || !right || !out) return fail(GSM_ERR_INVALID, "null pointer");
+  if (d0 < 0 || nd < 1 || d0 + nd > p->num_disp) return fail(GSM_ERR_INVALID, "slice range [%d,%d)", d0, d0 + nd);
+  if (view != 0 && view != 1) return fail(GSM_ERR_INVALID, "view %d", view);
+  CK(cudaSetDevice(c->device));
+  const size_t fpx = (size_t)rows * cols;
+  const size_t bytes = fpx * nd * 4;
+  if ((rc = ensure_export(c, bytes))) return rc;
+  cudaStream_t s = c->stream;
+  CK(cudaMemsetAsync(c->export_buf, 0, bytes, s));
+  CK(cudaMemcpyAsync(c->tightL, left, fpx, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->tightR, right, fpx, cudaMemcpyHostToDevice, s));
+  // evaluate only the 32-disparity chunks that cover [d0, d0+nd)
+  const int cb = d0 / WARP * WARP;
+  const int ce = std::min(p->num_disp, round_up(d0 + nd, WARP));
+  if ((rc = run_view_keys(c, p, 1, rows, cols, cb, ce, eps, view, c->tightL, c->tightR, c->keysL, s, c->export_buf, d0, nd)))
+    return rc;
+  CK(cudaMemcpyAsync(out, c->export_buf, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_all_sad(gsm_ctx* c, const uint8_t* left, const uint8_t* right, uint8_t* out, int rows, int cols,
+                           int radius, int num_disp) {
+  gsm_params p;
+  memset(&p, 0, sizeof(p));
+  p.mode = GSM_MODE_SAD;
+  p.radius = radius;
+  p.num_disp = num_disp;
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, &p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!left || !right || !out) return fail(GSM_ERR_INVALID, "null pointer");
+  CK(cudaSetDevice(c->device));
+  const size_t fpx = (size_t)rows * cols;
+  const size_t slice_bytes = fpx * num_disp * 4;
+  if ((rc = ensure_export(c, slice_bytes + fpx * num_disp))) return rc;
+  cudaStream_t s = c->stream;
+  u8* packed = (u8*)c->export_buf + slice_bytes;
+  CK(cudaMemsetAsync(c->export_buf, 0, slice_bytes, s));
+  CK(cudaMemcpyAsync(c->tightL, left, fpx, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->tightR, right, fpx, cudaMemcpyHostToDevice, s));
+  if ((rc = run_view_keys(c, &p, 1, rows, cols, 0, num_disp, eps, 0, c->tightL, c->tightR, c->keysL, s, c->export_buf, 0,
+                          num_disp)))
+    return rc;
+  all_sad_pack_kernel<<<dim3((cols + 255) / 256, rows, num_disp), 256, 0, s>>>((const int*)c->export_buf, packed, rows,
+                                                                                 cols, num_disp, 0, num_disp);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, packed, fpx * num_disp, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+// ---- post-filters as stand-alone calls -----------------------------------------------------------
+extern "C" int gsm_median(gsm_ctx* c, const uint8_t* src, uint8_t* dst, int rows, int cols, int radius) {
+  if (!c || !src || !dst) return fail(GSM_ERR_INVALID, "null pointer");
+  if (rows < 1 || cols < 1 || rows > c->max_rows || cols > c->max_cols) return fail(GSM_ERR_CAPACITY, "shape %dx%d", rows, cols);
+  if (radius < 0 || radius > MED_MAXR) return fail(GSM_ERR_INVALID, "median radius %d", radius);
+  CK(cudaSetDevice(c->device));
+  const size_t fpx = (size_t)rows * cols;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(c->dispA, src, fpx, cudaMemcpyHostToDevice, s));
+  int rc;
+  if ((rc = median_launch(c, c->dispA, c->dispB, 1, rows, cols, radius, s))) return rc;
+  CK(cudaMemcpyAsync(dst, c->dispB, fpx, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_lr_check(gsm_ctx* c, const uint8_t* dl, const uint8_t* dr, uint8_t* occ, uint8_t* mask, int rows,
+                            int cols) {
+  if (!c || !dl || !dr) return fail(GSM_ERR_INVALID, "null pointer");
+  if (rows < 1 || cols < 1 || rows > c->max_rows || cols > c->max_cols) return fail(GSM_ERR_CAPACITY, "shape %dx%d", rows, cols);
+  CK(cudaSetDevice(c->device));
+  const size_t fpx = (size_t)rows * cols;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(c->dispA, dl, fpx, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->dispB, dr, fpx, cudaMemcpyHostToDevice, s));
+  lr_check_kernel<<<dim3((cols + 255) / 256, rows, 1), 256, 0, s>>>(c->dispA, c->dispB, c->dispC, c->maskD, nullptr, rows,
+                                                                      cols, 1);
+  c->launches++;
+  CK(cudaGetLastError());
+  if (occ) CK(cudaMemcpyAsync(occ, c->dispC, fpx, cudaMemcpyDeviceToHost, s));
+  if (mask) CK(cudaMemcpyAsync(mask, c->maskD, fpx, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_measure_alu_peak(gsm_ctx* c, double* lane_ops_per_s) {
+  if (!c || !lane_ops_per_s) return fail(GSM_ERR_INVALID, "null pointer");
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  const int grid = prop.multiProcessorCount * 8, iters = 8192;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(e0, c->stream));
+    alu_peak_kernel<<<grid, 256, 0, c->stream>>>(c->peak_buf, iters);
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *lane_ops_per_s = (double)grid * 256 * iters * 8 * 2 / (best * 1e-3);
+  return GSM_OK;
+}

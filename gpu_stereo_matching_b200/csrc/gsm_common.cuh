@@ -1,0 +1,91 @@
+// gsm_common.cuh -- geometry, padded-plane layout and small device helpers shared by all kernels.
+//
+// HBM layout ("padded plane"): every u8 image the fused kernels read lives in a plane of
+//   plane_rows = H + 2*PADV rows x pitch bytes,  image pixel (y, x) at  (PADV + y) * pitch + xoff + x.
+// The pad is zero (or right-replicated for the right-view "other" image), pitch and xoff are chosen so
+// that every thread's run of K columns starts 16-byte aligned: one LDG.128 per guide row per thread.
+// Zero pad rows/cols make out-of-image absolute differences vanish without per-row predicates.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gsm {
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef long long i64;
+
+constexpr int PADV = 24;        // zero rows above and below the image
+constexpr int PADL_BASE = 320;  // >= max left halo (24) + max disparity (256) + word over-read
+constexpr int PADR = 544;       // >= strip width (<=256) + max disparity (256) + slack
+constexpr int MAX_DISP = 256;
+constexpr int WARP = 32;
+
+struct PlaneGeom {
+  int H, W;            // image size
+  int pitch;           // bytes per padded row (multiple of 16)
+  int xoff;            // byte offset of image column 0 inside a padded row
+  int plane_rows;      // H + 2*PADV
+  size_t plane_stride; // bytes per frame
+};
+
+// One launch of a fused aggregation+WTA kernel.
+struct FusedGeom {
+  PlaneGeom pg;
+  int D;          // total disparities (for validity)
+  int d_begin;    // first disparity evaluated by blockIdx.y == 0
+  int d_end;      // one past the last disparity evaluated
+  int TW;         // output columns per strip (multiple of 16)
+  int hl;         // left halo of a strip (multiple of 4, >= stage halo)
+  int runs;       // == blockDim.y
+  int bands;      // row bands per frame
+  int band_rows;  // rows per band
+  int view;       // 0: left (guide L, other R at x-d, zero for x<d); 1: right (guide R, other Lrep at x+d)
+  // debug export of aggregated cost slices (nullptr = off)
+  void* export_ptr;
+  int export_d0, export_nd;
+};
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// float -> int32 whose SIGNED order equals the float order (no NaNs on this path)
+__device__ __forceinline__ int sortable_i32(float f) {
+  int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float unsortable_f32(int s) {
+  return __int_as_float(s ^ ((s >> 31) & 0x7fffffff));
+}
+
+// K bytes from a 16/8-byte aligned address
+template <int K>
+__device__ __forceinline__ void load_aligned(const u8* p, u32 (&w)[K / 4]) {
+  if constexpr (K == 16) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+  } else {
+    static_assert(K == 8, "K must be 8 or 16");
+    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    w[0] = v.x; w[1] = v.y;
+  }
+}
+
+// K bytes from an arbitrary byte address: pa = address rounded down to 4, sel = PRMT selector for the
+// byte misalignment (0x3210 + 0x1111 * (addr & 3)); the misalignment is row-independent (pitch % 16 == 0).
+template <int K>
+__device__ __forceinline__ void load_unaligned(const u32* pa, u32 sel, u32 (&w)[K / 4]) {
+  u32 t[K / 4 + 1];
+#pragma unroll
+  for (int i = 0; i <= K / 4; ++i) t[i] = __ldg(pa + i);
+#pragma unroll
+  for (int i = 0; i < K / 4; ++i) w[i] = __byte_perm(t[i], t[i + 1], sel);
+}
+
+// acc + a.lo16 * b.byte0 + a.hi16 * b.byte1   (IDP.2A, signed 16-bit x unsigned 8-bit)
+__device__ __forceinline__ int dp2a_lo_su(int a16x2, u32 b8x4, int acc) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a16x2), "r"(b8x4), "r"(acc));
+  return d;
+}
+
+}  // namespace gsm

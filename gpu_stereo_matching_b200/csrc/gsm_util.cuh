@@ -1,0 +1,146 @@
+// gsm_util.cuh -- the small per-pixel kernels around the fused aggregation kernels:
+// plane packing, packed-min plane init / finalize, LR check, median, debug exports.
+#pragma once
+#include "gsm_common.cuh"
+
+namespace gsm {
+
+// tight [n][H][W] u8  ->  padded plane (see gsm_common.cuh).  fill 0: zero pad everywhere;
+// fill 1: columns >= W of image rows replicate src[y][W-1] (right-view "other" image,
+// STMatching/StereoHelper.cpp:170-176: x+d >= W falls back to the last valid disparity).
+__global__ void pack_plane_kernel(const u8* __restrict__ src, u8* __restrict__ dst, PlaneGeom pg, int fill) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;  // 4-byte group within a padded row
+  const int prow = blockIdx.y;
+  const int frame = blockIdx.z;
+  if (q * 4 >= pg.pitch) return;
+  const int y = prow - PADV;
+  u32 v = 0;
+  if (y >= 0 && y < pg.H) {
+    const u8* s = src + ((size_t)frame * pg.H + y) * pg.W;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int x = q * 4 + b - pg.xoff;
+      u32 px = 0;
+      if (x >= 0 && x < pg.W) px = s[x];
+      else if (fill == 1 && x >= pg.W) px = s[pg.W - 1];
+      v |= px << (8 * b);
+    }
+  }
+  reinterpret_cast<u32*>(dst + (size_t)frame * pg.plane_stride + (size_t)prow * pg.pitch)[q] = v;
+}
+
+__global__ void fill_keys_kernel(i64* __restrict__ keys, size_t n, i64 v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = v;
+}
+
+// packed (cost, d) word -> u8 disparity.  Both key formats keep d in the low byte.
+__global__ void finalize_keys_kernel(const i64* __restrict__ keys, u8* __restrict__ disp, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) disp[i] = (u8)(keys[i] & 0xff);
+}
+
+// STMatching/StereoDisparity.cpp:136-147.  out_disp (optional) = DL with occluded pixels zeroed.
+__global__ void lr_check_kernel(const u8* __restrict__ DL, const u8* __restrict__ DR, u8* __restrict__ occ,
+                                u8* __restrict__ mask, u8* __restrict__ out_disp, int H, int W, int n) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int f = blockIdx.z;
+  if (x >= W) return;
+  const size_t i = ((size_t)f * H + y) * W + x;
+  const int d = DL[i];
+  u8 o;
+  if (x - d >= 0) {
+    const int dc = DR[i - d];
+    o = (u8)(d == 0 || abs(d - dc) > 1);
+  } else {
+    o = 1;
+  }
+  if (occ) occ[i] = o;
+  if (mask) mask[i] = (u8)!o;
+  if (out_disp) out_disp[i] = o ? 0 : (u8)d;
+}
+
+// (2m+1)^2 median, replicate border: smallest v whose cumulative count exceeds t = 2m^2+2m
+// (STMatching/ctmf.c:281,288-294,319-325).  One pixel per thread, binary search on the value,
+// neighbourhood served from a shared-memory tile.
+constexpr int MED_TX = 32, MED_TY = 16, MED_MAXR = 7;
+__global__ void __launch_bounds__(MED_TX* MED_TY)
+median_kernel(const u8* __restrict__ src, u8* __restrict__ dst, int H, int W, int m) {
+  __shared__ u8 tile[(MED_TY + 2 * MED_MAXR) * (MED_TX + 2 * MED_MAXR)];
+  const int f = blockIdx.z;
+  const int bx = blockIdx.x * MED_TX, by = blockIdx.y * MED_TY;
+  const int tw = MED_TX + 2 * m, th = MED_TY + 2 * m;
+  const u8* s = src + (size_t)f * H * W;
+  for (int i = threadIdx.y * MED_TX + threadIdx.x; i < tw * th; i += MED_TX * MED_TY) {
+    const int ty = i / tw, tx = i - ty * tw;
+    const int yy = min(H - 1, max(0, by + ty - m));
+    const int xx = min(W - 1, max(0, bx + tx - m));
+    tile[ty * tw + tx] = s[(size_t)yy * W + xx];
+  }
+  __syncthreads();
+  const int x = bx + threadIdx.x, y = by + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int t = 2 * m * m + 2 * m;
+  int lo = 0, hi = 255;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    int cnt = 0;
+    for (int dy = 0; dy <= 2 * m; ++dy) {
+      const u8* row = tile + (threadIdx.y + dy) * tw + threadIdx.x;
+      for (int dx = 0; dx <= 2 * m; ++dx) cnt += (row[dx] <= mid);
+    }
+    if (cnt > t) hi = mid; else lo = mid + 1;
+  }
+  dst[((size_t)f * H + y) * W + x] = (u8)lo;
+}
+
+// PreCal, BlockMatching/BlockMatching.cpp:89-109 (== kernalPreCal_V2, Device.cu:19-32): debug export only,
+// the production path never materialises this volume.
+__global__ void ad_volume_kernel(const u8* __restrict__ L, const u8* __restrict__ R, u8* __restrict__ out, int H,
+                                 int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int d = blockIdx.z;
+  if (x >= W) return;
+  const size_t i = (size_t)y * W + x;
+  u8 v = 0;
+  if (x - d >= 0) v = (u8)abs((int)L[i] - (int)R[i - d]);
+  out[(size_t)d * H * W + i] = v;
+}
+
+// int32 SAD slices [nd][H][W] -> getAllSAD layout u8 [H*W][D] (BlockMatching.cpp:244-258)
+__global__ void all_sad_pack_kernel(const int* __restrict__ slices, u8* __restrict__ out, int H, int W, int D,
+                                    int d0, int nd) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int k = blockIdx.z;
+  if (x >= W || k >= nd) return;
+  const int d = d0 + k;
+  const size_t i = (size_t)y * W + x;
+  out[i * D + d] = (x + d > W) ? (u8)255 : (u8)slices[(size_t)k * H * W + i];
+}
+
+// FFMA + IADD3 issue-peak probe (roofline denominator for the ALU-bound fused kernels)
+__global__ void __launch_bounds__(256) alu_peak_kernel(u32* out, int iters) {
+  float f[8];
+  u32 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { f[i] = 1.0f + threadIdx.x * 1e-3f + i; a[i] = threadIdx.x * (i + 3) + 1u; }
+  const float fb = 1.000001f;
+  const u32 c = blockIdx.x + 7u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = (i + 1) & 7;
+      f[i] = fmaf(f[i], fb, f[j]);
+      a[i] = a[i] + a[j] + c;
+    }
+  }
+  u32 r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += a[i] + __float_as_uint(f[i]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+}  // namespace gsm

@@ -1,0 +1,140 @@
+/*
+ * gsm.h -- C ABI of libgsm.so: the B200-native (sm_100a) BlockMatching hot path.
+ *
+ * Drop-in boundary for ningw42/GPU_Stereo_Matching's GPU "proxy" functions
+ * (reference: BlockMatching/Device.cuh:50-52, implemented in BlockMatching/Device.cu:173-367)
+ * and the CPU functions they are checked against (BlockMatching/BlockMatching.h:8-15).
+ * Plain pointers and sizes only; no OpenCV, no torch types.  include/gsm_compat.hpp layers the
+ * reference's exact C++ signatures (cv::Mat&) on top of this file.
+ *
+ * Conventions
+ *   - images: uint8, row-major, contiguous, rows x cols  (reference: raw .data memcpy of
+ *     rows*cols bytes, Device.cu:213-214).
+ *   - radius  == the reference's `SADWindowSize` / `SAD` argument: window = 2*radius+1
+ *     (Device.cu:181, BlockMatching.cpp:119).
+ *   - num_disp == the reference's `searchRange`: disparities d in [0, num_disp), <= 256
+ *     (u8 output, BlockMatching.cpp:184).
+ *   - every entry point returns 0 on success, a negative gsm_status otherwise;
+ *     gsm_last_error() returns a thread-local description.  (The reference ignores every
+ *     CUDA status; this ABI never does.)
+ *   - a gsm_ctx owns all device memory, streams and pinned staging for ONE GPU and is used by
+ *     one host thread at a time.  Nothing is allocated per call once the context is warm
+ *     (reference: 6 cudaMalloc per call, never freed, Device.cu:187-194).
+ *   - There is NO CPU fallback: without a CUDA device every call fails with GSM_ERR_CUDA.
+ */
+#ifndef GSM_H
+#define GSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsm_ctx gsm_ctx;
+
+typedef enum {
+  GSM_OK = 0,
+  GSM_ERR_INVALID = -1,  /* bad argument (size, radius, num_disp, null pointer) */
+  GSM_ERR_CUDA = -2,     /* CUDA runtime error (message in gsm_last_error) */
+  GSM_ERR_CAPACITY = -3, /* request exceeds what the context was created for */
+  GSM_ERR_UNSUPPORTED = -4
+} gsm_status;
+
+typedef enum {
+  GSM_MODE_SAD = 0, /* clipped-window SAD + WTA with the reference quirks: bit-exact to getDisp,
+                       BlockMatching.cpp:111-189 / kernalFindCorr, Device.cu:34-64 */
+  GSM_MODE_GF = 1   /* guided-filter aggregation (north_star; no reference implementation) + WTA over
+                       all d, strict '<' (STMatching/StereoHelper.cpp:131-154) */
+} gsm_mode;
+
+/* Parameters of one stereo pass.  Zero-initialise, then set what you need. */
+typedef struct gsm_params {
+  int mode;          /* gsm_mode */
+  int radius;        /* window radius r: SAD 1..12, GF 1..9 */
+  int num_disp;      /* D, 1..256 */
+  float eps;         /* GF regulariser on the 0..255 intensity scale; <= 0 selects 6.5025 (= 1e-4 * 255^2) */
+  int lr_check;      /* GF only: also aggregate the right view (STMatching/StereoHelper.cpp:156-180) and
+                        apply the left-right consistency check (STMatching/StereoDisparity.cpp:128-147):
+                        occluded pixels -> disparity 0, mask = !occ */
+  int median_radius; /* > 0: (2m+1)^2 median, replicate border (STMatching/ctmf.c:378-433, applied like
+                        StereoDisparity.cpp:119,126 to both views before the LR check) */
+  int row_bands;     /* >= 1: split every frame into this many independent row bands (more CTAs for
+                        single-frame latency); 0 = automatic */
+  int d_begin;       /* disparity sub-range [d_begin, d_end) evaluated by this call; 0/0 = all.  Used by the */
+  int d_end;         /* multi-GPU disparity split: partial results combine through the packed-min plane. */
+} gsm_params;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Replaces the per-call cudaMalloc block of blockMatching_gpu (Device.cu:184-194). */
+int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols, int max_disp, int max_batch);
+void gsm_destroy(gsm_ctx* ctx);
+const char* gsm_last_error(void);
+const char* gsm_version(void);
+
+/* ---- the reference entry point -------------------------------------------------------------- */
+/* == blockMatching_gpu(h_left, h_right, h_disparity, SADWindowSize, searchRange), Device.cuh:50 /
+ *    Device.cu:173-301, and bit-exact to getDisp, BlockMatching.cpp:111-189.  HOST pointers;
+ *    blocking (upload, kernels, download), like the reference. */
+int gsm_block_matching(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, uint8_t* disparity,
+                       int rows, int cols, int radius, int num_disp);
+
+/* ---- full path, host buffers (the e2e path) ------------------------------------------------- */
+/* n frames of identical size, frame i at left + i*rows*cols.  mask may be NULL (written only with
+ * lr_check).  Pipelined internally: pinned staging, H2D / kernels / D2H overlapped across frames. */
+int gsm_stereo_batch(gsm_ctx* ctx, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
+                     uint8_t* disparity, uint8_t* mask, int rows, int cols);
+
+/* ---- full path, device-resident buffers ----------------------------------------------------- */
+/* Same computation on DEVICE pointers (tightly packed n x rows x cols), enqueued on `stream`
+ * (a cudaStream_t; NULL = the context's own stream).  Asynchronous: returns after enqueueing. */
+int gsm_stereo_device(gsm_ctx* ctx, const gsm_params* p, int n, const void* left_dev, const void* right_dev,
+                      void* disparity_dev, void* mask_dev, int rows, int cols, void* stream);
+int gsm_sync(gsm_ctx* ctx);
+
+/* ---- multi-GPU disparity split -------------------------------------------------- */
+/* Evaluate only d in [p->d_begin, p->d_end) for ONE frame and leave the per-pixel packed minimum in
+ * keys_dev (int64[rows*cols], device).  Packed word: SAD  (int64)((SAD << 8) | d);
+ * GF  ((int64)sortable_int32(q) << 32) | d  -- both order like (cost, d) under a SIGNED 64-bit min,
+ * so ranks combine with ncclAllReduce(ncclInt64, ncclMin) / torch.distributed ReduceOp.MIN and ties
+ * resolve to the lowest d exactly like the reference's strict '<' (BlockMatching.cpp:178).
+ * view: 0 = left disparity, 1 = right-view disparity (for the LR check). */
+int gsm_partial_keys_device(gsm_ctx* ctx, const gsm_params* p, int view, const void* left_dev,
+                            const void* right_dev, void* keys_dev, int rows, int cols, void* stream);
+/* keys -> u8 disparity (+ optional median / LR check against keys_right_dev, may be NULL). */
+int gsm_finalize_keys_device(gsm_ctx* ctx, const gsm_params* p, const void* keys_left_dev,
+                             const void* keys_right_dev, void* disparity_dev, void* mask_dev, int rows,
+                             int cols, void* stream);
+
+/* ---- cost-stage exports (keep the reference's compareDiff / compareSAD checks possible) ------ */
+/* AD volume u8 [D][rows][cols] == PreCal, BlockMatching.cpp:89-109 (what compareDiff :263-276 checks). */
+int gsm_ad_volume(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, uint8_t* volume, int rows, int cols,
+                  int num_disp);
+/* Aggregated cost slices for d in [d0, d0+nd): SAD mode -> int32 un-truncated SAD [nd][rows][cols];
+ * GF mode -> float32 q_d [nd][rows][cols].  Produced by the SAME fused kernel as the WTA path. view as above. */
+int gsm_cost_slices(gsm_ctx* ctx, const gsm_params* p, int view, const uint8_t* left, const uint8_t* right,
+                    int d0, int nd, void* out, int rows, int cols);
+/* getAllSAD layout: u8 [rows*cols][D], truncated, 255 where col+d > cols (BlockMatching.cpp:191-261). */
+int gsm_all_sad(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, uint8_t* out, int rows, int cols,
+                int radius, int num_disp);
+
+/* ---- post-filters as stand-alone calls ------------------------------------------------------ */
+int gsm_median(gsm_ctx* ctx, const uint8_t* src, uint8_t* dst, int rows, int cols, int radius);
+int gsm_lr_check(gsm_ctx* ctx, const uint8_t* disp_left, const uint8_t* disp_right, uint8_t* occ,
+                 uint8_t* mask, int rows, int cols);
+
+/* ---- introspection for benches -------------------------------------------------------------- */
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+long long gsm_launch_count(const gsm_ctx* ctx);
+/* Device time (ms, CUDA events on the launching stream) of the fused aggregation+WTA kernel(s) of the
+ * most recent gsm_stereo_device call with timing enabled; < 0 if none. */
+int gsm_set_kernel_timing(gsm_ctx* ctx, int enabled);
+float gsm_last_kernel_ms(gsm_ctx* ctx);
+/* FP32/INT issue-peak microbenchmark (FFMA + IADD3 mix): lane-ops per second on this device. */
+int gsm_measure_alu_peak(gsm_ctx* ctx, double* lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSM_H */

@@ -1,0 +1,254 @@
+"""ctypes front-end to the oracle libraries (TEST INFRASTRUCTURE ONLY).
+
+  liboracle.so    -- our plain-C restatement, oracle/stereo_oracle.c (always available after
+                     `make -C oracle`)
+  _ref/libref.so  -- the reference's own BlockMatching.cpp + ctmf.c compiled UNMODIFIED from
+                     /root/reference (built in the dev container, travels as a prebuilt .so)
+
+Every wrapper cites the reference file:line its C counterpart follows (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def build(verbose: bool = False) -> None:
+    """make -C oracle (liboracle.so always; _ref/libref.so when /root/reference exists)."""
+    out = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+
+
+_lib = None
+_ref = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_ad_slice.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_ad_volume.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_sad_slice.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p]
+        L.orc_sad_wta_direct.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_sad_wta.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_void_p]
+        L.orc_all_sad.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_gf_cost_slices.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                         C.c_int, C.c_int, _f64p]
+        L.orc_gf_wta.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                 _u8p, C.c_void_p]
+        L.orc_lr_check.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _u8p, _u8p]
+        L.orc_median.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int]
+        L.orc_fnv1a64.argtypes = [_u8p, C.c_size_t]
+        L.orc_fnv1a64.restype = C.c_uint64
+        for f in ("orc_ad_slice", "orc_ad_volume", "orc_sad_slice", "orc_sad_wta_direct", "orc_sad_wta",
+                  "orc_all_sad", "orc_gf_cost_slices", "orc_gf_wta", "orc_lr_check", "orc_median"):
+            getattr(L, f).restype = None
+        _lib = L
+    return _lib
+
+
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref.so"))
+
+
+def ref() -> C.CDLL:
+    """The reference's own CPU code, compiled unmodified (oracle/Makefile target _ref/libref.so)."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libref.so")
+        if not os.path.exists(path):
+            build()
+        R = C.CDLL(path)
+        for f in ("ref_PreCal", "ref_getDisp", "ref_getAllSAD"):
+            getattr(R, f).argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+            getattr(R, f).restype = None
+        R.ref_compareDisp.argtypes = [_u8p, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+        R.ref_compareDisp.restype = None
+        R.ref_median.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int]
+        R.ref_median.restype = None
+        _ref = R
+    return _ref
+
+
+@contextlib.contextmanager
+def quiet_stdout():
+    """The reference prints phase timings with cout (BlockMatching.cpp:136,153,188); silence fd 1."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        yield
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+def _u8(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 2
+    return a
+
+
+# ----------------------------------------------------------------------------- restatement
+def ad_slice(L, R, d: int, view: int = 0) -> np.ndarray:
+    """A.1: BlockMatching.cpp:101-108 (view 0); StereoHelper.cpp:156-180 (view 1)."""
+    L, R = _u8(L), _u8(R)
+    out = np.empty_like(L)
+    lib().orc_ad_slice(L, R, L.shape[0], L.shape[1], d, view, out)
+    return out
+
+
+def ad_volume(L, R, D: int) -> np.ndarray:
+    """PreCal, BlockMatching.cpp:89-109 -> u8 [D][H][W]."""
+    L, R = _u8(L), _u8(R)
+    out = np.empty((D,) + L.shape, np.uint8)
+    lib().orc_ad_volume(L, R, L.shape[0], L.shape[1], D, out)
+    return out
+
+
+def sad_slice(L, R, r: int, d: int, view: int = 0) -> np.ndarray:
+    """Un-truncated clipped-window SAD (BlockMatching.cpp:167-177) -> int32 [H][W]."""
+    L, R = _u8(L), _u8(R)
+    out = np.empty(L.shape, np.int32)
+    lib().orc_sad_slice(L, R, L.shape[0], L.shape[1], r, d, view, out)
+    return out
+
+
+def sad_wta(L, R, r: int, D: int, direct: bool = False, return_cost: bool = False):
+    """getDisp, BlockMatching.cpp:111-189 (A.2)."""
+    L, R = _u8(L), _u8(R)
+    out = np.empty_like(L)
+    if direct:
+        lib().orc_sad_wta_direct(L, R, L.shape[0], L.shape[1], r, D, out)
+        return out
+    cost = np.empty(L.shape, np.int32) if return_cost else None
+    lib().orc_sad_wta(L, R, L.shape[0], L.shape[1], r, D, out,
+                      cost.ctypes.data_as(C.c_void_p) if return_cost else None)
+    return (out, cost) if return_cost else out
+
+
+def all_sad(L, R, r: int, D: int) -> np.ndarray:
+    """getAllSAD, BlockMatching.cpp:191-261 -> u8 [H*W][D] (truncated, 255 where x+d > W)."""
+    L, R = _u8(L), _u8(R)
+    out = np.empty((L.size, D), np.uint8)
+    lib().orc_all_sad(L, R, L.shape[0], L.shape[1], r, D, out)
+    return out
+
+
+GF_EPS_DEFAULT = 1e-4 * 255.0 * 255.0  # 6.5025
+
+
+def gf_cost_slices(L, R, r: int, d0: int, nd: int, eps: float = GF_EPS_DEFAULT, view: int = 0) -> np.ndarray:
+    """GF-v1 aggregated costs q_d, float64 [nd][H][W] (A.3; parity unpinned)."""
+    L, R = _u8(L), _u8(R)
+    out = np.empty((nd,) + L.shape, np.float64)
+    lib().orc_gf_cost_slices(L, R, L.shape[0], L.shape[1], r, eps, view, d0, nd, out)
+    return out
+
+
+def gf_wta(L, R, r: int, D: int, eps: float = GF_EPS_DEFAULT, view: int = 0, return_cost: bool = False):
+    """GF-v1 + float WTA (A.3 + A.4, StereoHelper.cpp:137-150)."""
+    L, R = _u8(L), _u8(R)
+    out = np.empty_like(L)
+    cost = np.empty(L.shape, np.float64) if return_cost else None
+    lib().orc_gf_wta(L, R, L.shape[0], L.shape[1], r, D, eps, view, out,
+                     cost.ctypes.data_as(C.c_void_p) if return_cost else None)
+    return (out, cost) if return_cost else out
+
+
+def lr_check(DL, DR):
+    """StereoDisparity.cpp:136-147 -> (occ, mask)."""
+    DL, DR = _u8(DL), _u8(DR)
+    occ = np.empty_like(DL)
+    mask = np.empty_like(DL)
+    lib().orc_lr_check(DL, DR, DL.shape[0], DL.shape[1], occ, mask)
+    return occ, mask
+
+
+def median(img, r: int) -> np.ndarray:
+    """ctmf semantics (ctmf.c:378-433): (2r+1)^2 median, replicate border."""
+    img = _u8(img)
+    out = np.empty_like(img)
+    lib().orc_median(img, out, img.shape[0], img.shape[1], r)
+    return out
+
+
+def fnv1a64(a) -> str:
+    a = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    return "%016x" % lib().orc_fnv1a64(a, a.size)
+
+
+def stereo_pipeline(L, R, *, mode: str, r: int, D: int, eps: float = GF_EPS_DEFAULT,
+                    lr: bool = False, median_r: int = 0):
+    """Whole path as the product runs it (DESIGN.md "Pipeline order"):
+    WTA (left) [-> WTA (right) when lr] -> median on both -> LR check -> occluded pixels zeroed.
+    Returns (disp, mask) ; mask is None without lr.  Order follows StereoDisparity.cpp:115-147.
+    """
+    if mode == "sad":
+        dl = sad_wta(L, R, r, D)
+    else:
+        dl = gf_wta(L, R, r, D, eps, 0)
+    if median_r > 0:
+        dl = median(dl, median_r)
+    if not lr:
+        return dl, None
+    if mode == "sad":
+        raise ValueError("the reference defines no right-view SAD; lr needs mode='gf'")
+    dr = gf_wta(L, R, r, D, eps, 1)
+    if median_r > 0:
+        dr = median(dr, median_r)
+    occ, mask = lr_check(dl, dr)
+    out = dl.copy()
+    out[occ != 0] = 0
+    return out, mask
+
+
+# ----------------------------------------------------------------------------- real reference
+def ref_getDisp(L, R, r: int, D: int) -> np.ndarray:
+    L, R = _u8(L), _u8(R)
+    out = np.empty_like(L)
+    with quiet_stdout():
+        ref().ref_getDisp(L, R, L.shape[0], L.shape[1], r, D, out)
+    return out
+
+
+def ref_PreCal(L, R, D: int) -> np.ndarray:
+    L, R = _u8(L), _u8(R)
+    out = np.zeros((D,) + L.shape, np.uint8)
+    ref().ref_PreCal(L, R, L.shape[0], L.shape[1], 0, D, out)
+    return out
+
+
+def ref_getAllSAD(L, R, r: int, D: int) -> np.ndarray:
+    L, R = _u8(L), _u8(R)
+    out = np.full((L.size, D), 255, np.uint8)
+    with quiet_stdout():
+        ref().ref_getAllSAD(L, R, L.shape[0], L.shape[1], r, D, out)
+    return out
+
+
+def ref_median(img, r: int) -> np.ndarray:
+    img = _u8(img)
+    out = np.empty_like(img)
+    ref().ref_median(img, out, img.shape[0], img.shape[1], r)
+    return out
