@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the BlockMatching hot path on B200.
+
+Contract (see the task description): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+  step      = one pass of the fused hot path (guided-filter stereo: AD -> GF aggregation -> WTA) over one batch
+              of synthetic rectified 1280x720 pairs, 128 disparities, r = 9  (BASELINE config 3, the shape the
+              metric "MDE/s & fps at 720p x 128d" is quoted on).
+  value     = whole-job MDE/s (rows*cols*D*frames / s / 1e6) with the frames already resident in HBM.
+  e2e       = the same metric through the host-buffer C-ABI call gsm_stereo_batch (pinned host memory,
+              H2D + kernels + D2H inside the timed region).
+  N > 1     = frame batches sharded across ranks, no collective on the data path ("weak" scaling: every rank
+              processes `--frames` frames per step).
+  --impl reference = the reference's own CPU BlockMatching (getDisp, compiled unmodified into oracle/_ref)
+              timed on the host cores on a bounded sample of the same frames.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, D, R_GF = 720, 1280, 128, 9
+WORKLOAD = "config3: rectified 1280x720 synthetic stereo stream, 128 disparities, guided filter r=9, no LR"
+GF_OPS_PER_DE = 28   # algorithmic lane-ops per pixel*disparity, guided-filter mode
+HBM_BYTES_PER_PX = 3  # read L + R, write disparity
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._idx = gpu_index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self._idx), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
+
+
+def _reference_arm(args, rank, world):
+    """CPU baseline: the reference's own getDisp on the box's host cores (bounded sample, all cores)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from gpu_stereo_matching_b200 import data as gdata
+    kind = "reference" if O.have_ref() else "port"
+    cores = os.cpu_count() or 1
+    band_rows, r_ref = 24, 5
+    L, R, _ = gdata.synthetic_pair(H, W, 1234)
+    bands = [(L[i * band_rows:(i + 1) * band_rows].copy(), R[i * band_rows:(i + 1) * band_rows].copy())
+             for i in range(min(cores, H // band_rows))]
+    fn = (lambda a, b: O.ref().ref_getDisp(a, b, band_rows, W, r_ref, D, np.empty_like(a))) if kind == "reference" \
+        else (lambda a, b: O.sad_wta(a, b, r_ref, D, direct=True))
+
+    def step():
+        ths = [threading.Thread(target=fn, args=b) for b in bands]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    de = len(bands) * band_rows * W * D
+    with O.quiet_stdout():
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
+    v = de / dt / 1e6
+    sample = (f"{len(bands)} bands of {band_rows}x{W} px x {D} d of a config-3 frame, one band per thread; "
+              f"reference getDisp (SAD r={r_ref}, Caller.cpp:19 -- the reference has no guided filter)")
+    print(json.dumps({
+        "impl": "reference", "metric": "MDE/s", "value": v, "unit": "MDE/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32", "data": "synthetic", "fps": v * 1e6 / (H * W * D),
+        "config": {"workload": WORKLOAD, "reference_arm": sample},
+        "cpu_baseline": {"value": v, "unit": "MDE/s", "cores": len(bands), "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def _cpu_baseline(frames_L, frames_R):
+    """Bounded CPU sample for the product arm's JSON line (rank 0, N=1): the reference getDisp (1 core, as
+    shipped) and our GF oracle port (all cores) on crops of the first frame."""
+    from oracle import oracle as O
+    out = {}
+    L, R = frames_L[0], frames_R[0]
+    rows = 120
+    a, b = L[:rows].copy(), R[:rows].copy()
+    kind = "reference" if O.have_ref() else "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        O.ref_getDisp(a, b, 5, D)
+    else:
+        O.sad_wta(a, b, 5, D, direct=True)
+    dt = time.perf_counter() - t0
+    out.update({"value": rows * W * D / dt / 1e6, "unit": "MDE/s", "cores": 1, "kind": kind,
+                "sample": f"reference getDisp (SAD r=5, single-threaded as shipped) on a {rows}x{W} px x {D} d crop of frame 0"})
+    rows = 240
+    a, b = L[:rows].copy(), R[:rows].copy()
+    t0 = time.perf_counter()
+    O.gf_wta(a, b, R_GF, D)
+    dt = time.perf_counter() - t0
+    out["gf_port"] = {"value": rows * W * D / dt / 1e6, "unit": "MDE/s", "cores": os.cpu_count(), "kind": "port",
+                      "sample": f"oracle GF r={R_GF} float64 (OpenMP) on a {rows}x{W} px x {D} d crop of frame 0"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        _reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gpu_stereo_matching_b200 as g
+    from gpu_stereo_matching_b200 import data as gdata
+    from gpu_stereo_matching_b200.dist import shard_frames, torch_stream_handle
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this benchmark has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.frames
+    # every rank owns its own block of the global stream (frame sharding, no collective on the data path)
+    f0, f1 = shard_frames(n * world, world, rank)
+    uniq = 4  # distinct synthetic frames per rank, tiled to n (generation is host work outside the timed region)
+    Lu, Ru, rectified = gdata.rectified_stream(uniq, seed0=1234 + f0)
+    reps = (n + uniq - 1) // uniq
+    Lh = torch.from_numpy(np.tile(Lu, (reps, 1, 1))[:n]).pin_memory()
+    Rh = torch.from_numpy(np.tile(Ru, (reps, 1, 1))[:n]).pin_memory()
+    Dh = torch.empty_like(Lh).pin_memory()
+    ctx = g.StereoContext(H, W, D, min(n, 32), device=local_rank)
+    p = g.make_params("gf", R_GF, D, row_bands=0)
+    Ld, Rd = Lh.cuda(non_blocking=True), Rh.cuda(non_blocking=True)
+    Dd = torch.empty_like(Ld)
+    stream = torch.cuda.Stream()
+    sh = torch_stream_handle(stream)
+    de_step = n * H * W * D
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        ctx.stereo_device(Ld.data_ptr(), Rd.data_ptr(), Dd.data_ptr(), 0, n, H, W, p, sh)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- device-resident timing --------------------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+    barrier()
+    ctx.set_kernel_timing(True)
+    l0 = ctx.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kms = []
+    with ClockSampler(local_rank) as clk:
+        with torch.cuda.stream(stream):
+            for a, b in evs:
+                flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+                a.record(stream)
+                step_device()
+                b.record(stream)
+                stream.synchronize()
+                kms.append(ctx.last_kernel_ms())
+        barrier()
+    launches = ctx.launch_count - l0
+    ctx.set_kernel_timing(False)
+    ms = float(sum(a.elapsed_time(b) for a, b in evs) / args.steps)
+    kernel_ms = float(np.mean(kms))
+    # ---- end-to-end through the host-buffer C-ABI call -----------------------------------------------------
+    for _ in range(2):
+        ctx.stereo_batch(Lh.numpy(), Rh.numpy(), p, out=Dh.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.stereo_batch(Lh.numpy(), Rh.numpy(), p, out=Dh.numpy())
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    barrier()
+    checksum = int(Dh.numpy().astype(np.uint64).sum())
+    alu_peak = ctx.measure_alu_peak()
+
+    # ---- max over ranks ----------------------------------------------------------------------------------
+    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = [float(x) for x in t.tolist()]
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        value = de_step * world / (ms * 1e-3) / 1e6
+        e2e = de_step * world / (e2e_ms * 1e-3) / 1e6
+        de_s_kernel = de_step / (kernel_ms * 1e-3)
+        line = {
+            "metric": "MDE/s", "value": value, "unit": "MDE/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32+fp32", "data": "synthetic",
+            "fps": value * 1e6 / (H * W * D),
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": n, "rows": H, "cols": W, "num_disp": D,
+                       "mode": "gf", "radius": R_GF, "rectified_with_calib_maps": bool(rectified),
+                       "parallelism": f"frame-batch x{world} (no collective)", "l2": "flushed between timed steps (256 MiB fill)",
+                       "result_checksum": checksum},
+            "e2e": {"value": e2e, "unit": "MDE/s", "fps": e2e * 1e6 / (H * W * D), "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 2 * n * H * W, "d2h_bytes_per_step": n * H * W},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "roofline": {
+                "bound": "alu", "kernel": "gf_wta_kernel<9,16>",
+                "achieved": GF_OPS_PER_DE * de_s_kernel / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s",
+                "frac": GF_OPS_PER_DE * de_s_kernel / alu_peak,
+                "peak_source": "FFMA+IADD3 issue-peak microbenchmark run live on this GPU (gsm_measure_alu_peak); "
+                               "MEASURED_PEAKS.json has no ALU figure",
+                "algorithmic_ops_per_de": GF_OPS_PER_DE, "kernel_ms_per_step": kernel_ms,
+                "kernel_share_of_step": kernel_ms / ms,
+                "hbm": {"achieved": HBM_BYTES_PER_PX * n * H * W / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": HBM_BYTES_PER_PX * n * H * W / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "peak_source": peak_src},
+                "traffic": None,
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            with O.quiet_stdout():
+                cb = _cpu_baseline(Lu, Ru)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,74 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed as plumbing).
+
+Two strategies, nothing else:
+  * frame batches  -- frames of a stream are independent: contiguous blocks of frames per rank,
+                      NO collective on the data path (shard_frames).
+  * disparity split -- one very large frame: rank g evaluates d in [d_begin, d_end) over the full frame and
+                      leaves a per-pixel packed (cost, d) int64 word; ONE exchange step, an all-reduce(MIN)
+                      over NCCL/NVLink, combines the ranks exactly (lowest d wins ties, like the reference's
+                      strict '<', BlockMatching.cpp:178), independent of the number of ranks (dsplit_stereo).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+WARP = 32  # the fused kernels evaluate disparities in chunks of 32 (one warp)
+
+
+def shard_frames(n_frames: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [start, stop) of frames for `rank`; blocks differ in size by at most one frame."""
+    if world < 1 or not (0 <= rank < world) or n_frames < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(n_frames, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_disparities(num_disp: int, world: int, rank: int, align: int = WARP) -> Tuple[int, int]:
+    """[d_begin, d_end) for `rank`: whole 32-disparity chunks, as even as possible; may be empty."""
+    if world < 1 or not (0 <= rank < world) or num_disp < 1:
+        raise ValueError("bad shard request")
+    chunks = (num_disp + align - 1) // align
+    c0, c1 = shard_frames(chunks, world, rank)
+    return min(c0 * align, num_disp), min(c1 * align, num_disp)
+
+
+def key_init(mode: int, radius: int) -> int:
+    """Initial packed word of the min plane (must be identical on every rank)."""
+    if mode == 0:  # SAD: acceptance threshold 50*(2r+1)^2, d = 0  (BlockMatching.cpp:157-158)
+        w = 2 * radius + 1
+        return (50 * w * w) << 8
+    return 0x7FFFFFFFFFFFFF00  # GF: +inf, d = 0
+
+
+def torch_stream_handle(stream=None) -> int:
+    """cudaStream_t for libgsm: torch's current stream; the legacy default stream is passed as
+    cudaStreamLegacy (1) because 0 means "the context's own stream" in the C ABI."""
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream or 1
+
+
+def dsplit_stereo(partial_keys: Callable, finalize: Callable, keys_left, keys_right, params, world: int, rank: int,
+                  group=None, all_reduce: Optional[Callable] = None):
+    """Disparity-split evaluation of ONE frame.
+
+    partial_keys(view, d_begin, d_end, keys_tensor) fills keys_tensor (int64 [rows*cols]) with this rank's
+    packed minima (gsm_partial_keys_device on a GPU rank); finalize(keys_left, keys_right|None) turns reduced
+    keys into the disparity map (gsm_finalize_keys_device).  all_reduce defaults to torch.distributed's MIN.
+    Ranks whose range is empty contribute the init word only.
+    """
+    import torch.distributed as dist
+    if all_reduce is None:
+        def all_reduce(t):
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    d0, d1 = shard_disparities(params.num_disp, world, rank)
+    views = (0, 1) if params.lr_check else (0,)
+    for view, keys in zip(views, (keys_left, keys_right)):
+        if d1 > d0:
+            partial_keys(view, d0, d1, keys)
+        else:
+            keys.fill_(key_init(params.mode, params.radius))
+        if world > 1:
+            all_reduce(keys)
+    return finalize(keys_left, keys_right if params.lr_check else None)

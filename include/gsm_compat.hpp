@@ -1,0 +1,88 @@
+// gsm_compat.hpp -- the reference's own C++ entry points as thin wrappers over the C ABI (gsm.h).
+//
+// Keeps  void blockMatching_gpu(Mat &h_left, Mat &h_right, Mat &h_disparity, int SADWindowSize, int searchRange);
+// (BlockMatching/Device.cuh:50, definition Device.cu:173-301) source-compatible, so Caller.cpp:19 and the
+// debug hooks compareDisp/compareDiff (BlockMatching.cpp:263-293) keep working unchanged.
+//
+// The wrappers are templates over any cv::Mat-shaped type (members rows, cols, data and the constructor
+// Mat(rows, cols, type, void*)), so the same header builds against real OpenCV 2.4/3/4 and against the
+// 15-line shim used by this repository's tests (oracle/shim/cvshim.hpp).  Include it AFTER the OpenCV core
+// header; define GSM_COMPAT_REFERENCE_NAMES to also get the un-templated global names for cv::Mat.
+#ifndef GSM_COMPAT_HPP
+#define GSM_COMPAT_HPP
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "gsm.h"
+
+namespace gsm_compat {
+
+// One lazily created context per process, grown on demand (the reference allocates per call and leaks,
+// Device.cu:184-194).  Not thread-safe, like the reference.
+inline gsm_ctx*& shared_ctx() {
+  static gsm_ctx* ctx = nullptr;
+  return ctx;
+}
+inline gsm_ctx* ctx_for(int rows, int cols) {
+  static int cap_rows = 0, cap_cols = 0;
+  gsm_ctx*& ctx = shared_ctx();
+  if (!ctx || rows > cap_rows || cols > cap_cols) {
+    if (ctx) gsm_destroy(ctx);
+    ctx = nullptr;
+    cap_rows = rows > 1080 ? rows : 1080;
+    cap_cols = cols > 1920 ? cols : 1920;
+    if (gsm_create(&ctx, 0, cap_rows, cap_cols, 256, 1) != GSM_OK) {
+      std::fprintf(stderr, "gsm_compat: %s\n", gsm_last_error());
+      std::abort();  // the reference has no error path either; failing loudly beats silent garbage
+    }
+  }
+  return ctx;
+}
+
+// Same contract as the reference: CV_8UC1, equal sizes, continuous; SADWindowSize is a RADIUS; the output
+// Mat is assigned a header over a freshly new[]-ed buffer the caller never frees (Device.cu:185,300).
+template <class Mat>
+void blockMatching_gpu(Mat& h_left, Mat& h_right, Mat& h_disparity, int SADWindowSize, int searchRange) {
+  const int rows = h_left.rows, cols = h_left.cols;
+  unsigned char* out = new unsigned char[(size_t)rows * cols];
+  const int rc = gsm_block_matching(ctx_for(rows, cols), h_left.data, h_right.data, out, rows, cols, SADWindowSize,
+                                    searchRange);
+  if (rc != GSM_OK) {
+    std::fprintf(stderr, "blockMatching_gpu: %s\n", gsm_last_error());
+    std::abort();
+  }
+  h_disparity = Mat(rows, cols, /*CV_8UC1*/ 0, out);
+}
+
+// Guided-filter variant of the same call (north_star path; no reference counterpart).
+template <class Mat>
+void guidedMatching_gpu(Mat& h_left, Mat& h_right, Mat& h_disparity, int radius, int searchRange, bool lrCheck = false,
+                        int medianRadius = 0) {
+  const int rows = h_left.rows, cols = h_left.cols;
+  unsigned char* out = new unsigned char[(size_t)rows * cols];
+  gsm_params p = {};
+  p.mode = GSM_MODE_GF;
+  p.radius = radius;
+  p.num_disp = searchRange;
+  p.lr_check = lrCheck ? 1 : 0;
+  p.median_radius = medianRadius;
+  const int rc = gsm_stereo_batch(ctx_for(rows, cols), &p, 1, h_left.data, h_right.data, out, nullptr, rows, cols);
+  if (rc != GSM_OK) {
+    std::fprintf(stderr, "guidedMatching_gpu: %s\n", gsm_last_error());
+    std::abort();
+  }
+  h_disparity = Mat(rows, cols, 0, out);
+}
+
+}  // namespace gsm_compat
+
+#ifdef GSM_COMPAT_REFERENCE_NAMES
+// exact reference name and signature (Device.cuh:50) for translation units that `using namespace cv;`
+inline void blockMatching_gpu(cv::Mat& h_left, cv::Mat& h_right, cv::Mat& h_disparity, int SADWindowSize,
+                              int searchRange) {
+  gsm_compat::blockMatching_gpu<cv::Mat>(h_left, h_right, h_disparity, SADWindowSize, searchRange);
+}
+#endif
+
+#endif  // GSM_COMPAT_HPP

@@ -1,0 +1,243 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI vs the oracle.
+
+Bars (north_star): integer AD / SAD / WTA stages bit-exact; guided-filter costs within
+GF_RTOL = 1e-4 of the float64 oracle, measured as |dq| <= GF_RTOL * max(|q_ref|, 1) on the 0..255 scale
+(q crosses zero, hence the absolute floor of one grey level); final disparity maps >= 99.9 % identical
+and no pixel off by more than 1.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, SETS
+
+pytestmark = pytest.mark.gpu
+
+GF_RTOL = 1e-4
+import gpu_stereo_matching_b200 as g  # noqa: E402
+from gpu_stereo_matching_b200 import data as gdata  # noqa: E402
+
+
+def _gf_err(q, qref):
+    return np.abs(q.astype(np.float64) - qref) / np.maximum(np.abs(qref), 1.0)
+
+
+def _disp_bar(a, b):
+    diff = np.abs(a.astype(int) - b.astype(int))
+    return float((diff == 0).mean()), int((diff > 1).sum())
+
+
+# ------------------------------------------------------------------------------------------ SAD (pinned)
+def test_sad_golden_digests_all_sets(ctx, fx, digests, orc):
+    """blockMatching_gpu == the reference's getDisp (digests made by the unmodified reference CPU code)."""
+    for s in SETS + ["ArtDemo"]:
+        d = ctx.block_matching(fx[s + "_L"], fx[s + "_R"], 5, 64)
+        assert orc.fnv1a64(d) == digests["getDisp"][s]["fnv1a64"], s
+
+
+@pytest.mark.parametrize("r,D", [(1, 16), (2, 33), (3, 48), (5, 64), (7, 100), (9, 64), (12, 128), (5, 256)])
+def test_sad_bit_exact_vs_oracle(ctx, fx, orc, r, D):
+    for name in ("Art", "Laundry"):
+        L, R = fx[name + "_L"], fx[name + "_R"]
+        assert np.array_equal(ctx.block_matching(L, R, r, D), orc.sad_wta(L, R, r, D)), (name, r, D)
+
+
+def test_sad_edge_shapes(ctx, orc):
+    """Ragged / tiny / degenerate inputs: W < D, H or W below the window, single row/column, W % 16 != 0."""
+    rng = np.random.default_rng(21)
+    for (h, w, r, D) in [(1, 1, 1, 1), (1, 40, 2, 8), (40, 1, 2, 8), (3, 5, 4, 16), (17, 23, 5, 64), (33, 130, 9, 200),
+                         (64, 209, 3, 32), (70, 161, 12, 17), (240, 367, 5, 96)]:
+        L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        R = np.roll(L, -min(3, w - 1), axis=1) ^ rng.integers(0, 16, (h, w), dtype=np.uint8)
+        assert np.array_equal(ctx.block_matching(L, R, r, D), orc.sad_wta(L, R, r, D)), (h, w, r, D)
+
+
+def test_sad_white_noise_and_constant(ctx, orc):
+    L, R = gdata.noise_pair(120, 200, 5)
+    assert np.array_equal(ctx.block_matching(L, R, 5, 64), orc.sad_wta(L, R, 5, 64))  # nothing passes the threshold
+    z = np.zeros((50, 70), np.uint8)
+    assert np.array_equal(ctx.block_matching(z, z, 5, 64), orc.sad_wta(z, z, 5, 64))  # all ties -> lowest d
+    w = np.full((50, 70), 255, np.uint8)
+    assert np.array_equal(ctx.block_matching(w, z, 5, 64), orc.sad_wta(w, z, 5, 64))  # maximum SAD everywhere
+
+
+def test_cost_stage_exports(ctx, fx, orc, digests):
+    """PreCal / un-truncated SAD slices / getAllSAD: what compareDiff and compareSAD check."""
+    L, R = fx["ArtDemo_L"], fx["ArtDemo_R"]
+    vol = ctx.ad_volume(L, R, 64)
+    assert orc.fnv1a64(vol) == digests["PreCal_ArtDemo_D64"]
+    p = g.make_params("sad", 5, 64)
+    sl = ctx.cost_slices(L, R, p, 0, 64)
+    ref = np.stack([orc.sad_slice(L, R, 5, d) for d in range(64)])
+    assert np.array_equal(sl, ref)
+    part = ctx.cost_slices(L, R, p, 37, 9)
+    assert np.array_equal(part, ref[37:46])
+    assert orc.fnv1a64(ctx.all_sad(L, R, 5, 64)) == digests["getAllSAD_ArtDemo_r5_D64"]
+
+
+def test_reference_caller_dropin(ctx, fx, tmp_path):
+    """singleFrame()'s compute through the kept C++ signature, then the reference's own compareDisp."""
+    exe = tmp_path / "caller_dropin"
+    cmd = ["g++", "-O1", "-std=c++14", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "shim"),
+           os.path.join(ROOT, "tests", "cpp", "caller_dropin.cpp"), "-o", str(exe),
+           "-L", os.path.join(ROOT, "gpu_stereo_matching_b200"), "-lgsm",
+           "-Wl,-rpath," + os.path.join(ROOT, "gpu_stereo_matching_b200")]
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    with_ref = os.path.exists(os.path.join(ref, "libref.so"))
+    if with_ref:
+        cmd += ["-DWITH_REF", "-L", ref, "-lref", "-Wl,-rpath," + ref]
+    subprocess.run(cmd, check=True)
+    L, R = fx["ArtDemo_L"], fx["ArtDemo_R"]  # the 320x256 pair Caller.cpp:12-13 loads
+    L.tofile(tmp_path / "l.gray"); R.tofile(tmp_path / "r.gray")
+    out = subprocess.run([str(exe), str(tmp_path / "l.gray"), str(tmp_path / "r.gray"), "256", "320", "5", "64",
+                          str(tmp_path / "d.gray")], capture_output=True, text=True, check=True)
+    assert "GPU_DONE 256 320" in out.stdout
+    if with_ref:
+        tail = out.stdout.split("GPU_DONE 256 320\n", 1)[1]
+        assert "CPU =" not in tail and "[" not in tail, tail[:400]  # compareDisp printed no mismatch
+    d = np.fromfile(tmp_path / "d.gray", np.uint8).reshape(256, 320)
+    assert np.array_equal(d, ctx.block_matching(L, R, 5, 64))
+
+
+# ------------------------------------------------------------------------------------------ post filters
+def test_median_and_lr_kernels(ctx, fx, orc):
+    d = ctx.block_matching(fx["Art_L"], fx["Art_R"], 5, 64)
+    for m in (1, 2, 3, 5):
+        assert np.array_equal(ctx.median(d, m), orc.median(d, m))
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 64, (97, 131), dtype=np.uint8); b = rng.integers(0, 64, (97, 131), dtype=np.uint8)
+    occ, mask = ctx.lr_check(a, b)
+    o2, m2 = orc.lr_check(a, b)
+    assert np.array_equal(occ, o2) and np.array_equal(mask, m2)
+
+
+# ------------------------------------------------------------------------------------------ GF (unpinned)
+@pytest.mark.parametrize("name,r,D", [("ArtDemo", 9, 64), ("Art", 9, 64), ("Books", 5, 32), ("Laundry", 2, 40),
+                                       ("Reindeer", 9, 48)])
+def test_gf_costs_within_tolerance(ctx, fx, orc, name, r, D):
+    L, R = fx[name + "_L"], fx[name + "_R"]
+    p = g.make_params("gf", r, D)
+    for view in (0, 1):
+        q = ctx.cost_slices(L, R, p, 0, D, view=view)
+        qref = orc.gf_cost_slices(L, R, r, 0, D, view=view)
+        err = _gf_err(q, qref)
+        assert err.max() <= GF_RTOL, (name, r, D, view, float(err.max()))
+
+
+def test_gf_costs_synthetic_and_noise(ctx, orc):
+    L, R, _ = gdata.synthetic_pair(180, 320, 77, dmax=60)
+    p = g.make_params("gf", 9, 64)
+    err = _gf_err(ctx.cost_slices(L, R, p, 0, 64), orc.gf_cost_slices(L, R, 9, 0, 64))
+    assert err.max() <= GF_RTOL, float(err.max())
+    L, R = gdata.noise_pair(96, 170, 9)
+    err = _gf_err(ctx.cost_slices(L, R, p, 0, 64), orc.gf_cost_slices(L, R, 9, 0, 64))
+    assert err.max() <= GF_RTOL, float(err.max())
+
+
+@pytest.mark.parametrize("name", SETS)
+def test_gf_disparity_bar_config1_2(ctx, fx, orc, name):
+    """BASELINE configs 1-2: every Middlebury set, D=64, GF r=9, with L-R check (and the 7x7 median)."""
+    L, R = fx[name + "_L"], fx[name + "_R"]
+    disp, _ = ctx.stereo_batch(L, R, g.make_params("gf", 9, 64))
+    same, off = _disp_bar(disp, orc.gf_wta(L, R, 9, 64))
+    assert same >= 0.999 and off == 0, (name, same, off)
+    disp, mask = ctx.stereo_batch(L, R, g.make_params("gf", 9, 64, lr_check=True, median_radius=3))
+    dref, mref = orc.stereo_pipeline(L, R, mode="gf", r=9, D=64, lr=True, median_r=3)
+    same, off = _disp_bar(disp, dref)
+    # a flipped near-tie can flip the occlusion flag, which zeroes the pixel: count those separately
+    flipped = (mask != mref)
+    assert same >= 0.999, (name, same)
+    assert int((np.abs(disp.astype(int) - dref.astype(int)) > 1)[~flipped].sum()) == 0
+    assert flipped.mean() <= 1e-3
+
+
+def test_gf_edge_shapes(ctx, orc):
+    rng = np.random.default_rng(31)
+    for (h, w, r, D) in [(1, 1, 1, 1), (2, 50, 3, 8), (50, 2, 3, 8), (7, 9, 9, 16), (40, 145, 9, 100), (65, 300, 4, 33)]:
+        L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        R = np.roll(L, -min(2, w - 1), axis=1) ^ rng.integers(0, 8, (h, w), dtype=np.uint8)
+        p = g.make_params("gf", r, D)
+        for view in (0, 1):
+            err = _gf_err(ctx.cost_slices(L, R, p, 0, D, view=view), orc.gf_cost_slices(L, R, r, 0, D, view=view))
+            assert err.max() <= GF_RTOL, (h, w, r, D, view, float(err.max()))
+
+
+# ------------------------------------------------------------------------------------------ properties at full size
+def _dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_full_size_720p_properties(ctx, orc):
+    """BASELINE config 3 shape (1280x720, D=128, GF r=9): size-independent properties + a cropped oracle check."""
+    import torch
+    L, R, _ = gdata.synthetic_pair(720, 1280, 1234)
+    p = g.make_params("gf", 9, 128)
+    full, _ = ctx.stereo_batch(L, R, p)
+    # (1) result does not depend on the row-band decomposition
+    for bands in (1, 3, 7):
+        alt, _ = ctx.stereo_batch(L, R, g.make_params("gf", 9, 128, row_bands=bands))
+        same, off = _disp_bar(alt, full)
+        assert same >= 0.9999 and off == 0, (bands, same, off)
+    # (2) disparity split: partial packed minima of 4 ranges combined by min == the single pass, bit for bit
+    Ld, Rd = _dev(L), _dev(R)
+    keys = []
+    for k in range(4):
+        kt = torch.empty(720 * 1280, dtype=torch.int64, device="cuda")
+        ctx.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), kt.data_ptr(), 720, 1280,
+                                g.make_params("gf", 9, 128, row_bands=1, d_begin=32 * k, d_end=32 * (k + 1)))
+        ctx.sync()
+        keys.append(kt.clone())
+    red = torch.stack(keys).min(dim=0).values
+    one = torch.empty(720 * 1280, dtype=torch.int64, device="cuda")
+    ctx.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), one.data_ptr(), 720, 1280, g.make_params("gf", 9, 128, row_bands=1))
+    ctx.sync()
+    assert torch.equal(red, one)
+    # (3) a batch equals its frames one by one
+    L2, R2, _ = gdata.synthetic_pair(720, 1280, 1235)
+    b, _ = ctx.stereo_batch(np.stack([L, L2]), np.stack([R, R2]), g.make_params("gf", 9, 128, row_bands=1))
+    s0, _ = ctx.stereo_batch(L, R, g.make_params("gf", 9, 128, row_bands=1))
+    s1, _ = ctx.stereo_batch(L2, R2, g.make_params("gf", 9, 128, row_bands=1))
+    assert np.array_equal(b[0], s0) and np.array_equal(b[1], s1)
+    # (4) a crop far from the borders against the oracle run on a padded crop (windows need 2r context)
+    y0, x0, hh, ww, pad = 300, 500, 64, 96, 18
+    Lc = L[y0 - pad:y0 + hh + pad, x0 - pad - 128:x0 + ww + pad]
+    Rc = R[y0 - pad:y0 + hh + pad, x0 - pad - 128:x0 + ww + pad]
+    ref = orc.gf_wta(Lc, Rc, 9, 128)[pad:pad + hh, pad + 128:pad + 128 + ww]
+    same, off = _disp_bar(full[y0:y0 + hh, x0:x0 + ww], ref)
+    assert same >= 0.999 and off == 0, (same, off)
+    # (5) SAD mode at full size: bit-exact against the oracle
+    assert np.array_equal(ctx.block_matching(L, R, 5, 128), orc.sad_wta(L, R, 5, 128))
+
+
+def test_full_size_1080p_lr_median(ctx, orc):
+    """BASELINE config 4 shape (1920x1080, D=192, GF r=9, LR + median): idempotence and crop check."""
+    L, R, _ = gdata.synthetic_pair(1080, 1920, 2000, dmax=180)
+    p = g.make_params("gf", 9, 192, lr_check=True, median_radius=3)
+    d1, m1 = ctx.stereo_batch(L, R, p)
+    d2, m2 = ctx.stereo_batch(L, R, p)
+    assert np.array_equal(d1, d2) and np.array_equal(m1, m2)  # deterministic (atomicMin on packed words)
+    assert set(np.unique(m1)) <= {0, 1}
+    assert np.all(d1[m1 == 0] == 0)  # occluded pixels are zeroed
+    y0, x0, hh, ww, pad = 500, 900, 48, 80, 24
+    sl = (slice(y0 - pad, y0 + hh + pad), slice(x0 - pad - 192, x0 + ww + pad + 192))
+    dref, mref = orc.stereo_pipeline(L[sl], R[sl], mode="gf", r=9, D=192, lr=True, median_r=3)
+    ref = dref[pad:pad + hh, pad + 192:pad + 192 + ww]
+    same, off = _disp_bar(d1[y0:y0 + hh, x0:x0 + ww], ref)
+    assert same >= 0.995, same
+
+
+def test_errors_are_reported(ctx):
+    z = np.zeros((16, 16), np.uint8)
+    with pytest.raises(g.GsmError):
+        ctx.block_matching(z, z, 0, 16)       # radius out of range
+    with pytest.raises(g.GsmError):
+        ctx.block_matching(z, z, 5, 300)      # D > 256 would wrap the u8 output
+    with pytest.raises(g.GsmError):
+        ctx.stereo_batch(z, z, g.make_params("gf", 12, 16))  # GF radius > 9 (int32 numerator bound)
+    with pytest.raises(g.GsmError):
+        ctx.stereo_batch(np.zeros((2000, 16), np.uint8), np.zeros((2000, 16), np.uint8), g.make_params("sad", 5, 16))
+    with pytest.raises(TypeError):
+        ctx.block_matching(z.astype(np.float32), z, 5, 16)

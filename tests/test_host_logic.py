@@ -1,0 +1,151 @@
+"""CPU tests of the host-side partitioning logic, incl. the N>1 path on gloo (world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from gpu_stereo_matching_b200 import dist as gdist  # noqa: E402
+from gpu_stereo_matching_b200 import make_params  # noqa: E402
+
+
+def test_shard_frames_partition():
+    for n in (0, 1, 7, 64, 256, 257):
+        for world in (1, 2, 3, 4, 8):
+            spans = [gdist.shard_frames(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_disparities_partition():
+    for D in (1, 31, 32, 33, 64, 100, 128, 192, 256):
+        for world in (1, 2, 4, 8):
+            spans = [gdist.shard_disparities(D, world, r) for r in range(world)]
+            covered = []
+            for a, b in spans:
+                assert 0 <= a <= b <= D
+                assert a % 32 == 0 or a == D
+                covered += list(range(a, b))
+            assert covered == list(range(D))
+
+
+def test_key_init_matches_reference_threshold():
+    assert gdist.key_init(0, 5) == (50 * 121) << 8  # BlockMatching.cpp:157
+    assert gdist.key_init(1, 9) == 0x7FFFFFFFFFFFFF00
+
+
+def _sortable(q32):
+    b = q32.view(np.int32).astype(np.int64)
+    return b ^ ((b >> 31) & 0x7FFFFFFF)
+
+
+def _oracle_partial_keys(O, L, R, p, view, d0, d1):
+    """CPU stand-in for gsm_partial_keys_device built from the ORACLE (tests only)."""
+    h, w = L.shape
+    keys = np.full((h, w), gdist.key_init(p.mode, p.radius), np.int64)
+    xs = np.arange(w)[None, :]
+    for d in range(d0, d1):
+        if p.mode == 0:
+            sad = O.sad_slice(L, R, p.radius, d).astype(np.int64)
+            cand = np.where(xs + d <= w, (sad << 8) | d, np.int64(2 ** 62))
+        else:
+            q = O.gf_cost_slices(L, R, p.radius, d, 1, view=view)[0].astype(np.float32)
+            cand = (_sortable(q) << 32) | d
+        keys = np.minimum(keys, cand)
+    return keys
+
+
+def _dsplit_worker(rank, world, port, mode, out_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "middlebury_gray.npz"))
+    L, R = fx["ArtDemo_L"][40:120, 60:220].copy(), fx["ArtDemo_R"][40:120, 60:220].copy()
+    p = make_params(mode, 5 if mode == "sad" else 3, 64, lr_check=(mode == "gf"))
+    h, w = L.shape
+    kl = torch.empty(h * w, dtype=torch.int64)
+    kr = torch.empty(h * w, dtype=torch.int64)
+
+    def partial(view, d0, d1, keys):
+        keys.copy_(torch.from_numpy(_oracle_partial_keys(O, L, R, p, view, d0, d1).reshape(-1)))
+
+    def finalize(a, b):
+        dl = (a.numpy().reshape(h, w) & 0xFF).astype(np.uint8)
+        if b is None:
+            return dl
+        dr = (b.numpy().reshape(h, w) & 0xFF).astype(np.uint8)
+        occ, _ = O.lr_check(dl, dr)
+        dl[occ != 0] = 0
+        return dl
+
+    disp = gdist.dsplit_stereo(partial, finalize, kl, kr, p, world, rank)
+    if rank == 0:
+        np.save(out_path, disp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize("mode", ["sad", "gf"])
+def test_dsplit_world2_gloo(tmp_path, mode, orc, fx):
+    """Disparity split over 2 ranks + all-reduce(MIN) on packed int64 words == single-rank result."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / f"disp_{mode}.npy")
+    mp.spawn(_dsplit_worker, args=(2, _free_port(), mode, out), nprocs=2, join=True)
+    disp = np.load(out)
+    L, R = fx["ArtDemo_L"][40:120, 60:220].copy(), fx["ArtDemo_R"][40:120, 60:220].copy()
+    if mode == "sad":
+        ref = orc.sad_wta(L, R, 5, 64)
+    else:
+        # float32 keys: compare against the oracle evaluated on the same float32-rounded costs
+        ql = orc.gf_cost_slices(L, R, 3, 0, 64, view=0).astype(np.float32)
+        qr = orc.gf_cost_slices(L, R, 3, 0, 64, view=1).astype(np.float32)
+        dl = np.argmin(ql, axis=0).astype(np.uint8)
+        dr = np.argmin(qr, axis=0).astype(np.uint8)
+        occ, _ = orc.lr_check(dl, dr)
+        ref = dl.copy()
+        ref[occ != 0] = 0
+    assert np.array_equal(disp, ref)
+
+
+def _frames_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 7
+    a, b = gdist.shard_frames(n, world, rank)
+    # no collective on the data path: each rank just reports which frames it owns
+    mine = torch.zeros(n, dtype=torch.int64)
+    mine[a:b] = rank + 1
+    dist.all_reduce(mine)  # bookkeeping only (test-side)
+    if rank == 0:
+        np.save(out_path, mine.numpy())
+    dist.destroy_process_group()
+
+
+def test_frame_sharding_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "own.npy")
+    mp.spawn(_frames_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    own = np.load(out)
+    assert own.tolist() == [1, 1, 1, 1, 2, 2, 2]  # every frame owned exactly once, contiguous blocks

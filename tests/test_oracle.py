@@ -1,0 +1,173 @@
+"""CPU tests: the oracle against the reference's golden outputs and against itself (no GPU)."""
+import numpy as np
+import pytest
+
+from conftest import SETS
+
+
+def test_getdisp_digests_all_sets(fx, digests, orc):
+    """oracle.sad_wta == the reference's getDisp (compiled unmodified) on every shipped pair, r=5, D=64."""
+    for s in SETS + ["ArtDemo"]:
+        d = orc.sad_wta(fx[s + "_L"], fx[s + "_R"], 5, 64)
+        g = digests["getDisp"][s]
+        assert list(d.shape) == g["shape"]
+        assert int(d.sum()) == g["sum"] and int((d == 0).sum()) == g["zeros"], s
+        assert orc.fnv1a64(d) == g["fnv1a64"], s
+
+
+def test_survey_probe_values(fx, orc):
+    """Sum / zero counts recorded by the survey's probe of the compiled reference."""
+    d = orc.sad_wta(fx["ArtDemo_L"], fx["ArtDemo_R"], 5, 64)
+    assert (int(d.sum()), int((d == 0).sum())) == (2489456, 1702)
+    d = orc.sad_wta(fx["Art_L"], fx["Art_R"], 5, 64)
+    assert (int(d.sum()), int((d == 0).sum())) == (6887115, 3738)
+
+
+def test_other_digests(fx, digests, orc):
+    L, R = fx["ArtDemo_L"], fx["ArtDemo_R"]
+    assert orc.fnv1a64(orc.ad_volume(L, R, 64)) == digests["PreCal_ArtDemo_D64"]
+    assert orc.fnv1a64(orc.all_sad(L, R, 5, 64)) == digests["getAllSAD_ArtDemo_r5_D64"]
+    d = orc.sad_wta(L, R, 5, 64)
+    assert orc.fnv1a64(orc.median(d, 3)) == digests["ctmf_r3_on_getDisp_ArtDemo"]
+    assert orc.fnv1a64(orc.sad_wta(L, R, 9, 64)) == digests["getDisp_ArtDemo_r9_D64"]
+    assert orc.fnv1a64(orc.sad_wta(L, R, 2, 16)) == digests["getDisp_ArtDemo_r2_D16"]
+
+
+def test_direct_loop_equals_box_sums(orc):
+    """The literal getDisp loop structure and the O(1) box-sum version agree, incl. degenerate shapes."""
+    rng = np.random.default_rng(7)
+    for (h, w, r, D) in [(23, 31, 2, 12), (9, 40, 5, 33), (40, 9, 3, 16), (5, 5, 4, 8), (1, 17, 1, 4), (17, 1, 2, 3)]:
+        L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(orc.sad_wta(L, R, r, D), orc.sad_wta(L, R, r, D, direct=True)), (h, w, r, D)
+
+
+def test_against_compiled_reference(orc):
+    """Direct comparison with oracle/_ref/libref.so when it travelled with the repo."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(11)
+    for (h, w, r, D) in [(37, 53, 5, 20), (30, 70, 2, 64), (64, 48, 7, 40)]:
+        L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        # correlated right image so that some SADs pass the 50*(2r+1)^2 threshold
+        R = np.roll(L, -3, axis=1) ^ rng.integers(0, 8, (h, w), dtype=np.uint8)
+        assert np.array_equal(orc.sad_wta(L, R, r, D), orc.ref_getDisp(L, R, r, D))
+        assert np.array_equal(orc.ad_volume(L, R, D), orc.ref_PreCal(L, R, D))
+        assert np.array_equal(orc.all_sad(L, R, r, D), orc.ref_getAllSAD(L, R, r, D))
+    # MeanFilter passes memsize = area*channels (Toolkit.cpp:39-41): ctmf stripes need area/544 > 2r+1
+    img = rng.integers(0, 64, (128, 160), dtype=np.uint8)
+    for r in (1, 2, 3):
+        assert np.array_equal(orc.median(img, r), orc.ref_median(img, r))
+
+
+def test_quirks(orc):
+    """Appendix A.2: threshold, -256 -> 0, search cut-off x+d > W, zero AD for x < d, lowest-d ties."""
+    h, w, r, D = 12, 20, 2, 8
+    L = np.full((h, w), 200, np.uint8)
+    R = np.zeros((h, w), np.uint8)  # AD = 200 everywhere it is defined -> full windows fail the 50*N threshold
+    d = orc.sad_wta(L, R, r, D)
+    # interior pixels far from the x<d zero region: nothing accepted -> 0
+    assert d[6, 15] == 0
+    # identical images: every d has SAD 0 only at d = 0 ... ties resolve to the lowest d
+    L = np.arange(h * w, dtype=np.uint8).reshape(h, w)
+    assert np.all(orc.sad_wta(L, L, r, D)[:, r + D:] == 0)
+    # AD slice zero region
+    rng = np.random.default_rng(1)
+    L = rng.integers(0, 256, (h, w), dtype=np.uint8); R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    vol = orc.ad_volume(L, R, D)
+    for dd in range(D):
+        assert np.all(vol[dd, :, :dd] == 0)
+        assert np.array_equal(vol[dd, :, dd:], np.abs(L[:, dd:].astype(int) - R[:, :w - dd].astype(int)).astype(np.uint8))
+
+
+def _gf_naive(I, p, r, eps):
+    """Pure-numpy float64 GF-v1 with explicit clipped windows (tiny inputs only)."""
+    h, w = I.shape
+    I = I.astype(np.float64); p = p.astype(np.float64)
+    a = np.zeros((h, w)); b = np.zeros((h, w)); N = np.zeros((h, w))
+    for y in range(h):
+        for x in range(w):
+            ys = slice(max(0, y - r), min(h, y + r + 1)); xs = slice(max(0, x - r), min(w, x + r + 1))
+            wi, wp = I[ys, xs], p[ys, xs]
+            n = wi.size
+            mi, mp = wi.mean(), wp.mean()
+            var = (wi * wi).mean() - mi * mi
+            cov = (wi * wp).mean() - mi * mp
+            a[y, x] = cov / (var + eps)
+            b[y, x] = mp - a[y, x] * mi
+            N[y, x] = n
+    q = np.zeros((h, w))
+    for y in range(h):
+        for x in range(w):
+            ys = slice(max(0, y - r), min(h, y + r + 1)); xs = slice(max(0, x - r), min(w, x + r + 1))
+            q[y, x] = (a[ys, xs].sum() * I[y, x] + b[ys, xs].sum()) / N[y, x]
+    return q
+
+
+def test_gf_matches_naive_definition(orc):
+    rng = np.random.default_rng(3)
+    h, w, r, D = 14, 19, 2, 6
+    L = rng.integers(0, 256, (h, w), dtype=np.uint8); R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    for view in (0, 1):
+        q = orc.gf_cost_slices(L, R, r, 0, D, eps=6.5025, view=view)
+        for d in range(D):
+            p = orc.ad_slice(L, R, d, view)
+            ref = _gf_naive(L if view == 0 else R, p, r, 6.5025)
+            assert np.allclose(q[d], ref, rtol=1e-9, atol=1e-9)
+    disp, cost = orc.gf_wta(L, R, r, D, return_cost=True)
+    q = orc.gf_cost_slices(L, R, r, 0, D)
+    assert np.array_equal(disp, np.argmin(q, axis=0).astype(np.uint8))  # first minimum wins
+    assert np.allclose(cost, q.min(axis=0))
+
+
+def test_right_view_and_lr(orc):
+    """StereoHelper.cpp:156-180 (right volume) and StereoDisparity.cpp:136-147 (LR check), literal loops."""
+    rng = np.random.default_rng(5)
+    h, w, D = 6, 13, 9
+    L = rng.integers(0, 256, (h, w), dtype=np.uint8); R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    left = np.stack([orc.ad_slice(L, R, d, 0) for d in range(D)], axis=-1).astype(int)  # [y][x][d]
+    right = left.copy()
+    for y in range(h):
+        for x in range(w):
+            for d in range(D):
+                if x + d < w:
+                    right[y, x, d] = np.abs(int(L[y, x + d]) - int(R[y, x]))  # == leftPtr(y, x+d, d): x+d >= d
+                else:
+                    right[y, x, d] = right[y, x, d - 1]
+    for d in range(D):
+        assert np.array_equal(orc.ad_slice(L, R, d, 1), right[:, :, d].astype(np.uint8))
+    DL = rng.integers(0, 6, (h, w), dtype=np.uint8); DR = rng.integers(0, 6, (h, w), dtype=np.uint8)
+    occ, mask = orc.lr_check(DL, DR)
+    for y in range(h):
+        for x in range(w):
+            d = int(DL[y, x])
+            e = 1 if x - d < 0 else int(d == 0 or abs(d - int(DR[y, x - d])) > 1)
+            assert occ[y, x] == e and mask[y, x] == (not e)
+
+
+def test_median_is_replicate_border(orc):
+    from scipy.ndimage import median_filter
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (33, 47), dtype=np.uint8)
+    for r in (1, 2, 3):
+        assert np.array_equal(orc.median(img, r), median_filter(img, size=2 * r + 1, mode="nearest"))
+
+
+def test_packed_min_equivalence(fx, orc):
+    """Appendix A.2: any partition of the d range combined by min over (SAD<<8|d), starting from the init
+    word (50*(2r+1)^2)<<8, reproduces getDisp -- the identity the CTAs and GPUs rely on."""
+    L, R = fx["ArtDemo_L"][:96, :160].copy(), fx["ArtDemo_R"][:96, :160].copy()
+    r, D = 5, 64
+    h, w = L.shape
+    init = (50 * (2 * r + 1) ** 2) << 8
+    xs = np.arange(w)[None, :]
+    parts = []
+    for k in range(4):  # 4-way interleaved split
+        keys = np.full((h, w), init, np.int64)
+        for d in range(k, D, 4):
+            sad = orc.sad_slice(L, R, r, d).astype(np.int64)
+            cand = np.where(xs + d <= w, (sad << 8) | d, np.int64(2 ** 62))
+            keys = np.minimum(keys, cand)
+        parts.append(keys)
+    disp = (np.minimum.reduce(parts) & 0xFF).astype(np.uint8)
+    assert np.array_equal(disp, orc.sad_wta(L, R, r, D))
