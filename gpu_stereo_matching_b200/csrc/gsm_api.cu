@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -292,10 +293,12 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
                      int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
                      int end_) {
   constexpr int K = 16;
-  const int runs = 12;
+  static const int runs_env = getenv("GSM_GF_RUNS") ? atoi(getenv("GSM_GF_RUNS")) : 0;
+  const int runs = (runs_env >= 4 && runs_env <= 12) ? runs_env : 12;  // 12 warps x 16 columns per CTA
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, 2 * R, 6, HL4);
+  pl.smem = gf_smem_bytes(runs, K, HL4);
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
   pl.g.export_nd = end_;

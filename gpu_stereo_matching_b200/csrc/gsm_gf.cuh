@@ -28,6 +28,9 @@ namespace gsm {
 constexpr int GF_STAT_PLANES = 7;
 enum { ST_N = 0, ST_SI = 1, ST_INVDEN = 2, ST_CMEAN = 3, ST_INVN = 4, ST_IC = 5, ST_COEF = 6 };
 constexpr float GF_CENTRE = 128.0f;
+#ifndef GSM_GF_FRESH
+#define GSM_GF_FRESH 0  // 1: add-only shadow accumulators swapped in every 2R+1 rows (bounds stage-2 drift; ~15% slower)
+#endif
 
 // N, S_I, 1/(N*S_II - S_I^2 + eps*N^2), S_I/N - 128, 1/N, I - 128 for every image pixel.
 constexpr int GS_T = 32;
@@ -162,31 +165,122 @@ __device__ __forceinline__ void slide_f32(const u32 (&win)[HL4 + K + HL4], float
   }
 }
 
-template <int K>
-__device__ __forceinline__ void ad_row(const u8* gbase, const u32* obase, u32 osel, size_t ro, u32 (&p)[K / 4]) {
-  u32 gw[K / 4], ow[K / 4];
-  load_aligned<K>(gbase + ro, gw);
-  load_unaligned<K>(reinterpret_cast<const u32*>(reinterpret_cast<const u8*>(obase) + ro), osel, ow);
-#pragma unroll
-  for (int w = 0; w < K / 4; ++w) p[w] = __vabsdiffu4(gw[w], ow[w]);
+// ---- asynchronous row staging (cp.async.bulk == TMA 1-D, completion on an mbarrier) -------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  u32 done;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 
-// a, b of one row from the exact stage-1 sums and the guide statistics of that row
+// Shared-memory stage holding every global input of ONE march step for the CTA's strip (TWt columns):
+//   G[3][TWt] u8        guide rows   t+R, t-R-1, t-3R-2
+//   O[3][TWt+64] u8     other-image rows, shifted window covering the CTA's 32 disparities
+//   COEF[2][TWt] i32    IDP.2A coefficient rows t, t-2R-1
+//   ST[2][5][TWt]       N, S_I, 1/den, mean_I-128, 1/N at rows t (lead) and t-2R-1 (trail)
+//   ICY[TWt], INVNY[TWt] f32   I-128 and 1/N at the output row t-R
+struct GfStage {
+  int TWt, OW;
+  int off_O, off_COEF, off_ST, off_ICY, off_INVNY, bytes;
+  __host__ __device__ explicit GfStage(int twt) {
+    TWt = twt;
+    OW = twt + 64;
+    off_O = 3 * TWt;
+    off_COEF = off_O + 3 * OW;
+    off_ST = off_COEF + 2 * 4 * TWt;
+    off_ICY = off_ST + 10 * 4 * TWt;
+    off_INVNY = off_ICY + 4 * TWt;
+    bytes = off_INVNY + 4 * TWt;
+  }
+};
+
+__host__ __device__ inline size_t gf_smem_bytes(int runs, int K, int HL4) {
+  return 64 + 2 * (size_t)GfStage(runs * K).bytes + 6 * (size_t)WARP * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+}
+
+// K bytes at byte offset `off` (any alignment) of a shared-memory row
 template <int K>
-__device__ __forceinline__ void ab_row(const float* srow, size_t plane_elems, const int (&Sp)[K], const int (&SIp)[K],
-                                       float (&a)[K], float (&b)[K]) {
-  int N[K], SI[K];
-  float invden[K], cmean[K], invn[K];
-  load_i32x<K>(reinterpret_cast<const int*>(srow + ST_N * plane_elems), N);
-  load_i32x<K>(reinterpret_cast<const int*>(srow + ST_SI * plane_elems), SI);
-  load_f32x<K>(srow + ST_INVDEN * plane_elems, invden);
-  load_f32x<K>(srow + ST_CMEAN * plane_elems, cmean);
-  load_f32x<K>(srow + ST_INVN * plane_elems, invn);
+__device__ __forceinline__ void lds_unaligned(const u8* row, int off, u32 (&w)[K / 4]) {
+  const u32* pa = reinterpret_cast<const u32*>(row + (off & ~3));
+  const u32 sel = 0x3210u + 0x1111u * (u32)(off & 3);
+  u32 t[K / 4 + 1];
 #pragma unroll
-  for (int c = 0; c < K; ++c) {
-    const int num = N[c] * SIp[c] - SI[c] * Sp[c];  // exact modulo 2^32, true value fits int32 for r <= 9
-    a[c] = (float)num * invden[c];
-    b[c] = fmaf(-a[c], cmean[c], (float)Sp[c] * invn[c]);  // mean_p - a * (mean_I - 128)
+  for (int i = 0; i <= K / 4; ++i) t[i] = pa[i];
+#pragma unroll
+  for (int i = 0; i < K / 4; ++i) w[i] = __byte_perm(t[i], t[i + 1], sel);
+}
+
+template <int K>
+__device__ __forceinline__ void ad_row_s(const u8* grow, const u8* orow, int ooff, u32 (&p)[K / 4]) {
+  u32 ow[K / 4];
+  lds_unaligned<K>(orow, ooff, ow);
+#pragma unroll
+  for (int w = 0; w < K / 4; w += 4) {
+    const uint4 gq = *reinterpret_cast<const uint4*>(grow + 4 * w);
+    p[w] = __vabsdiffu4(gq.x, ow[w]);
+    p[w + 1] = __vabsdiffu4(gq.y, ow[w + 1]);
+    p[w + 2] = __vabsdiffu4(gq.z, ow[w + 2]);
+    p[w + 3] = __vabsdiffu4(gq.w, ow[w + 3]);
+  }
+}
+
+// One (a, b) row: slide the two exact stage-1 sums across the thread's K columns and fold
+// SIGN * (a, b) into the stage-2 vertical running sums.  st = staged statistics of that row for this thread.
+template <int R, int K, int HL4, int SIGN>
+__device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const int (&Vp)[K], const int (&VIp)[K],
+                                        const float* st, int TWt, float (&VA)[K], float (&VB)[K],
+                                        float (&VAf)[K], float (&VBf)[K]) {
+  int Sp[K];
+  {
+    u32 win[HL4 + K + HL4];
+    exch_window<K, HL4>(xbP, reinterpret_cast<const u32(&)[K]>(Vp), win);
+    slide_i32<R, K, HL4>(win, Sp);
+  }
+  u32 win[HL4 + K + HL4];
+  exch_window<K, HL4>(xbI, reinterpret_cast<const u32(&)[K]>(VIp), win);
+  int s = 0;
+#pragma unroll
+  for (int j = -R; j <= R; ++j) s += (int)win[HL4 + j];
+#pragma unroll
+  for (int g4 = 0; g4 < K; g4 += 4) {
+    const int4 N = *reinterpret_cast<const int4*>(st + ST_N * TWt + g4);
+    const int4 SI = *reinterpret_cast<const int4*>(st + ST_SI * TWt + g4);
+    const float4 invden = *reinterpret_cast<const float4*>(st + ST_INVDEN * TWt + g4);
+    const float4 cmean = *reinterpret_cast<const float4*>(st + ST_CMEAN * TWt + g4);
+    const float4 invn = *reinterpret_cast<const float4*>(st + ST_INVN * TWt + g4);
+    const int Nn[4] = {N.x, N.y, N.z, N.w}, SIi[4] = {SI.x, SI.y, SI.z, SI.w};
+    const float idn[4] = {invden.x, invden.y, invden.z, invden.w}, cm[4] = {cmean.x, cmean.y, cmean.z, cmean.w},
+                inn[4] = {invn.x, invn.y, invn.z, invn.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = g4 + j;
+      if (c > 0) s += (int)win[HL4 + c + R] - (int)win[HL4 + c - R - 1];
+      const int num = Nn[j] * s - SIi[j] * Sp[c];  // exact modulo 2^32; true value fits int32 for r <= 9
+      const float a = (float)num * idn[j];
+      const float b = fmaf(-a, cm[j], (float)Sp[c] * inn[j]);  // mean_p - a * (mean_I - 128)
+      if (SIGN > 0) {
+        VA[c] += a; VB[c] += b;
+        if (GSM_GF_FRESH) { VAf[c] += a; VBf[c] += b; }
+      } else {
+        VA[c] -= a; VB[c] -= b;
+      }
+    }
   }
 }
 
@@ -196,13 +290,14 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
               i64* __restrict__ keys, FusedGeom g) {
   constexpr int HL4 = (R + 3) / 4 * 4;
   constexpr int KW = K / 4;
-  extern __shared__ __align__(16) u32 smem[];
+  extern __shared__ __align__(128) u8 smem_raw[];
 
   const int lane = threadIdx.x;
   const int run = threadIdx.y;
   const int runs = blockDim.y;
   const int strip = blockIdx.x;
-  const int d = g.d_begin + blockIdx.y * WARP + lane;
+  const int d0 = g.d_begin + blockIdx.y * WARP;
+  const int d = d0 + lane;
   const int frame = blockIdx.z / g.bands;
   const int band = blockIdx.z - frame * g.bands;
   const int H = g.pg.H, W = g.pg.W, pitch = g.pg.pitch;
@@ -210,25 +305,65 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   const int yb1 = min(H, yb0 + g.band_rows);
   if (yb0 >= H) return;
 
+  const int TWt = runs * K;
+  const GfStage sg(TWt);
   const int pitchw = exch_pitch_words(runs, K, HL4);
   const int planew = WARP * pitchw;
-  for (int i = threadIdx.y * WARP + threadIdx.x; i < 6 * planew; i += runs * WARP) smem[i] = 0u;
+  u8* stage_base = smem_raw + 64;
+  u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);
+  const u32 bar0 = smem_u32(smem_raw);  // two 8-byte mbarriers at the start of shared memory
+  const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
+
+  for (int i = threadIdx.y * WARP + threadIdx.x; i < 6 * planew; i += runs * WARP) exch[i] = 0u;
+  if (producer) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  u32* xb = smem + (size_t)lane * pitchw + HL4 + run * K;  // this thread's slot in exchange plane 0
+  u32* xb = exch + (size_t)lane * pitchw + HL4 + run * K;  // this thread's slot in exchange plane 0
 
-  const int x0 = strip * g.TW - g.hl + run * K;
-  const int dd = min(d, MAX_DISP - 1);
-  const int osh = (g.view == 0) ? -dd : dd;
+  const int xs = strip * g.TW - g.hl;  // image column of the strip's first (halo) column
+  const int x0 = xs + run * K;
   const size_t plane_elems = g.pg.plane_stride;
-  const size_t org = (size_t)PADV * pitch + g.pg.xoff + x0;  // (row 0, column x0) inside a padded plane
-  const u8* gbase = Gp + (size_t)frame * g.pg.plane_stride + org;
-  const u8* obase_b = Op + (size_t)frame * g.pg.plane_stride + org + osh;
-  const u32 omis = (u32)(reinterpret_cast<uintptr_t>(obase_b) & 3u);
-  const u32* obase = reinterpret_cast<const u32*>(obase_b - omis);
-  const u32 osel = 0x3210u + 0x1111u * omis;
-  const float* sbase = stats + (size_t)frame * GF_STAT_PLANES * plane_elems + org;
-  const int* coefbase = reinterpret_cast<const int*>(sbase + ST_COEF * plane_elems);
+  const int row_lo = -PADV, row_hi = H + PADV - 1;
 
+  // producer-side source addresses (row 0 of the padded planes, strip column xs)
+  const size_t org = (size_t)PADV * pitch + g.pg.xoff + xs;
+  const u8* gsrc = Gp + (size_t)frame * g.pg.plane_stride + org;
+  const int ostart = g.pg.xoff + xs + (g.view == 0 ? -(d0 + 31) : d0);  // byte column of the staged O window
+  const int oalign = ostart & 15;
+  const u8* osrc = Op + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + (ostart - oalign);
+  const float* ssrc = stats + (size_t)frame * GF_STAT_PLANES * plane_elems + org;
+  // consumer-side byte offset of this thread's first pixel inside a staged O row
+  const int ooff = oalign + run * K + (g.view == 0 ? (31 - lane) : lane);
+
+  auto issue = [&](int t, int s) {
+    const u32 bar = bar0 + 8 * s;
+    const u32 dst = smem_u32(stage_base + (size_t)s * sg.bytes);
+    mbar_expect_tx(bar, (u32)sg.bytes);
+    const int rows3[3] = {t + R, t - R - 1, t - 3 * R - 2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const long long ro = (long long)max(row_lo, min(row_hi, rows3[i])) * pitch;
+      bulk_g2s(dst + i * TWt, gsrc + ro, TWt, bar);
+      bulk_g2s(dst + sg.off_O + i * sg.OW, osrc + ro, sg.OW, bar);
+    }
+    const int rows2[2] = {t, t - 2 * R - 1};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long ro = (long long)max(row_lo, min(row_hi, rows2[i])) * pitch;
+      bulk_g2s(dst + sg.off_COEF + i * 4 * TWt, ssrc + ST_COEF * plane_elems + ro, 4 * TWt, bar);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        bulk_g2s(dst + sg.off_ST + (i * 5 + k) * 4 * TWt, ssrc + (size_t)k * plane_elems + ro, 4 * TWt, bar);
+    }
+    const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
+    bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
+    bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
+  };
+
+  const int dd = min(d, MAX_DISP - 1);
   u32 mask[KW];
   bool full = true;
 #pragma unroll
@@ -252,47 +387,70 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   const bool all_valid = __all_sync(0xffffffffu, c_lo == 0 && c_hi == K - 1);
 
   int Vp_l[K], VIp_l[K], Vp_t[K], VIp_t[K];
-  float VA[K], VB[K];
+  // Stage-2 vertical sums.  VA/VB are add/subtract running sums; VAf/VBf only ever add and are swapped in every
+  // 2R+1 rows, when they hold exactly the current window: rounding drift is bounded by 2(2R+1) additions
+  // instead of growing with the image height.
+  float VA[K], VB[K], VAf[K], VBf[K];
 #pragma unroll
-  for (int c = 0; c < K; ++c) { Vp_l[c] = VIp_l[c] = Vp_t[c] = VIp_t[c] = 0; VA[c] = VB[c] = 0.f; }
+  for (int c = 0; c < K; ++c) {
+    Vp_l[c] = VIp_l[c] = Vp_t[c] = VIp_t[c] = 0;
+    VA[c] = VB[c] = VAf[c] = VBf[c] = 0.f;
+  }
+  int fresh_cnt = 0;
 
   const int r0 = yb0 - 2 * R;  // first image row whose AD may enter a stage-1 window of this band
   const int a0 = yb0 - R;      // first row whose (a, b) may enter a stage-2 window of this band
   constexpr int COEF_PM = (int)0xFFFF0001;  // lo16 = +1, hi16 = -1
-  const int row_lo = -PADV, row_hi = H + PADV - 1;
+  const int t_begin = yb0 - 3 * R, t_end = yb1 + R;
 
-  for (int t = yb0 - 3 * R; t < yb1 + R; ++t) {
-    // ---------------- stage 1, vertical: rows t+R (enters lead), t-R-1 (lead -> trail), t-3R-2 (leaves trail)
+  if (producer) issue(t_begin, 0);
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int it = t - t_begin;
+    const int s = it & 1;
+    // prefetch the next step's rows into the other stage (its previous contents were last read before the
+    // second __syncthreads of the previous step)
+    if (producer && t + 1 < t_end) issue(t + 1, s ^ 1);
+    mbar_wait(bar0 + 8 * s, (u32)((it >> 1) & 1));
+    const u8* stg = stage_base + (size_t)s * sg.bytes;
     const int t2 = t - 2 * R - 1;  // row of (a, b) recomputed by the trail pipeline
-    u32 pn[KW], pm[KW], po[KW];
-    ad_row<K>(gbase, obase, osel, (size_t)((long long)(t + R) * pitch), pn);
-    if (t - R - 1 >= r0) ad_row<K>(gbase, obase, osel, (size_t)((long long)(t - R - 1) * pitch), pm);
-    else {
-#pragma unroll
-      for (int w = 0; w < KW; ++w) pm[w] = 0u;
-    }
-    if (t - 3 * R - 2 >= r0) ad_row<K>(gbase, obase, osel, (size_t)((long long)(t - 3 * R - 2) * pitch), po);
-    else {
-#pragma unroll
-      for (int w = 0; w < KW; ++w) po[w] = 0u;
-    }
-    if (need_mask) {
-#pragma unroll
-      for (int w = 0; w < KW; ++w) { pn[w] &= mask[w]; pm[w] &= mask[w]; po[w] &= mask[w]; }
-    }
+
+    // ---------------- stage 1, vertical: rows t+R (enters lead), t-R-1 (lead -> trail), t-3R-2 (leaves trail)
     {
-      int cA[K], cB[K];
-      load_i32x<K>(coefbase + (long long)max(row_lo, min(row_hi, t)) * pitch, cA);
-      load_i32x<K>(coefbase + (long long)max(row_lo, min(row_hi, t2)) * pitch, cB);
+      u32 pn[KW], pm[KW], po[KW];
+      ad_row_s<K>(stg + run * K, stg + sg.off_O, ooff, pn);
+      if (t - R - 1 >= r0) ad_row_s<K>(stg + TWt + run * K, stg + sg.off_O + sg.OW, ooff, pm);
+      else {
 #pragma unroll
-      for (int c = 0; c < K; ++c) {
-        const u32 sel = (c & 3) | ((4 + (c & 3)) << 4);
-        const u32 nm = __byte_perm(pn[c / 4], pm[c / 4], sel);  // {p_enter, p_leave, x, x}
-        const u32 mo = __byte_perm(pm[c / 4], po[c / 4], sel);
-        Vp_l[c] = dp2a_lo_su(COEF_PM, nm, Vp_l[c]);
-        VIp_l[c] = dp2a_lo_su(cA[c], nm, VIp_l[c]);
-        Vp_t[c] = dp2a_lo_su(COEF_PM, mo, Vp_t[c]);
-        VIp_t[c] = dp2a_lo_su(cB[c], mo, VIp_t[c]);
+        for (int w = 0; w < KW; ++w) pm[w] = 0u;
+      }
+      if (t - 3 * R - 2 >= r0) ad_row_s<K>(stg + 2 * TWt + run * K, stg + sg.off_O + 2 * sg.OW, ooff, po);
+      else {
+#pragma unroll
+        for (int w = 0; w < KW; ++w) po[w] = 0u;
+      }
+      if (need_mask) {
+#pragma unroll
+        for (int w = 0; w < KW; ++w) { pn[w] &= mask[w]; pm[w] &= mask[w]; po[w] &= mask[w]; }
+      }
+      const int* cA = reinterpret_cast<const int*>(stg + sg.off_COEF) + run * K;
+      const int* cB = cA + TWt;
+#pragma unroll
+      for (int g4 = 0; g4 < K; g4 += 4) {
+        const int4 a4 = *reinterpret_cast<const int4*>(cA + g4);
+        const int4 b4 = *reinterpret_cast<const int4*>(cB + g4);
+        const int ca[4] = {a4.x, a4.y, a4.z, a4.w}, cb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = g4 + j;
+          const u32 sel = j | ((4 + j) << 4);
+          const u32 nm = __byte_perm(pn[c / 4], pm[c / 4], sel);  // {p_enter, p_leave, x, x}
+          const u32 mo = __byte_perm(pm[c / 4], po[c / 4], sel);
+          Vp_l[c] = dp2a_lo_su(COEF_PM, nm, Vp_l[c]);
+          VIp_l[c] = dp2a_lo_su(ca[j], nm, VIp_l[c]);
+          Vp_t[c] = dp2a_lo_su(COEF_PM, mo, Vp_t[c]);
+          VIp_t[c] = dp2a_lo_su(cb[j], mo, VIp_t[c]);
+        }
       }
     }
     // ---------------- stage 1, horizontal
@@ -301,34 +459,15 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     exch_store<K, HL4>(xb + 2 * planew, reinterpret_cast<u32(&)[K]>(Vp_t));
     exch_store<K, HL4>(xb + 3 * planew, reinterpret_cast<u32(&)[K]>(VIp_t));
     __syncthreads();
-    float al[K], bl[K];
-    if (t >= a0) {
-      int Sp[K], SIp[K];
-      u32 win[HL4 + K + HL4];
-      exch_window<K, HL4>(xb + 0 * planew, reinterpret_cast<u32(&)[K]>(Vp_l), win);
-      slide_i32<R, K, HL4>(win, Sp);
-      exch_window<K, HL4>(xb + 1 * planew, reinterpret_cast<u32(&)[K]>(VIp_l), win);
-      slide_i32<R, K, HL4>(win, SIp);
-      ab_row<K>(sbase + (long long)t * pitch, plane_elems, Sp, SIp, al, bl);
-    } else {
+    const float* st_l = reinterpret_cast<const float*>(stg + sg.off_ST) + run * K;
+    if (t >= a0) fold_ab<R, K, HL4, +1>(xb + 0 * planew, xb + 1 * planew, Vp_l, VIp_l, st_l, TWt, VA, VB, VAf, VBf);
+    if (t2 >= a0)
+      fold_ab<R, K, HL4, -1>(xb + 2 * planew, xb + 3 * planew, Vp_t, VIp_t, st_l + 5 * TWt, TWt, VA, VB, VAf, VBf);
+    if (GSM_GF_FRESH && t >= a0 && ++fresh_cnt == 2 * R + 1) {
+      fresh_cnt = 0;
 #pragma unroll
-      for (int c = 0; c < K; ++c) al[c] = bl[c] = 0.f;
+      for (int c = 0; c < K; ++c) { VA[c] = VAf[c]; VB[c] = VBf[c]; VAf[c] = 0.f; VBf[c] = 0.f; }
     }
-    if (t2 >= a0) {
-      int Sp[K], SIp[K];
-      float at[K], bt[K];
-      u32 win[HL4 + K + HL4];
-      exch_window<K, HL4>(xb + 2 * planew, reinterpret_cast<u32(&)[K]>(Vp_t), win);
-      slide_i32<R, K, HL4>(win, Sp);
-      exch_window<K, HL4>(xb + 3 * planew, reinterpret_cast<u32(&)[K]>(VIp_t), win);
-      slide_i32<R, K, HL4>(win, SIp);
-      ab_row<K>(sbase + (long long)t2 * pitch, plane_elems, Sp, SIp, at, bt);
-#pragma unroll
-      for (int c = 0; c < K; ++c) { al[c] -= at[c]; bl[c] -= bt[c]; }
-    }
-    // ---------------- stage 2, vertical
-#pragma unroll
-    for (int c = 0; c < K; ++c) { VA[c] += al[c]; VB[c] += bl[c]; }
 
     const int y = t - R;  // output row
     if (y >= yb0) {
@@ -347,14 +486,17 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
       exch_window<K, HL4>(xb + 5 * planew, reinterpret_cast<u32(&)[K]>(VB), win);
       slide_f32<R, K, HL4>(win, B);
     }
-    float ic[K], invn[K];
-    load_f32x<K>(sbase + ST_IC * plane_elems + (long long)y * pitch, ic);
-    load_f32x<K>(sbase + ST_INVN * plane_elems + (long long)y * pitch, invn);
-    u32 key[K];
+    const float* icy = reinterpret_cast<const float*>(stg + sg.off_ICY) + run * K;
+    const float* iny = reinterpret_cast<const float*>(stg + sg.off_INVNY) + run * K;
+    int key[K];  // signed order == float order
 #pragma unroll
-    for (int c = 0; c < K; ++c) {
-      const float q = fmaf(A[c], ic[c], B[c]) * invn[c];
-      key[c] = (u32)sortable_i32(q) ^ 0x80000000u;  // unsigned order == float order
+    for (int g4 = 0; g4 < K; g4 += 4) {
+      const float4 ic = *reinterpret_cast<const float4*>(icy + g4);
+      const float4 in = *reinterpret_cast<const float4*>(iny + g4);
+      key[g4 + 0] = sortable_i32(fmaf(A[g4 + 0], ic.x, B[g4 + 0]) * in.x);
+      key[g4 + 1] = sortable_i32(fmaf(A[g4 + 1], ic.y, B[g4 + 1]) * in.y);
+      key[g4 + 2] = sortable_i32(fmaf(A[g4 + 2], ic.z, B[g4 + 2]) * in.z);
+      key[g4 + 3] = sortable_i32(fmaf(A[g4 + 3], ic.w, B[g4 + 3]) * in.w);
     }
     if constexpr (EXPORT) {
       const int de = d - g.export_d0;
@@ -363,25 +505,27 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
 #pragma unroll
         for (int c = 0; c < K; ++c) {
           const int x = x0 + c;
-          if (x >= out0 && x < min(out0 + g.TW, W)) out[x] = unsortable_f32((int)(key[c] ^ 0x80000000u));
+          if (x >= out0 && x < min(out0 + g.TW, W)) out[x] = unsortable_f32(key[c]);
         }
       }
     }
+    // WTA over the warp's 32 disparities: the lane index rides in the 5 low bits of the sortable key, so one
+    // REDUX gives both the minimum and (lowest-d-first) its owner; costs closer than 2^-18 relative count as ties.
+#pragma unroll
+    for (int c = 0; c < K; ++c) key[c] = (key[c] & ~31) | lane;
     if (!all_valid) {
 #pragma unroll
       for (int c = 0; c < K; ++c)
-        if (c < c_lo || c > c_hi) key[c] = 0xffffffffu;
+        if (c < c_lo || c > c_hi) key[c] = 0x7fffffff;
     }
-    u32 mine = 0xffffffffu;
-    int mine_d = 0;
+    int mine = 0x7fffffff;
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      const u32 m = __reduce_min_sync(0xffffffffu, key[c]);
-      const u32 who = __ballot_sync(0xffffffffu, key[c] == m);  // strict '<': the lowest d among equal costs wins
-      if (lane == c) { mine = m; mine_d = d - lane + (__ffs(who) - 1); }
+      const int m = __reduce_min_sync(0xffffffffu, key[c]);
+      if (lane == c) mine = m;
     }
-    if (lane < K && mine != 0xffffffffu) {
-      const i64 k64 = (i64)(((unsigned long long)(mine ^ 0x80000000u) << 32) | (u32)mine_d);
+    if (lane < K && mine != 0x7fffffff) {
+      const i64 k64 = (i64)(((unsigned long long)(u32)(mine & ~31) << 32) | (u32)(d0 + (mine & 31)));
       atomicMin(keys + ((size_t)frame * H + y) * W + x0 + lane, k64);
     }
   }
