@@ -34,7 +34,10 @@ static int fail(int code, const char* fmt, ...) {
 struct gsm_ctx {
   int device = 0;
   int max_rows = 0, max_cols = 0, max_disp = 0, max_batch = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;                 // compute
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // host path: uploads / downloads overlap the kernels
+  cudaEvent_t ev_h2d[2] = {}, ev_in_free[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
+  int slot_frames = 1;                             // frames per host-path slot (two slots)
   // device buffers, each sized for max_batch frames
   u8 *tightL = nullptr, *tightR = nullptr;                       // uploads on the host path
   u8 *planeL = nullptr, *planeR = nullptr, *planeLrep = nullptr;  // padded planes
@@ -80,6 +83,14 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+    if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+  }
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -118,8 +129,18 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
     if (st == cudaSuccess) st = cudaMemset(*p, 0, bytes);
   };
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) st = cudaErrorUnknown;
-  A((void**)&c->tightL, px);
-  A((void**)&c->tightR, px);
+  if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) st = cudaErrorUnknown;
+  if (cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) st = cudaErrorUnknown;
+  for (int i = 0; i < 2 && st == cudaSuccess; ++i) {
+    st = cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming);
+    if (st == cudaSuccess) st = cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming);
+    if (st == cudaSuccess) st = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+    if (st == cudaSuccess) st = cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming);
+  }
+  c->slot_frames = (max_batch + 1) / 2;
+  const size_t slot_px = (size_t)max_rows * max_cols * c->slot_frames * 2;  // two host-path slots
+  A((void**)&c->tightL, slot_px);
+  A((void**)&c->tightR, slot_px);
   A((void**)&c->planeL, plane);
   A((void**)&c->planeR, plane);
   A((void**)&c->planeLrep, plane);
@@ -131,8 +152,8 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
   A((void**)&c->dispB, px);
   A((void**)&c->dispC, px);
   A((void**)&c->dispD, px);
-  A((void**)&c->maskD, px);
-  A((void**)&c->dispOut, px);
+  A((void**)&c->maskD, slot_px);
+  A((void**)&c->dispOut, slot_px);
   A((void**)&c->peak_buf, (size_t)prop.multiProcessorCount * 8 * 256 * sizeof(u32));
   if (st != cudaSuccess) {
     int rc = fail(GSM_ERR_CUDA, "gsm_create: allocation failed: %s", cudaGetErrorString(st));
@@ -318,6 +339,8 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     c->launches++;
     gf_coef_kernel<<<dim3((cols + 255) / 256, rows + 2 * R + 1, n), 256, 0, s>>>(G, stats, pg, R);
     c->launches++;
+    gf_centre_kernel<<<dim3((pg.pitch / 16 + 63) / 64, rows, n), 64, 0, s>>>(stats, pg);
+    c->launches++;
     CK(cudaGetLastError());
   }
   int rc;
@@ -471,21 +494,39 @@ extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const ui
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const size_t fpx = (size_t)rows * cols;
-  for (int f0 = 0; f0 < n; f0 += c->max_batch) {
-    const int nb = std::min(c->max_batch, n - f0);
-    CK(cudaMemcpyAsync(c->tightL, left + f0 * fpx, nb * fpx, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->tightR, right + f0 * fpx, nb * fpx, cudaMemcpyHostToDevice, s));
-    u8* dres = c->dispOut;
-    if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 0, c->tightL, c->tightR, c->keysL, s))) return rc;
+  const size_t slot_stride = (size_t)c->max_rows * c->max_cols * c->slot_frames;
+  const bool want_mask = mask && p->lr_check;
+  c->ev_used = 0;
+  // Two slots of input / output buffers: while the kernels of chunk i run on the compute stream, chunk i+1 is
+  // uploaded and chunk i-1 downloaded on their own streams (asynchronous when the host buffers are pinned).
+  int chunk = 0;
+  for (int f0 = 0; f0 < n; f0 += c->slot_frames, ++chunk) {
+    const int nb = std::min(c->slot_frames, n - f0);
+    const int slot = chunk & 1;
+    u8* tl = c->tightL + slot * slot_stride;
+    u8* tr = c->tightR + slot * slot_stride;
+    u8* dres = c->dispOut + slot * slot_stride;
+    u8* mres = c->maskD + slot * slot_stride;
+    if (chunk >= 2) CK(cudaStreamWaitEvent(c->s_h2d, c->ev_in_free[slot], 0));
+    CK(cudaMemcpyAsync(tl, left + f0 * fpx, nb * fpx, cudaMemcpyHostToDevice, c->s_h2d));
+    CK(cudaMemcpyAsync(tr, right + f0 * fpx, nb * fpx, cudaMemcpyHostToDevice, c->s_h2d));
+    CK(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
+    CK(cudaStreamWaitEvent(s, c->ev_h2d[slot], 0));
+    if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 0, tl, tr, c->keysL, s))) return rc;
     if (p->lr_check)
-      if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 1, c->tightL, c->tightR, c->keysR, s)))
-        return rc;
+      if ((rc = run_view_keys(c, p, nb, rows, cols, d_begin, d_end, eps, 1, tl, tr, c->keysR, s))) return rc;
+    CK(cudaEventRecord(c->ev_in_free[slot], s));
+    if (chunk >= 2) CK(cudaStreamWaitEvent(s, c->ev_d2h[slot], 0));
     if ((rc = finalize_views(c, p, nb, rows, cols, c->keysL, p->lr_check ? c->keysR : nullptr, dres,
-                             (mask && p->lr_check) ? c->maskD : nullptr, s)))
+                             want_mask ? mres : nullptr, s)))
       return rc;
-    CK(cudaMemcpyAsync(disparity + f0 * fpx, dres, nb * fpx, cudaMemcpyDeviceToHost, s));
-    if (mask && p->lr_check) CK(cudaMemcpyAsync(mask + f0 * fpx, c->maskD, nb * fpx, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(c->ev_done[slot], s));
+    CK(cudaStreamWaitEvent(c->s_d2h, c->ev_done[slot], 0));
+    CK(cudaMemcpyAsync(disparity + f0 * fpx, dres, nb * fpx, cudaMemcpyDeviceToHost, c->s_d2h));
+    if (want_mask) CK(cudaMemcpyAsync(mask + f0 * fpx, mres, nb * fpx, cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
   }
+  CK(cudaStreamSynchronize(c->s_d2h));
   CK(cudaStreamSynchronize(s));
   return GSM_OK;
 }

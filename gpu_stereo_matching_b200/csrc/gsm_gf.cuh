@@ -15,7 +15,12 @@
 //            removes the leaving row), exchanged through shared memory, horizontal sliding sums with IADD3;
 //            the numerator N*S_Ip - S_I*S_p is evaluated modulo 2^32, exact because |N^2 cov| < 2^31 for r <= 9.
 //   stage 2 (fp32):  a, b per pixel; vertical running sums V_a, V_b; exchange; horizontal sliding sums; q.
-//            b is formed against the centred guide (I - 128) so the stage-2 sums are ~2x smaller.
+//            b is formed against a LOCAL centre: b' = mean_p - a*(mean_I - c_run), c_run = rounded local mean of the
+//            guide over the thread's 16-column run, re-centred (VB += dc*VA, exact identity) when it drifts by more
+//            than GF_RECENTRE grey levels.  q = (A*(I - c_run) + B')/N is independent of c in exact arithmetic, but
+//            with c near the local intensities the two terms no longer cancel, which is what fp32 needs to stay
+//            within 1e-4 of the float64 oracle.  Halo columns owned by neighbour runs (different centres) are
+//            converted through the partial sums A_L, A_R of the window: B' += (c_own - c_nbr) * A_{L|R}.
 //   WTA:     warp min over the 32 disparities of a run (REDUX on the sortable bit pattern, ballot for the
 //            lowest d among equals), one 64-bit atomicMin per pixel into the packed-min plane.
 #pragma once
@@ -25,9 +30,10 @@
 namespace gsm {
 
 // guide statistic planes (float/int32, same padded geometry as the u8 planes; zero outside the image)
-constexpr int GF_STAT_PLANES = 7;
-enum { ST_N = 0, ST_SI = 1, ST_INVDEN = 2, ST_CMEAN = 3, ST_INVN = 4, ST_IC = 5, ST_COEF = 6 };
+constexpr int GF_STAT_PLANES = 8;
+enum { ST_N = 0, ST_SI = 1, ST_INVDEN = 2, ST_CMEAN = 3, ST_INVN = 4, ST_IC = 5, ST_COEF = 6, ST_CEN = 7 };
 constexpr float GF_CENTRE = 128.0f;
+constexpr float GF_RECENTRE = 8.0f;
 #ifndef GSM_GF_FRESH
 #define GSM_GF_FRESH 0  // 1: add-only shadow accumulators swapped in every 2R+1 rows (bounds stage-2 drift; ~15% slower)
 #endif
@@ -101,6 +107,27 @@ __global__ void gf_coef_kernel(const u8* __restrict__ Ip, float* __restrict__ st
   const int out = p[(size_t)(PADV + t - R - 1) * pg.pitch];
   int* coef = reinterpret_cast<int*>(stats + ((size_t)f * GF_STAT_PLANES + ST_COEF) * pg.plane_stride);
   coef[(size_t)(PADV + t) * pg.pitch + pg.xoff + x] = in - 65536 * out;
+}
+
+// Local centre plane: for every image row and every 16-column block of the padded grid (the blocks the fused
+// kernel's runs are aligned to), the rounded mean of (mean_I - 128) over the block's in-image columns.  Stored 4x
+// replicated (one float per 4 columns) so that a strip's centres are a 16-byte aligned, contiguous run.
+__global__ void gf_centre_kernel(float* __restrict__ stats, PlaneGeom pg) {
+  const int blk = blockIdx.x * blockDim.x + threadIdx.x;  // 16-column block of the padded row
+  const int y = blockIdx.y;
+  const int f = blockIdx.z;
+  if (blk * 16 >= pg.pitch) return;
+  float* base = stats + (size_t)f * GF_STAT_PLANES * pg.plane_stride;
+  const float* cm = base + ST_CMEAN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + blk * 16;
+  float sum = 0.f;
+  int n = 0;
+  for (int i = 0; i < 16; ++i) {
+    const int x = blk * 16 + i - pg.xoff;
+    if (x >= 0 && x < pg.W) { sum += cm[i]; ++n; }
+  }
+  const float c = n ? rintf(sum / (float)n) : 0.f;
+  float* cen = base + ST_CEN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + blk * 4;
+  cen[0] = cen[1] = cen[2] = cen[3] = c;
 }
 
 template <int K>
@@ -195,9 +222,10 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
 //   COEF[2][TWt] i32    IDP.2A coefficient rows t, t-2R-1
 //   ST[2][5][TWt]       N, S_I, 1/den, mean_I-128, 1/N at rows t (lead) and t-2R-1 (trail)
 //   ICY[TWt], INVNY[TWt] f32   I-128 and 1/N at the output row t-R
+//   CEN[TWt/4] f32     local centre (mean_I - 128, rounded) of each 16-column run at the output row, 4x replicated
 struct GfStage {
   int TWt, OW;
-  int off_O, off_COEF, off_ST, off_ICY, off_INVNY, bytes;
+  int off_O, off_COEF, off_ST, off_ICY, off_INVNY, off_CEN, bytes;
   __host__ __device__ explicit GfStage(int twt) {
     TWt = twt;
     OW = twt + 64;
@@ -206,12 +234,13 @@ struct GfStage {
     off_ST = off_COEF + 2 * 4 * TWt;
     off_ICY = off_ST + 10 * 4 * TWt;
     off_INVNY = off_ICY + 4 * TWt;
-    bytes = off_INVNY + 4 * TWt;
+    off_CEN = off_INVNY + 4 * TWt;
+    bytes = off_CEN + TWt;
   }
 };
 
 __host__ __device__ inline size_t gf_smem_bytes(int runs, int K, int HL4) {
-  return 64 + 2 * (size_t)GfStage(runs * K).bytes + 6 * (size_t)WARP * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+  return 64 + 64 + 2 * (size_t)GfStage(runs * K).bytes + 6 * (size_t)WARP * exch_pitch_words(runs, K, HL4) * sizeof(u32);
 }
 
 // K bytes at byte offset `off` (any alignment) of a shared-memory row
@@ -224,6 +253,34 @@ __device__ __forceinline__ void lds_unaligned(const u8* row, int off, u32 (&w)[K
   for (int i = 0; i <= K / 4; ++i) t[i] = pa[i];
 #pragma unroll
   for (int i = 0; i < K / 4; ++i) w[i] = __byte_perm(t[i], t[i + 1], sel);
+}
+
+// Stage-2 horizontal pass.  winA / winB: [left halo HL4 | own K | right halo HL4].  The A window sum is kept as
+// three partial sums (columns owned by the left neighbour, by this run, by the right neighbour) because the
+// neighbours' B' sums are relative to THEIR centres: B'(x) = sum(winB) + dl * A_L(x) + dr * A_R(x).
+template <int R, int K, int HL4>
+__device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const u32 (&winB)[HL4 + K + HL4], float dl,
+                                         float dr, float (&A)[K], float (&B)[K]) {
+  static_assert(R < K, "window must not reach beyond the adjacent runs");
+  float aL = 0.f, aO = 0.f, aR = 0.f, b = 0.f;
+#pragma unroll
+  for (int j = -R; j <= R; ++j) {
+    const float va = __uint_as_float(winA[HL4 + j]);
+    if (j < 0) aL += va; else if (j < K) aO += va; else aR += va;
+    b += __uint_as_float(winB[HL4 + j]);
+  }
+  A[0] = (aL + aO) + aR;
+  B[0] = fmaf(dr, aR, fmaf(dl, aL, b));
+#pragma unroll
+  for (int c = 1; c < K; ++c) {
+    const int in = c + R, out = c - R - 1;
+    const float vin = __uint_as_float(winA[HL4 + in]), vout = __uint_as_float(winA[HL4 + out]);
+    if (in < K) aO += vin; else aR += vin;
+    if (out < 0) aL -= vout; else aO -= vout;
+    b = (b + __uint_as_float(winB[HL4 + in])) - __uint_as_float(winB[HL4 + out]);
+    A[c] = (aL + aO) + aR;
+    B[c] = fmaf(dr, aR, fmaf(dl, aL, b));
+  }
 }
 
 template <int K>
@@ -244,7 +301,7 @@ __device__ __forceinline__ void ad_row_s(const u8* grow, const u8* orow, int oof
 // SIGN * (a, b) into the stage-2 vertical running sums.  st = staged statistics of that row for this thread.
 template <int R, int K, int HL4, int SIGN>
 __device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const int (&Vp)[K], const int (&VIp)[K],
-                                        const float* st, int TWt, float (&VA)[K], float (&VB)[K],
+                                        const float* st, int TWt, float cc, float (&VA)[K], float (&VB)[K],
                                         float (&VAf)[K], float (&VBf)[K]) {
   int Sp[K];
   {
@@ -273,7 +330,7 @@ __device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const in
       if (c > 0) s += (int)win[HL4 + c + R] - (int)win[HL4 + c - R - 1];
       const int num = Nn[j] * s - SIi[j] * Sp[c];  // exact modulo 2^32; true value fits int32 for r <= 9
       const float a = (float)num * idn[j];
-      const float b = fmaf(-a, cm[j], (float)Sp[c] * inn[j]);  // mean_p - a * (mean_I - 128)
+      const float b = fmaf(-a, cm[j] - cc, (float)Sp[c] * inn[j]);  // mean_p - a * (mean_I - centre)
       if (SIGN > 0) {
         VA[c] += a; VB[c] += b;
         if (GSM_GF_FRESH) { VAf[c] += a; VBf[c] += b; }
@@ -309,7 +366,8 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   const GfStage sg(TWt);
   const int pitchw = exch_pitch_words(runs, K, HL4);
   const int planew = WARP * pitchw;
-  u8* stage_base = smem_raw + 64;
+  float* ccs = reinterpret_cast<float*>(smem_raw + 64);  // per-run centres of the current step (<= 16 runs)
+  u8* stage_base = smem_raw + 128;
   u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);
   const u32 bar0 = smem_u32(smem_raw);  // two 8-byte mbarriers at the start of shared memory
   const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
@@ -335,6 +393,8 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   const int oalign = ostart & 15;
   const u8* osrc = Op + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + (ostart - oalign);
   const float* ssrc = stats + (size_t)frame * GF_STAT_PLANES * plane_elems + org;
+  const float* csrc = stats + ((size_t)frame * GF_STAT_PLANES + ST_CEN) * plane_elems + (size_t)PADV * pitch +
+                      (g.pg.xoff + xs) / 4;  // 4x replicated centre plane: one float per 4 columns
   // consumer-side byte offset of this thread's first pixel inside a staged O row
   const int ooff = oalign + run * K + (g.view == 0 ? (31 - lane) : lane);
 
@@ -361,6 +421,7 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
     bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
     bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
+    bulk_g2s(dst + sg.off_CEN, csrc + ry, TWt, bar);
   };
 
   const int dd = min(d, MAX_DISP - 1);
@@ -397,6 +458,7 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     VA[c] = VB[c] = VAf[c] = VBf[c] = 0.f;
   }
   int fresh_cnt = 0;
+  float cc = 0.f;  // current centre of this run, relative to 128 (warp-uniform)
 
   const int r0 = yb0 - 2 * R;  // first image row whose AD may enter a stage-1 window of this band
   const int a0 = yb0 - R;      // first row whose (a, b) may enter a stage-2 window of this band
@@ -460,9 +522,23 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     exch_store<K, HL4>(xb + 3 * planew, reinterpret_cast<u32(&)[K]>(VIp_t));
     __syncthreads();
     const float* st_l = reinterpret_cast<const float*>(stg + sg.off_ST) + run * K;
-    if (t >= a0) fold_ab<R, K, HL4, +1>(xb + 0 * planew, xb + 1 * planew, Vp_l, VIp_l, st_l, TWt, VA, VB, VAf, VBf);
+    {
+      // follow the local intensity level: B'(c + dc) = B'(c) + dc * A exactly, applied to the running sums
+      const float target = reinterpret_cast<const float*>(stg + sg.off_CEN)[run * (K / 4)];
+      const float dc = target - cc;
+      if (fabsf(dc) > GF_RECENTRE) {
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          VB[c] = fmaf(dc, VA[c], VB[c]);
+          if (GSM_GF_FRESH) VBf[c] = fmaf(dc, VAf[c], VBf[c]);
+        }
+        cc = target;
+      }
+    }
+    if (t >= a0)
+      fold_ab<R, K, HL4, +1>(xb + 0 * planew, xb + 1 * planew, Vp_l, VIp_l, st_l, TWt, cc, VA, VB, VAf, VBf);
     if (t2 >= a0)
-      fold_ab<R, K, HL4, -1>(xb + 2 * planew, xb + 3 * planew, Vp_t, VIp_t, st_l + 5 * TWt, TWt, VA, VB, VAf, VBf);
+      fold_ab<R, K, HL4, -1>(xb + 2 * planew, xb + 3 * planew, Vp_t, VIp_t, st_l + 5 * TWt, TWt, cc, VA, VB, VAf, VBf);
     if (GSM_GF_FRESH && t >= a0 && ++fresh_cnt == 2 * R + 1) {
       fresh_cnt = 0;
 #pragma unroll
@@ -473,6 +549,7 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     if (y >= yb0) {
       exch_store<K, HL4>(xb + 4 * planew, reinterpret_cast<u32(&)[K]>(VA));
       exch_store<K, HL4>(xb + 5 * planew, reinterpret_cast<u32(&)[K]>(VB));
+      if (lane == 0) ccs[run] = cc;
     }
     __syncthreads();
     if (y < yb0) continue;
@@ -480,11 +557,12 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     // ---------------- stage 2, horizontal + q + WTA
     float A[K], B[K];
     {
-      u32 win[HL4 + K + HL4];
-      exch_window<K, HL4>(xb + 4 * planew, reinterpret_cast<u32(&)[K]>(VA), win);
-      slide_f32<R, K, HL4>(win, A);
-      exch_window<K, HL4>(xb + 5 * planew, reinterpret_cast<u32(&)[K]>(VB), win);
-      slide_f32<R, K, HL4>(win, B);
+      u32 winA[HL4 + K + HL4], winB[HL4 + K + HL4];
+      exch_window<K, HL4>(xb + 4 * planew, reinterpret_cast<u32(&)[K]>(VA), winA);
+      exch_window<K, HL4>(xb + 5 * planew, reinterpret_cast<u32(&)[K]>(VB), winB);
+      const float dl = run > 0 ? cc - ccs[run - 1] : 0.f;          // outer halos of the strip are zero pad
+      const float dr = run + 1 < runs ? cc - ccs[run + 1] : 0.f;
+      slide_ab<R, K, HL4>(winA, winB, dl, dr, A, B);
     }
     const float* icy = reinterpret_cast<const float*>(stg + sg.off_ICY) + run * K;
     const float* iny = reinterpret_cast<const float*>(stg + sg.off_INVNY) + run * K;
@@ -493,10 +571,10 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     for (int g4 = 0; g4 < K; g4 += 4) {
       const float4 ic = *reinterpret_cast<const float4*>(icy + g4);
       const float4 in = *reinterpret_cast<const float4*>(iny + g4);
-      key[g4 + 0] = sortable_i32(fmaf(A[g4 + 0], ic.x, B[g4 + 0]) * in.x);
-      key[g4 + 1] = sortable_i32(fmaf(A[g4 + 1], ic.y, B[g4 + 1]) * in.y);
-      key[g4 + 2] = sortable_i32(fmaf(A[g4 + 2], ic.z, B[g4 + 2]) * in.z);
-      key[g4 + 3] = sortable_i32(fmaf(A[g4 + 3], ic.w, B[g4 + 3]) * in.w);
+      key[g4 + 0] = sortable_i32(fmaf(A[g4 + 0], ic.x - cc, B[g4 + 0]) * in.x);
+      key[g4 + 1] = sortable_i32(fmaf(A[g4 + 1], ic.y - cc, B[g4 + 1]) * in.y);
+      key[g4 + 2] = sortable_i32(fmaf(A[g4 + 2], ic.z - cc, B[g4 + 2]) * in.z);
+      key[g4 + 3] = sortable_i32(fmaf(A[g4 + 3], ic.w - cc, B[g4 + 3]) * in.w);
     }
     if constexpr (EXPORT) {
       const int de = d - g.export_d0;

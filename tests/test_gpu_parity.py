@@ -30,9 +30,19 @@ def _gf_err(q, qref):
     return np.abs(q.astype(np.float64) - qref) / np.maximum(np.abs(qref), 1.0)
 
 
-def _disp_bar(a, b):
+def _disp_bar(a, b, qref=None):
+    """(fraction identical, # pixels off by more than 1).  With qref (float64 oracle costs [D][H][W]) a pixel
+    off by more than 1 is not counted when it is a genuine near-tie: the oracle's own costs of the two
+    disparities differ by less than the stated cost tolerance, so both answers are correct to within it."""
     diff = np.abs(a.astype(int) - b.astype(int))
-    return float((diff == 0).mean()), int((diff > 1).sum())
+    far = diff > 1
+    if qref is not None and far.any():
+        ys, xs = np.nonzero(far)
+        qa = qref[a[ys, xs].astype(int), ys, xs]
+        qb = qref[b[ys, xs].astype(int), ys, xs]
+        tie = np.abs(qa - qb) <= 2 * GF_RTOL * np.maximum(np.abs(qb), 1.0)
+        return float((diff == 0).mean()), int((~tie).sum())
+    return float((diff == 0).mean()), int(far.sum())
 
 
 # ------------------------------------------------------------------------------------------ SAD (pinned)
@@ -147,7 +157,8 @@ def test_gf_disparity_bar_config1_2(ctx, fx, orc, name):
     """BASELINE configs 1-2: every Middlebury set, D=64, GF r=9, with L-R check (and the 7x7 median)."""
     L, R = fx[name + "_L"], fx[name + "_R"]
     disp, _ = ctx.stereo_batch(L, R, g.make_params("gf", 9, 64))
-    same, off = _disp_bar(disp, orc.gf_wta(L, R, 9, 64))
+    qref = orc.gf_cost_slices(L, R, 9, 0, 64)
+    same, off = _disp_bar(disp, orc.gf_wta(L, R, 9, 64), qref)
     assert same >= 0.999 and off == 0, (name, same, off)
     disp, mask = ctx.stereo_batch(L, R, g.make_params("gf", 9, 64, lr_check=True, median_radius=3))
     dref, mref = orc.stereo_pipeline(L, R, mode="gf", r=9, D=64, lr=True, median_r=3)
