@@ -314,8 +314,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
                      int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
                      int end_) {
   constexpr int K = 16;
-  static const int runs_env = getenv("GSM_GF_RUNS") ? atoi(getenv("GSM_GF_RUNS")) : 0;
-  const int runs = (runs_env >= 4 && runs_env <= 12) ? runs_env : 12;  // 12 warps x 16 columns per CTA
+  constexpr int runs = 12;  // 12 warps x 16 columns per CTA (compile-time: shared-memory offsets become immediates)
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, 2 * R, 6, HL4);
@@ -348,7 +347,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   switch (R) {
 #define X(r)                                                                                  \
   case r: {                                                                                   \
-    auto kfn = gf_wta_kernel<r, K, EXPORT>;                                                   \
+    auto kfn = gf_wta_kernel<r, K, runs, EXPORT>;                                             \
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
     kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                          \
     break;                                                                                    \

@@ -226,17 +226,11 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
 struct GfStage {
   int TWt, OW;
   int off_O, off_COEF, off_ST, off_ICY, off_INVNY, off_CEN, bytes;
-  __host__ __device__ explicit GfStage(int twt) {
-    TWt = twt;
-    OW = twt + 64;
-    off_O = 3 * TWt;
-    off_COEF = off_O + 3 * OW;
-    off_ST = off_COEF + 2 * 4 * TWt;
-    off_ICY = off_ST + 10 * 4 * TWt;
-    off_INVNY = off_ICY + 4 * TWt;
-    off_CEN = off_INVNY + 4 * TWt;
-    bytes = off_CEN + TWt;
-  }
+  __host__ __device__ constexpr explicit GfStage(int twt)
+      : TWt(twt), OW(twt + 64), off_O(3 * twt), off_COEF(3 * twt + 3 * (twt + 64)),
+        off_ST(3 * twt + 3 * (twt + 64) + 8 * twt), off_ICY(3 * twt + 3 * (twt + 64) + 48 * twt),
+        off_INVNY(3 * twt + 3 * (twt + 64) + 52 * twt), off_CEN(3 * twt + 3 * (twt + 64) + 56 * twt),
+        bytes(3 * twt + 3 * (twt + 64) + 57 * twt) {}
 };
 
 __host__ __device__ inline size_t gf_smem_bytes(int runs, int K, int HL4) {
@@ -341,8 +335,8 @@ __device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const in
   }
 }
 
-template <int R, int K, bool EXPORT>
-__global__ void __launch_bounds__(384, 1)
+template <int R, int K, int RUNS, bool EXPORT>
+__global__ void __launch_bounds__(RUNS * 32, 1)
 gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
               i64* __restrict__ keys, FusedGeom g) {
   constexpr int HL4 = (R + 3) / 4 * 4;
@@ -351,7 +345,7 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
 
   const int lane = threadIdx.x;
   const int run = threadIdx.y;
-  const int runs = blockDim.y;
+  constexpr int runs = RUNS;  // == blockDim.y (checked by the launcher): all shared-memory offsets are immediates
   const int strip = blockIdx.x;
   const int d0 = g.d_begin + blockIdx.y * WARP;
   const int d = d0 + lane;
@@ -362,10 +356,10 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   const int yb1 = min(H, yb0 + g.band_rows);
   if (yb0 >= H) return;
 
-  const int TWt = runs * K;
-  const GfStage sg(TWt);
-  const int pitchw = exch_pitch_words(runs, K, HL4);
-  const int planew = WARP * pitchw;
+  constexpr int TWt = runs * K;
+  constexpr GfStage sg(TWt);
+  constexpr int pitchw = exch_pitch_words(runs, K, HL4);
+  constexpr int planew = WARP * pitchw;
   float* ccs = reinterpret_cast<float*>(smem_raw + 64);  // per-run centres of the current step (<= 16 runs)
   u8* stage_base = smem_raw + 128;
   u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);
@@ -446,6 +440,10 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   int c_hi = min(K - 1, min(out0 + g.TW, W) - 1 - x0);
   if (d >= g.d_end) c_hi = -1;
   const bool all_valid = __all_sync(0xffffffffu, c_lo == 0 && c_hi == K - 1);
+  // Runs that only supply stage-1 halo columns skip the later stages (warp-uniform): (a, b) is needed on strip
+  // columns [hl-R, hl+TW+R) inside the image (+R), outputs on [hl, hl+TW) inside the image.
+  const bool need_out = min(K - 1, min(out0 + g.TW, W) - 1 - x0) >= c_lo;
+  const bool need_ab = (run * K < g.hl + g.TW + R) && (run * K + K > g.hl - R) && (x0 < W + R) && (x0 + K > -R);
 
   int Vp_l[K], VIp_l[K], Vp_t[K], VIp_t[K];
   // Stage-2 vertical sums.  VA/VB are add/subtract running sums; VAf/VBf only ever add and are swapped in every
@@ -535,9 +533,9 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
         cc = target;
       }
     }
-    if (t >= a0)
+    if (need_ab && t >= a0)
       fold_ab<R, K, HL4, +1>(xb + 0 * planew, xb + 1 * planew, Vp_l, VIp_l, st_l, TWt, cc, VA, VB, VAf, VBf);
-    if (t2 >= a0)
+    if (need_ab && t2 >= a0)
       fold_ab<R, K, HL4, -1>(xb + 2 * planew, xb + 3 * planew, Vp_t, VIp_t, st_l + 5 * TWt, TWt, cc, VA, VB, VAf, VBf);
     if (GSM_GF_FRESH && t >= a0 && ++fresh_cnt == 2 * R + 1) {
       fresh_cnt = 0;
@@ -546,13 +544,13 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     }
 
     const int y = t - R;  // output row
-    if (y >= yb0) {
+    if (need_ab && y >= yb0) {
       exch_store<K, HL4>(xb + 4 * planew, reinterpret_cast<u32(&)[K]>(VA));
       exch_store<K, HL4>(xb + 5 * planew, reinterpret_cast<u32(&)[K]>(VB));
       if (lane == 0) ccs[run] = cc;
     }
     __syncthreads();
-    if (y < yb0) continue;
+    if (y < yb0 || !need_out) continue;
 
     // ---------------- stage 2, horizontal + q + WTA
     float A[K], B[K];

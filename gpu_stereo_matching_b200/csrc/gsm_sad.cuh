@@ -17,10 +17,9 @@
 
 namespace gsm {
 
-__host__ __device__ inline int exch_pitch_words(int runs, int K, int HL4) {
-  int pw = HL4 + runs * K + HL4;  // multiple of 4
-  if (((pw / 4) & 1) == 0) pw += 4;  // (pitch/4) odd: the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups
-  return pw;
+// (pitch/4) odd: the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups
+__host__ __device__ constexpr int exch_pitch_words(int runs, int K, int HL4) {
+  return (HL4 + runs * K + HL4) + (((((HL4 + runs * K + HL4) / 4) & 1) == 0) ? 4 : 0);
 }
 
 template <int R, int K, bool EXPORT>
