@@ -226,7 +226,7 @@ struct Plan {
 };
 
 static Plan make_plan(const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, int view, int K,
-                      int runs, int stage_halo, int exch_planes, int HL4) {
+                      int runs, int stage_halo, int exch_planes, int HL4, int lpr = WARP) {
   Plan pl;
   const int hl = round_up(stage_halo, 4);
   const int TWt = runs * K;
@@ -240,7 +240,7 @@ static Plan make_plan(const gsm_params* p, int n, int rows, int cols, int d_begi
   pl.g.runs = runs;
   int bands = p->row_bands;
   const int strips = (cols + TW - 1) / TW;
-  const int dchunks = (d_end - d_begin + WARP - 1) / WARP;
+  const int dchunks = (d_end - d_begin + lpr - 1) / lpr;
   if (bands <= 0) {
     // automatic: enough CTAs for ~2 waves of 148 SMs, bands no shorter than 64 rows
     bands = 1;
@@ -254,7 +254,7 @@ static Plan make_plan(const gsm_params* p, int n, int rows, int cols, int d_begi
   pl.g.export_d0 = 0;
   pl.g.export_nd = 0;
   pl.grid = dim3(strips, dchunks, n * bands);
-  pl.block = dim3(WARP, runs, 1);
+  pl.block = dim3(WARP, runs * lpr / WARP, 1);
   pl.smem = (size_t)exch_planes * WARP * exch_pitch_words(runs, K, HL4) * sizeof(u32);
   return pl;
 }
@@ -314,11 +314,12 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
                      int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
                      int end_) {
   constexpr int K = 16;
-  constexpr int runs = 12;  // 12 warps x 16 columns per CTA (compile-time: shared-memory offsets become immediates)
+  // 24 runs of 16 columns x 16 disparities per CTA (two runs per warp): a 384-column strip, 346 of them output
+  constexpr int runs = 24, lpr = 16;
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
-  Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, 2 * R, 6, HL4);
-  pl.smem = gf_smem_bytes(runs, K, HL4);
+  Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, 2 * R, 6, HL4, lpr);
+  pl.smem = gf_smem_bytes(runs, K, HL4, lpr);
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
   pl.g.export_nd = end_;
@@ -347,7 +348,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   switch (R) {
 #define X(r)                                                                                  \
   case r: {                                                                                   \
-    auto kfn = gf_wta_kernel<r, K, runs, EXPORT>;                                             \
+    auto kfn = gf_wta_kernel<r, K, runs, lpr, EXPORT>;                                        \
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
     kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                          \
     break;                                                                                    \

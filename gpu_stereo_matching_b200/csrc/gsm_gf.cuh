@@ -233,8 +233,8 @@ struct GfStage {
         bytes(3 * twt + 3 * (twt + 64) + 57 * twt) {}
 };
 
-__host__ __device__ inline size_t gf_smem_bytes(int runs, int K, int HL4) {
-  return 64 + 64 + 2 * (size_t)GfStage(runs * K).bytes + 6 * (size_t)WARP * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+__host__ __device__ inline size_t gf_smem_bytes(int runs, int K, int HL4, int LPR) {
+  return 256 + 2 * (size_t)GfStage(runs * K).bytes + 6 * (size_t)LPR * exch_pitch_words(runs, K, HL4) * sizeof(u32);
 }
 
 // K bytes at byte offset `off` (any alignment) of a shared-memory row
@@ -335,19 +335,22 @@ __device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const in
   }
 }
 
-template <int R, int K, int RUNS, bool EXPORT>
-__global__ void __launch_bounds__(RUNS * 32, 1)
+template <int R, int K, int RUNS, int LPR, bool EXPORT>
+__global__ void __launch_bounds__(RUNS * LPR, 1)
 gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
               i64* __restrict__ keys, FusedGeom g) {
   constexpr int HL4 = (R + 3) / 4 * 4;
   constexpr int KW = K / 4;
   extern __shared__ __align__(128) u8 smem_raw[];
 
-  const int lane = threadIdx.x;
-  const int run = threadIdx.y;
-  constexpr int runs = RUNS;  // == blockDim.y (checked by the launcher): all shared-memory offsets are immediates
+  // LPR lanes (= disparities) per run: 32 -> one run per warp; 16 -> two runs per warp, i.e. a strip twice as wide
+  // for the same thread count (less halo overhead) at the price of staging the rows for half as many disparities.
+  static_assert(LPR == 32 || LPR == 16, "lanes per run");
+  const int lane = threadIdx.x & (LPR - 1);
+  const int run = threadIdx.y * (WARP / LPR) + threadIdx.x / LPR;
+  constexpr int runs = RUNS;  // blockDim = (32, RUNS*LPR/32): all shared-memory offsets are immediates
   const int strip = blockIdx.x;
-  const int d0 = g.d_begin + blockIdx.y * WARP;
+  const int d0 = g.d_begin + blockIdx.y * LPR;
   const int d = d0 + lane;
   const int frame = blockIdx.z / g.bands;
   const int band = blockIdx.z - frame * g.bands;
@@ -359,14 +362,14 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   constexpr int TWt = runs * K;
   constexpr GfStage sg(TWt);
   constexpr int pitchw = exch_pitch_words(runs, K, HL4);
-  constexpr int planew = WARP * pitchw;
-  float* ccs = reinterpret_cast<float*>(smem_raw + 64);  // per-run centres of the current step (<= 16 runs)
-  u8* stage_base = smem_raw + 128;
+  constexpr int planew = LPR * pitchw;
+  float* ccs = reinterpret_cast<float*>(smem_raw + 64);  // per-run centres of the current step (<= 48 runs)
+  u8* stage_base = smem_raw + 256;
   u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);
   const u32 bar0 = smem_u32(smem_raw);  // two 8-byte mbarriers at the start of shared memory
   const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
 
-  for (int i = threadIdx.y * WARP + threadIdx.x; i < 6 * planew; i += runs * WARP) exch[i] = 0u;
+  for (int i = threadIdx.y * WARP + threadIdx.x; i < 6 * planew; i += runs * LPR) exch[i] = 0u;
   if (producer) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -383,14 +386,14 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   // producer-side source addresses (row 0 of the padded planes, strip column xs)
   const size_t org = (size_t)PADV * pitch + g.pg.xoff + xs;
   const u8* gsrc = Gp + (size_t)frame * g.pg.plane_stride + org;
-  const int ostart = g.pg.xoff + xs + (g.view == 0 ? -(d0 + 31) : d0);  // byte column of the staged O window
+  const int ostart = g.pg.xoff + xs + (g.view == 0 ? -(d0 + LPR - 1) : d0);  // byte column of the staged O window
   const int oalign = ostart & 15;
   const u8* osrc = Op + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + (ostart - oalign);
   const float* ssrc = stats + (size_t)frame * GF_STAT_PLANES * plane_elems + org;
   const float* csrc = stats + ((size_t)frame * GF_STAT_PLANES + ST_CEN) * plane_elems + (size_t)PADV * pitch +
                       (g.pg.xoff + xs) / 4;  // 4x replicated centre plane: one float per 4 columns
   // consumer-side byte offset of this thread's first pixel inside a staged O row
-  const int ooff = oalign + run * K + (g.view == 0 ? (31 - lane) : lane);
+  const int ooff = oalign + run * K + (g.view == 0 ? (LPR - 1 - lane) : lane);
 
   auto issue = [&](int t, int s) {
     const u32 bar = bar0 + 8 * s;
@@ -442,8 +445,12 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   const bool all_valid = __all_sync(0xffffffffu, c_lo == 0 && c_hi == K - 1);
   // Runs that only supply stage-1 halo columns skip the later stages (warp-uniform): (a, b) is needed on strip
   // columns [hl-R, hl+TW+R) inside the image (+R), outputs on [hl, hl+TW) inside the image.
-  const bool need_out = min(K - 1, min(out0 + g.TW, W) - 1 - x0) >= c_lo;
-  const bool need_ab = (run * K < g.hl + g.TW + R) && (run * K + K > g.hl - R) && (x0 < W + R) && (x0 + K > -R);
+  // Control flow must stay warp-uniform (__syncthreads inside the loop), so with two runs per warp the warp runs a
+  // stage when either of its runs needs it.
+  const bool need_out =
+      __any_sync(0xffffffffu, min(K - 1, min(out0 + g.TW, W) - 1 - x0) >= c_lo);
+  const bool need_ab = __any_sync(
+      0xffffffffu, (run * K < g.hl + g.TW + R) && (run * K + K > g.hl - R) && (x0 < W + R) && (x0 + K > -R));
 
   int Vp_l[K], VIp_l[K], Vp_t[K], VIp_t[K];
   // Stage-2 vertical sums.  VA/VB are add/subtract running sums; VAf/VBf only ever add and are swapped in every
@@ -468,9 +475,6 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   for (int t = t_begin; t < t_end; ++t) {
     const int it = t - t_begin;
     const int s = it & 1;
-    // prefetch the next step's rows into the other stage (its previous contents were last read before the
-    // second __syncthreads of the previous step)
-    if (producer && t + 1 < t_end) issue(t + 1, s ^ 1);
     mbar_wait(bar0 + 8 * s, (u32)((it >> 1) & 1));
     const u8* stg = stage_base + (size_t)s * sg.bytes;
     const int t2 = t - 2 * R - 1;  // row of (a, b) recomputed by the trail pipeline
@@ -519,6 +523,10 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
     exch_store<K, HL4>(xb + 2 * planew, reinterpret_cast<u32(&)[K]>(Vp_t));
     exch_store<K, HL4>(xb + 3 * planew, reinterpret_cast<u32(&)[K]>(VIp_t));
     __syncthreads();
+    // Prefetch the next step's rows into the other stage.  Its previous contents (step t-1) are read up to the end
+    // of that step (I-128, 1/N of the output row), so the earliest safe point is after this barrier, which every
+    // thread reaches only once it has finished step t-1.
+    if (producer && t + 1 < t_end) issue(t + 1, s ^ 1);
     const float* st_l = reinterpret_cast<const float*>(stg + sg.off_ST) + run * K;
     {
       // follow the local intensity level: B'(c + dc) = B'(c) + dc * A exactly, applied to the running sums
@@ -595,10 +603,21 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
         if (c < c_lo || c > c_hi) key[c] = 0x7fffffff;
     }
     int mine = 0x7fffffff;
+    if (LPR == 32) {
 #pragma unroll
-    for (int c = 0; c < K; ++c) {
-      const int m = __reduce_min_sync(0xffffffffu, key[c]);
-      if (lane == c) mine = m;
+      for (int c = 0; c < K; ++c) {
+        const int m = __reduce_min_sync(0xffffffffu, key[c]);
+        if (lane == c) mine = m;
+      }
+    } else {
+      // two runs per warp: two full-warp REDUX per column, each half contributing the neutral element to the other's
+      const bool upper = (threadIdx.x & 16) != 0;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const int m0 = __reduce_min_sync(0xffffffffu, upper ? 0x7fffffff : key[c]);
+        const int m1 = __reduce_min_sync(0xffffffffu, upper ? key[c] : 0x7fffffff);
+        if (lane == c) mine = upper ? m1 : m0;
+      }
     }
     if (lane < K && mine != 0x7fffffff) {
       const i64 k64 = (i64)(((unsigned long long)(u32)(mine & ~31) << 32) | (u32)(d0 + (mine & 31)));
