@@ -315,7 +315,10 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
                      int end_) {
   constexpr int K = 16;
   // 24 runs of 16 columns x 16 disparities per CTA (two runs per warp): a 384-column strip, 346 of them output
-  constexpr int runs = 24, lpr = 16;
+#ifndef GSM_GF_RUNS
+#define GSM_GF_RUNS 24
+#endif
+  constexpr int runs = GSM_GF_RUNS, lpr = 16;
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, 2 * R, 6, HL4, lpr);

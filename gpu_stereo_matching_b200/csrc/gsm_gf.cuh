@@ -167,28 +167,52 @@ __device__ __forceinline__ void exch_window(const u32* buf, const u32 (&own)[K],
 #pragma unroll
   for (int c = 0; c < K; ++c) win[HL4 + c] = own[c];
 }
+// sum of win[LO..HI] (inclusive, window-relative indices) with three independent partial sums (short dependency chain)
+template <int LO, int HI, int N>
+__device__ __forceinline__ int wsum_i(const u32 (&win)[N], int base) {
+  int p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+  for (int j = LO; j <= HI; ++j) {
+    const int v = (int)win[base + j];
+    if ((j - LO) % 3 == 0) p0 += v; else if ((j - LO) % 3 == 1) p1 += v; else p2 += v;
+  }
+  return p0 + p1 + p2;
+}
+template <int LO, int HI, int N>
+__device__ __forceinline__ float wsum_f(const u32 (&win)[N], int base) {
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+  for (int j = LO; j <= HI; ++j) {
+    const float v = __uint_as_float(win[base + j]);
+    if ((j - LO) % 3 == 0) p0 += v; else if ((j - LO) % 3 == 1) p1 += v; else p2 += v;
+  }
+  return (p0 + p1) + p2;
+}
+
+// Horizontal sliding window sums over the thread's K = 16 columns as TWO independent chains (columns 0..7 and
+// 8..15): with only ~3 warps per scheduler the dependent add chain of a single slide is what the issue slots wait
+// on.  The two starting sums share their overlapping middle part.
 template <int R, int K, int HL4>
 __device__ __forceinline__ void slide_i32(const u32 (&win)[HL4 + K + HL4], int (&S)[K]) {
-  int s = 0;
-#pragma unroll
-  for (int j = -R; j <= R; ++j) s += (int)win[HL4 + j];
-  S[0] = s;
-#pragma unroll
-  for (int c = 1; c < K; ++c) {
-    s += (int)win[HL4 + c + R] - (int)win[HL4 + c - R - 1];
-    S[c] = s;
+  static_assert(K == 16, "two chains of 8");
+  constexpr int H = K / 2;
+  int sA, sB;
+  if constexpr (2 * R + 1 > H) {
+    const int mid = wsum_i<H - R, R>(win, HL4);                // columns common to both start windows
+    sA = mid + wsum_i<-R, H - R - 1>(win, HL4);
+    sB = mid + wsum_i<R + 1, H + R>(win, HL4);
+  } else {
+    sA = wsum_i<-R, R>(win, HL4);
+    sB = wsum_i<H - R, H + R>(win, HL4);
   }
-}
-template <int R, int K, int HL4>
-__device__ __forceinline__ void slide_f32(const u32 (&win)[HL4 + K + HL4], float (&S)[K]) {
-  float s = 0.f;
+  S[0] = sA;
+  S[H] = sB;
 #pragma unroll
-  for (int j = -R; j <= R; ++j) s += __uint_as_float(win[HL4 + j]);
-  S[0] = s;
-#pragma unroll
-  for (int c = 1; c < K; ++c) {
-    s = (s + __uint_as_float(win[HL4 + c + R])) - __uint_as_float(win[HL4 + c - R - 1]);
-    S[c] = s;
+  for (int c = 1; c < H; ++c) {
+    sA += (int)win[HL4 + c + R] - (int)win[HL4 + c - R - 1];
+    sB += (int)win[HL4 + H + c + R] - (int)win[HL4 + H + c - R - 1];
+    S[c] = sA;
+    S[H + c] = sB;
   }
 }
 
@@ -252,28 +276,49 @@ __device__ __forceinline__ void lds_unaligned(const u8* row, int off, u32 (&w)[K
 // Stage-2 horizontal pass.  winA / winB: [left halo HL4 | own K | right halo HL4].  The A window sum is kept as
 // three partial sums (columns owned by the left neighbour, by this run, by the right neighbour) because the
 // neighbours' B' sums are relative to THEIR centres: B'(x) = sum(winB) + dl * A_L(x) + dr * A_R(x).
+// Two independent chains (columns 0..7 and 8..15), see slide_i32.
 template <int R, int K, int HL4>
 __device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const u32 (&winB)[HL4 + K + HL4], float dl,
                                          float dr, float (&A)[K], float (&B)[K]) {
-  static_assert(R < K, "window must not reach beyond the adjacent runs");
-  float aL = 0.f, aO = 0.f, aR = 0.f, b = 0.f;
+  static_assert(R < K && K == 16, "window must not reach beyond the adjacent runs");
+  constexpr int H = K / 2;
+  // chain starting at column c0: window [c0-R, c0+R]; parts: left halo (< 0), own [0, K), right halo (>= K)
+  float aL[2], aO[2], aR[2], b[2];
 #pragma unroll
-  for (int j = -R; j <= R; ++j) {
-    const float va = __uint_as_float(winA[HL4 + j]);
-    if (j < 0) aL += va; else if (j < K) aO += va; else aR += va;
-    b += __uint_as_float(winB[HL4 + j]);
+  for (int h = 0; h < 2; ++h) {
+    const int c0 = h * H;
+    float l = 0.f, o = 0.f, r = 0.f;
+#pragma unroll
+    for (int j = -R; j <= R; ++j) {
+      const int idx = c0 + j;
+      const float va = __uint_as_float(winA[HL4 + idx]);
+      if (idx < 0) l += va; else if (idx < K) o += va; else r += va;
+    }
+    aL[h] = l; aO[h] = o; aR[h] = r;
   }
-  A[0] = (aL + aO) + aR;
-  B[0] = fmaf(dr, aR, fmaf(dl, aL, b));
+  if constexpr (2 * R + 1 > H) {
+    const float mid = wsum_f<H - R, R>(winB, HL4);
+    b[0] = mid + wsum_f<-R, H - R - 1>(winB, HL4);
+    b[1] = mid + wsum_f<R + 1, H + R>(winB, HL4);
+  } else {
+    b[0] = wsum_f<-R, R>(winB, HL4);
+    b[1] = wsum_f<H - R, H + R>(winB, HL4);
+  }
 #pragma unroll
-  for (int c = 1; c < K; ++c) {
-    const int in = c + R, out = c - R - 1;
-    const float vin = __uint_as_float(winA[HL4 + in]), vout = __uint_as_float(winA[HL4 + out]);
-    if (in < K) aO += vin; else aR += vin;
-    if (out < 0) aL -= vout; else aO -= vout;
-    b = (b + __uint_as_float(winB[HL4 + in])) - __uint_as_float(winB[HL4 + out]);
-    A[c] = (aL + aO) + aR;
-    B[c] = fmaf(dr, aR, fmaf(dl, aL, b));
+  for (int c = 0; c < H; ++c) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = h * H + c;
+      if (c > 0) {
+        const int in = col + R, out = col - R - 1;
+        const float vin = __uint_as_float(winA[HL4 + in]), vout = __uint_as_float(winA[HL4 + out]);
+        if (in < K) aO[h] += vin; else aR[h] += vin;
+        if (out < 0) aL[h] -= vout; else aO[h] -= vout;
+        b[h] = (b[h] + __uint_as_float(winB[HL4 + in])) - __uint_as_float(winB[HL4 + out]);
+      }
+      A[col] = (aL[h] + aO[h]) + aR[h];
+      B[col] = fmaf(dr, aR[h], fmaf(dl, aL[h], b[h]));
+    }
   }
 }
 
@@ -297,17 +342,17 @@ template <int R, int K, int HL4, int SIGN>
 __device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const int (&Vp)[K], const int (&VIp)[K],
                                         const float* st, int TWt, float cc, float (&VA)[K], float (&VB)[K],
                                         float (&VAf)[K], float (&VBf)[K]) {
-  int Sp[K];
+  int Sp[K], SIp[K];
   {
     u32 win[HL4 + K + HL4];
     exch_window<K, HL4>(xbP, reinterpret_cast<const u32(&)[K]>(Vp), win);
     slide_i32<R, K, HL4>(win, Sp);
   }
-  u32 win[HL4 + K + HL4];
-  exch_window<K, HL4>(xbI, reinterpret_cast<const u32(&)[K]>(VIp), win);
-  int s = 0;
-#pragma unroll
-  for (int j = -R; j <= R; ++j) s += (int)win[HL4 + j];
+  {
+    u32 win[HL4 + K + HL4];
+    exch_window<K, HL4>(xbI, reinterpret_cast<const u32(&)[K]>(VIp), win);
+    slide_i32<R, K, HL4>(win, SIp);
+  }
 #pragma unroll
   for (int g4 = 0; g4 < K; g4 += 4) {
     const int4 N = *reinterpret_cast<const int4*>(st + ST_N * TWt + g4);
@@ -321,8 +366,7 @@ __device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const in
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = g4 + j;
-      if (c > 0) s += (int)win[HL4 + c + R] - (int)win[HL4 + c - R - 1];
-      const int num = Nn[j] * s - SIi[j] * Sp[c];  // exact modulo 2^32; true value fits int32 for r <= 9
+      const int num = Nn[j] * SIp[c] - SIi[j] * Sp[c];  // exact modulo 2^32; true value fits int32 for r <= 9
       const float a = (float)num * idn[j];
       const float b = fmaf(-a, cm[j] - cc, (float)Sp[c] * inn[j]);  // mean_p - a * (mean_I - centre)
       if (SIGN > 0) {
@@ -336,7 +380,7 @@ __device__ __forceinline__ void fold_ab(const u32* xbP, const u32* xbI, const in
 }
 
 template <int R, int K, int RUNS, int LPR, bool EXPORT>
-__global__ void __launch_bounds__(RUNS * LPR, 1)
+__global__ void __launch_bounds__(RUNS * LPR, (RUNS * LPR <= 192) ? 2 : 1)
 gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
               i64* __restrict__ keys, FusedGeom g) {
   constexpr int HL4 = (R + 3) / 4 * 4;
@@ -367,10 +411,10 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   u8* stage_base = smem_raw + 256;
   u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);
   const u32 bar0 = smem_u32(smem_raw);  // two 8-byte mbarriers at the start of shared memory
-  const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
+  const bool producer = (threadIdx.x == 0);  // lane 0 of every warp issues its share of the bulk copies
 
   for (int i = threadIdx.y * WARP + threadIdx.x; i < 6 * planew; i += runs * LPR) exch[i] = 0u;
-  if (producer) {
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -395,30 +439,38 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   // consumer-side byte offset of this thread's first pixel inside a staged O row
   const int ooff = oalign + run * K + (g.view == 0 ? (LPR - 1 - lane) : lane);
 
+  // The 20 bulk copies of a step are spread over the warps (lane 0 of warp w issues copies w, w+NW, ...): issued by a
+  // single thread they serialise (~50 cycles each) on that warp and every other warp waits for it at the barrier.
+  constexpr int NCOPY = 20;
+  constexpr int NW = RUNS * LPR / WARP;
+  const int warp_id = threadIdx.y;
   auto issue = [&](int t, int s) {
     const u32 bar = bar0 + 8 * s;
     const u32 dst = smem_u32(stage_base + (size_t)s * sg.bytes);
-    mbar_expect_tx(bar, (u32)sg.bytes);
-    const int rows3[3] = {t + R, t - R - 1, t - 3 * R - 2};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const long long ro = (long long)max(row_lo, min(row_hi, rows3[i])) * pitch;
-      bulk_g2s(dst + i * TWt, gsrc + ro, TWt, bar);
-      bulk_g2s(dst + sg.off_O + i * sg.OW, osrc + ro, sg.OW, bar);
+    if (warp_id == 0) mbar_expect_tx(bar, (u32)sg.bytes);
+    for (int i = warp_id; i < NCOPY; i += NW) {
+      if (i < 6) {  // guide (even) / other-image (odd) rows t+R, t-R-1, t-3R-2
+        const int k = i >> 1;
+        const int row = k == 0 ? t + R : (k == 1 ? t - R - 1 : t - 3 * R - 2);
+        const long long ro = (long long)max(row_lo, min(row_hi, row)) * pitch;
+        if ((i & 1) == 0) bulk_g2s(dst + k * TWt, gsrc + ro, TWt, bar);
+        else bulk_g2s(dst + sg.off_O + k * sg.OW, osrc + ro, sg.OW, bar);
+      } else if (i < 18) {  // per row t / t-2R-1: coefficient row + 5 statistic rows
+        const int k = i - 6, which = k / 6, pl = k - which * 6;
+        const int row = which == 0 ? t : t - 2 * R - 1;
+        const long long ro = (long long)max(row_lo, min(row_hi, row)) * pitch;
+        if (pl == 5) bulk_g2s(dst + sg.off_COEF + which * 4 * TWt, ssrc + ST_COEF * plane_elems + ro, 4 * TWt, bar);
+        else bulk_g2s(dst + sg.off_ST + (which * 5 + pl) * 4 * TWt, ssrc + (size_t)pl * plane_elems + ro, 4 * TWt, bar);
+      } else {  // output row t-R: I-128 and 1/N (18), centres (19)
+        const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
+        if (i == 18) {
+          bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
+          bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
+        } else {
+          bulk_g2s(dst + sg.off_CEN, csrc + ry, TWt, bar);
+        }
+      }
     }
-    const int rows2[2] = {t, t - 2 * R - 1};
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const long long ro = (long long)max(row_lo, min(row_hi, rows2[i])) * pitch;
-      bulk_g2s(dst + sg.off_COEF + i * 4 * TWt, ssrc + ST_COEF * plane_elems + ro, 4 * TWt, bar);
-#pragma unroll
-      for (int k = 0; k < 5; ++k)
-        bulk_g2s(dst + sg.off_ST + (i * 5 + k) * 4 * TWt, ssrc + (size_t)k * plane_elems + ro, 4 * TWt, bar);
-    }
-    const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
-    bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
-    bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
-    bulk_g2s(dst + sg.off_CEN, csrc + ry, TWt, bar);
   };
 
   const int dd = min(d, MAX_DISP - 1);
