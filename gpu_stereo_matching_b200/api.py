@@ -160,6 +160,26 @@ class StereoContext:
         _l.check(self._lib.gsm_lr_check(self._h, _ptr(a), _ptr(b), _ptr(occ), _ptr(mask), a.shape[0], a.shape[1]))
         return occ, mask
 
+    # ---- the other two Device.cuh proxy functions ----------------------------------
+    def remap(self, src, mapx, mapy) -> np.ndarray:
+        """== kernalRemap / CPU_Remap: bilinear, OOB -> 0, round-nearest-even (Device.cu:127-167)."""
+        a = _u8c(src, "src")
+        mx = np.ascontiguousarray(mapx, np.float32); my = np.ascontiguousarray(mapy, np.float32)
+        if a.ndim != 2 or mx.shape != a.shape or my.shape != a.shape:
+            raise ValueError("src, mapx, mapy must be 2-D and the same size")
+        out = np.empty_like(a)
+        _l.check(self._lib.gsm_remap(self._h, _ptr(a), _ptr(mx), _ptr(my), _ptr(out), a.shape[0], a.shape[1]))
+        return out
+
+    def cvtcolor(self, src3, truncate: bool = False) -> np.ndarray:
+        """== kernalCvtColor (round) / cvtColor_cpu (truncate): .299/.587/.114 on channels 0/1/2 as stored."""
+        a = _u8c(src3, "src3")
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise ValueError("src3 must be [rows, cols, 3]")
+        out = np.empty(a.shape[:2], np.uint8)
+        _l.check(self._lib.gsm_cvtcolor(self._h, _ptr(a), _ptr(out), a.shape[0], a.shape[1], int(truncate)))
+        return out
+
     # ---- introspection -----------------------------------------------------------------------
     @property
     def launch_count(self) -> int:
@@ -202,6 +222,23 @@ def singleFrame(left_gray, right_gray) -> np.ndarray:
     """Compute part of singleFrame() (BlockMatching/Caller.cpp:9-25): blockMatching_gpu(g1, g2, disp, 5, 64).
     Image loading (imread + cvtColor) and display (imshow/waitKey) stay with the caller."""
     return blockMatching_gpu(left_gray, right_gray, 5, 64)
+
+
+def remap_gpu(left, right, mapX1, mapY1, mapX2, mapY2) -> np.ndarray:
+    """Drop-in for remap_gpu(left, right, mapX1, mapY1, mapX2, mapY2, rows, cols, total, result)
+    (BlockMatching/Device.cuh:51, Device.cu:303-342): like the reference it returns only the LEFT remapped image
+    (Device.cu:341); the right image is remapped too and discarded."""
+    L = _u8c(left, "left")
+    c = _ctx_for(L.shape[0], L.shape[1], 1)
+    res = c.remap(L, mapX1, mapY1)
+    c.remap(right, mapX2, mapY2)
+    return res
+
+
+def cvtColor_gpu(src3) -> np.ndarray:
+    """Drop-in for cvtColor_gpu(uchar3* src, uchar* dst, rows, cols) (Device.cuh:52, Device.cu:344-367)."""
+    a = _u8c(src3, "src3")
+    return _ctx_for(a.shape[0], a.shape[1], 1).cvtcolor(a, truncate=False)
 
 
 def compare_disp(reference_disp, gpu_disp):

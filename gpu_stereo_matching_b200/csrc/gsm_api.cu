@@ -703,6 +703,49 @@ extern "C" int gsm_lr_check(gsm_ctx* c, const uint8_t* dl, const uint8_t* dr, ui
   return GSM_OK;
 }
 
+extern "C" int gsm_remap(gsm_ctx* c, const uint8_t* src, const float* mapx, const float* mapy, uint8_t* dst, int rows,
+                         int cols) {
+  if (!c || !src || !mapx || !mapy || !dst) return fail(GSM_ERR_INVALID, "null pointer");
+  if (rows < 1 || cols < 1) return fail(GSM_ERR_INVALID, "bad shape %dx%d", rows, cols);
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)rows * cols;
+  int rc;
+  if ((rc = ensure_export(c, n * 10))) return rc;  // [mapx f32][mapy f32][src u8][dst u8]
+  float* dmx = (float*)c->export_buf;
+  float* dmy = dmx + n;
+  u8* dsrc = (u8*)(dmy + n);
+  u8* ddst = dsrc + n;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(dmx, mapx, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dmy, mapy, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dsrc, src, n, cudaMemcpyHostToDevice, s));
+  remap_kernel<<<dim3((cols + 255) / 256, rows), 256, 0, s>>>(dsrc, dmx, dmy, ddst, rows, cols);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, ddst, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_cvtcolor(gsm_ctx* c, const uint8_t* src3, uint8_t* dst, int rows, int cols, int truncate) {
+  if (!c || !src3 || !dst) return fail(GSM_ERR_INVALID, "null pointer");
+  if (rows < 1 || cols < 1) return fail(GSM_ERR_INVALID, "bad shape %dx%d", rows, cols);
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)rows * cols;
+  int rc;
+  if ((rc = ensure_export(c, n * 4))) return rc;
+  u8* dsrc = (u8*)c->export_buf;
+  u8* ddst = dsrc + 3 * n;
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(dsrc, src3, 3 * n, cudaMemcpyHostToDevice, s));
+  cvtcolor_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dsrc, ddst, n, truncate);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(dst, ddst, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
 extern "C" int gsm_measure_alu_peak(gsm_ctx* c, double* lane_ops_per_s) {
   if (!c || !lane_ops_per_s) return fail(GSM_ERR_INVALID, "null pointer");
   CK(cudaSetDevice(c->device));

@@ -121,6 +121,44 @@ __global__ void all_sad_pack_kernel(const int* __restrict__ slices, u8* __restri
   out[i * D + d] = (x + d > W) ? (u8)255 : (u8)slices[(size_t)k * H * W + i];
 }
 
+// round-to-nearest-even + saturate to u8: the reference's float2uchar (Device.cu:145-150)
+__device__ __forceinline__ u8 float2uchar_rni_sat(float a) {
+  u32 res;
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(res) : "f"(a));
+  return (u8)res;
+}
+
+// kernalRemap + BilinearInterpolation (Device.cu:127-134,152-167).  Products and sums are rounded separately
+// (__fmul_rn/__fadd_rn: no FMA contraction) so the result equals the reference's CPU twin bit for bit.
+__global__ void remap_kernel(const u8* __restrict__ src, const float* __restrict__ mapx, const float* __restrict__ mapy,
+                             u8* __restrict__ dst, int rows, int cols) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= cols) return;
+  const size_t i = (size_t)row * cols + col;
+  const float x = mapy[i], y = mapx[i];  // called as (src, ycoo, xcoo): x is the row coordinate
+  const int x1 = (int)floorf(x), y1 = (int)floorf(y), x2 = x1 + 1, y2 = y1 + 1;
+  float result = 0.f;
+  if (!(x1 < 0 || x2 >= rows || y1 < 0 || y2 >= cols)) {
+    const size_t b = (size_t)x1 * cols + y1;
+    const float Q11 = src[b], Q12 = src[b + 1], Q21 = src[b + cols], Q22 = src[b + cols + 1];
+    const float wx2 = __fsub_rn((float)x2, x), wx1 = __fsub_rn(x, (float)x1);
+    const float left = __fadd_rn(__fmul_rn(wx2, Q11), __fmul_rn(wx1, Q21));
+    const float right = __fadd_rn(__fmul_rn(wx2, Q12), __fmul_rn(wx1, Q22));
+    result = __fadd_rn(__fmul_rn(__fsub_rn((float)y2, y), left), __fmul_rn(__fsub_rn(y, (float)y1), right));
+  }
+  dst[i] = float2uchar_rni_sat(result);
+}
+
+// kernalCvtColor (Device.cu:136-143) / cvtColor_cpu (Utility.cpp:289-298)
+__global__ void cvtcolor_kernel(const u8* __restrict__ src3, u8* __restrict__ dst, size_t n, int truncate) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c0 = src3[3 * i], c1 = src3[3 * i + 1], c2 = src3[3 * i + 2];
+  const float sum = __fadd_rn(__fadd_rn(__fmul_rn(.299f, c0), __fmul_rn(.587f, c1)), __fmul_rn(.114f, c2));
+  dst[i] = truncate ? (u8)sum : float2uchar_rni_sat(sum);
+}
+
 // FFMA + IADD3 issue-peak probe (roofline denominator for the ALU-bound fused kernels)
 __global__ void __launch_bounds__(256) alu_peak_kernel(u32* out, int iters) {
   float f[8];

@@ -56,6 +56,8 @@ SYMBOLS = {
     "gsm_all_sad": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gsm_median": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "gsm_lr_check": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "gsm_remap": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "gsm_cvtcolor": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "gsm_launch_count": (C.c_longlong, [_P]),
     "gsm_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "gsm_last_kernel_ms": (C.c_float, [_P]),

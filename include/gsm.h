@@ -124,6 +124,17 @@ int gsm_median(gsm_ctx* ctx, const uint8_t* src, uint8_t* dst, int rows, int col
 int gsm_lr_check(gsm_ctx* ctx, const uint8_t* disp_left, const uint8_t* disp_right, uint8_t* occ,
                  uint8_t* mask, int rows, int cols);
 
+/* ---- SURVEY 8(f) "next" rows: the other two proxy functions of Device.cuh:50-52 --------------------- */
+/* == kernalRemap / CPU_Remap (Device.cu:127-167, Utility.cpp:236-264): dst(r,c) = bilinear sample of src at
+ * (row = mapy(r,c), col = mapx(r,c)), 0 when the 2x2 footprint leaves the image, round-nearest-even + saturate.
+ * Host pointers; maps are float32 rows x cols (initUndistortRectifyMap CV_32FC1, Utility.cpp:232-233). */
+int gsm_remap(gsm_ctx* ctx, const uint8_t* src, const float* mapx, const float* mapy, uint8_t* dst, int rows,
+              int cols);
+/* == kernalCvtColor (Device.cu:136-143): gray = .299*ch0 + .587*ch1 + .114*ch2 of interleaved 3-channel u8,
+ * rounded to nearest-even (truncate = 0, the GPU kernel) or truncated (truncate = 1, cvtColor_cpu,
+ * Utility.cpp:289-298). */
+int gsm_cvtcolor(gsm_ctx* ctx, const uint8_t* src3, uint8_t* dst, int rows, int cols, int truncate);
+
 /* ---- introspection for benches -------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 long long gsm_launch_count(const gsm_ctx* ctx);

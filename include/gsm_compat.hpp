@@ -75,6 +75,37 @@ void guidedMatching_gpu(Mat& h_left, Mat& h_right, Mat& h_disparity, int radius,
   h_disparity = Mat(rows, cols, 0, out);
 }
 
+// remap_gpu(left, right, mapX1, mapY1, mapX2, mapY2, rows, cols, total, result), Device.cuh:51 / Device.cu:303-342:
+// both images are remapped, only the LEFT result is returned in the caller-allocated `result` (Device.cu:341).
+template <class Mat>
+void remap_gpu(Mat& left, Mat& right, Mat& mapX1, Mat& mapY1, Mat& mapX2, Mat& mapY2, int rows, int cols, int total,
+               unsigned char* result) {
+  (void)total;
+  gsm_ctx* ctx = ctx_for(rows, cols);
+  unsigned char* scratch = new unsigned char[(size_t)rows * cols];
+  int rc = gsm_remap(ctx, left.data, reinterpret_cast<const float*>(mapX1.data), reinterpret_cast<const float*>(mapY1.data),
+                     result, rows, cols);
+  if (rc == GSM_OK)
+    rc = gsm_remap(ctx, right.data, reinterpret_cast<const float*>(mapX2.data),
+                   reinterpret_cast<const float*>(mapY2.data), scratch, rows, cols);
+  delete[] scratch;
+  if (rc != GSM_OK) {
+    std::fprintf(stderr, "remap_gpu: %s\n", gsm_last_error());
+    std::abort();
+  }
+}
+
+// cvtColor_gpu(uchar3* src, uchar* dst, rows, cols), Device.cuh:52 / Device.cu:344-367 (one conversion; the
+// reference's 1000-iteration timing loop is a benchmark artefact and is not reproduced).
+template <class Pixel3>
+void cvtColor_gpu(Pixel3* src, unsigned char* dst, int rows, int cols) {
+  static_assert(sizeof(Pixel3) == 3, "interleaved 3-channel u8 expected (uchar3)");
+  if (gsm_cvtcolor(ctx_for(rows, cols), reinterpret_cast<const unsigned char*>(src), dst, rows, cols, 0) != GSM_OK) {
+    std::fprintf(stderr, "cvtColor_gpu: %s\n", gsm_last_error());
+    std::abort();
+  }
+}
+
 }  // namespace gsm_compat
 
 #ifdef GSM_COMPAT_REFERENCE_NAMES
@@ -82,6 +113,10 @@ void guidedMatching_gpu(Mat& h_left, Mat& h_right, Mat& h_disparity, int radius,
 inline void blockMatching_gpu(cv::Mat& h_left, cv::Mat& h_right, cv::Mat& h_disparity, int SADWindowSize,
                               int searchRange) {
   gsm_compat::blockMatching_gpu<cv::Mat>(h_left, h_right, h_disparity, SADWindowSize, searchRange);
+}
+inline void remap_gpu(cv::Mat& left, cv::Mat& right, cv::Mat& mapX1, cv::Mat& mapY1, cv::Mat& mapX2, cv::Mat& mapY2,
+                      int rows, int cols, int total, unsigned char* result) {
+  gsm_compat::remap_gpu<cv::Mat>(left, right, mapX1, mapY1, mapX2, mapY2, rows, cols, total, result);
 }
 #endif
 

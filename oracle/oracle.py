@@ -56,6 +56,11 @@ def lib() -> C.CDLL:
                                  _u8p, C.c_void_p]
         L.orc_lr_check.argtypes = [_u8p, _u8p, C.c_int, C.c_int, _u8p, _u8p]
         L.orc_median.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int]
+        _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+        L.orc_remap.argtypes = [_u8p, _f32p, _f32p, C.c_int, C.c_int, _u8p]
+        L.orc_remap.restype = None
+        L.orc_cvtcolor.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_cvtcolor.restype = None
         L.orc_fnv1a64.argtypes = [_u8p, C.c_size_t]
         L.orc_fnv1a64.restype = C.c_uint64
         for f in ("orc_ad_slice", "orc_ad_volume", "orc_sad_slice", "orc_sad_wta_direct", "orc_sad_wta",
@@ -190,6 +195,24 @@ def median(img, r: int) -> np.ndarray:
     img = _u8(img)
     out = np.empty_like(img)
     lib().orc_median(img, out, img.shape[0], img.shape[1], r)
+    return out
+
+
+def remap(src, mapx, mapy) -> np.ndarray:
+    """CPU_Remap / kernalRemap (Utility.cpp:236-264, Device.cu:127-167): bilinear, OOB -> 0, round-nearest-even."""
+    src = _u8(src)
+    mx = np.ascontiguousarray(mapx, np.float32); my = np.ascontiguousarray(mapy, np.float32)
+    out = np.empty_like(src)
+    lib().orc_remap(src, mx, my, src.shape[0], src.shape[1], out)
+    return out
+
+
+def cvtcolor(src3, truncate: bool = False) -> np.ndarray:
+    """kernalCvtColor (round, Device.cu:136-143) / cvtColor_cpu (truncate, Utility.cpp:289-298)."""
+    a = np.ascontiguousarray(src3, np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    out = np.empty(a.shape[:2], np.uint8)
+    lib().orc_cvtcolor(a.reshape(-1, 3).reshape(a.shape[0], -1), a.shape[0], a.shape[1], int(truncate), out)
     return out
 
 

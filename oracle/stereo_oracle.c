@@ -377,6 +377,50 @@ void orc_median(const u8* src, u8* dst, int H, int W, int r) {
   }
 }
 
+/* ------------------------------------------------------------------------------------
+ * SURVEY 8(f)-1  bilinear remap, BlockMatching/Utility.cpp:236-264 (CPU_Remap + CPU_BilinearInterpolation;
+ * GPU twin kernalRemap + BilinearInterpolation, Device.cu:127-134,152-167).  Note the argument order quirk:
+ * the interpolator is called as (src, ycoo, xcoo), so its `x` is the ROW coordinate.  Out-of-range
+ * (x1 < 0 || x2 >= rows || y1 < 0 || y2 >= cols) -> 0.  Result rounded to nearest-even and saturated
+ * (saturate_cast<uchar> == cvt.rni.sat.u8.f32, Device.cu:148).  Every product and sum is rounded to float
+ * separately (no FMA contraction; this file is built with -ffp-contract=off).
+ * ---------------------------------------------------------------------------------- */
+static inline u8 sat_rne_u8(float v) {
+  float r = nearbyintf(v); /* default rounding mode: to nearest, ties to even */
+  if (!(r > 0.0f)) return 0;
+  if (r > 255.0f) return 255;
+  return (u8)r;
+}
+
+void orc_remap(const u8* src, const float* mapx, const float* mapy, int rows, int cols, u8* dst) {
+  for (int row = 0; row < rows; ++row)
+    for (int col = 0; col < cols; ++col) {
+      size_t i = (size_t)row * cols + col;
+      float x = mapy[i], y = mapx[i]; /* CPU_BilinearInterpolation(src, ycoo, xcoo) */
+      int x1 = (int)floorf(x), y1 = (int)floorf(y), x2 = x1 + 1, y2 = y1 + 1;
+      float result = 0.0f;
+      if (!(x1 < 0 || x2 >= rows || y1 < 0 || y2 >= cols)) {
+        u8 Q11 = src[(size_t)x1 * cols + y1], Q12 = src[(size_t)x1 * cols + y2];
+        u8 Q21 = src[(size_t)x2 * cols + y1], Q22 = src[(size_t)x2 * cols + y2];
+        float left = ((float)x2 - x) * (float)Q11 + (x - (float)x1) * (float)Q21;
+        float right = ((float)x2 - x) * (float)Q12 + (x - (float)x1) * (float)Q22;
+        result = ((float)y2 - y) * left + (y - (float)y1) * right;
+      }
+      dst[i] = sat_rne_u8(result);
+    }
+}
+
+/* SURVEY 8(f)-2  3-channel -> gray, weights .299/.587/.114 applied to channels 0/1/2 as stored
+ * (the reference feeds OpenCV BGR data, Caller.cpp:106).  truncate = 1: cvtColor_cpu, Utility.cpp:289-298
+ * ((uchar)channelSum); truncate = 0: kernalCvtColor, Device.cu:136-143 (round-nearest-even, saturate). */
+void orc_cvtcolor(const u8* src3, int rows, int cols, int truncate, u8* dst) {
+  size_t n = (size_t)rows * cols;
+  for (size_t i = 0; i < n; ++i) {
+    float sum = .299f * (float)src3[3 * i] + .587f * (float)src3[3 * i + 1] + .114f * (float)src3[3 * i + 2];
+    dst[i] = truncate ? (u8)sum : sat_rne_u8(sum);
+  }
+}
+
 /* FNV-1a 64 over a byte buffer: digest format of tests/golden/  */
 uint64_t orc_fnv1a64(const u8* p, size_t n) {
   uint64_t h = 0xcbf29ce484222325ULL;

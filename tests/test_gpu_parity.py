@@ -258,3 +258,47 @@ def test_errors_are_reported(ctx):
         ctx.stereo_batch(np.zeros((2000, 16), np.uint8), np.zeros((2000, 16), np.uint8), g.make_params("sad", 5, 16))
     with pytest.raises(TypeError):
         ctx.block_matching(z.astype(np.float32), z, 5, 16)
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8(f) rows
+def test_remap_bit_exact(ctx, orc):
+    """remap_gpu / kernalRemap (Device.cu:127-167) == CPU_Remap (Utility.cpp:236-264): rig rectification maps at
+    1280x720 (BASELINE config 3's host-side step, here on the GPU) and random maps with out-of-range targets."""
+    L, R, _ = gdata.synthetic_pair(720, 1280, 5)
+    m1x, m1y, m2x, m2y = gdata.rectify_maps(1280, 720)
+    assert np.array_equal(ctx.remap(L, m1x, m1y), orc.remap(L, m1x, m1y))
+    assert np.array_equal(g.remap_gpu(L, R, m1x, m1y, m2x, m2y), orc.remap(L, m1x, m1y))  # returns the LEFT image
+    rng = np.random.default_rng(17)
+    img = rng.integers(0, 256, (97, 131), dtype=np.uint8)
+    mx = (rng.random((97, 131), dtype=np.float32) * 140 - 4).astype(np.float32)
+    my = (rng.random((97, 131), dtype=np.float32) * 105 - 4).astype(np.float32)
+    mx[::7, ::5] = np.floor(mx[::7, ::5]) + 0.5  # exact .5 weights: exercises round-half-to-even
+    assert np.array_equal(ctx.remap(img, mx, my), orc.remap(img, mx, my))
+
+
+def test_cvtcolor_bit_exact(ctx, orc):
+    rng = np.random.default_rng(19)
+    rgb = rng.integers(0, 256, (200, 320, 3), dtype=np.uint8)  # the 320x200 size cvtColorTest uses (Caller.cpp:81)
+    assert np.array_equal(ctx.cvtcolor(rgb), orc.cvtcolor(rgb))                       # kernalCvtColor (rounds)
+    assert np.array_equal(ctx.cvtcolor(rgb, truncate=True), orc.cvtcolor(rgb, True))  # cvtColor_cpu (truncates)
+    assert np.array_equal(g.cvtColor_gpu(rgb), orc.cvtcolor(rgb))
+    allv = np.stack(np.meshgrid(np.arange(256), np.arange(0, 256, 5), np.arange(0, 256, 17), indexing="ij"), -1)
+    allv = allv.reshape(256, -1, 3).astype(np.uint8)
+    assert np.array_equal(ctx.cvtcolor(allv), orc.cvtcolor(allv))
+
+
+def test_determinism_under_repetition(ctx, fx):
+    """The fused kernels exchange rows through shared memory under two barriers per row and an asynchronous
+    staging ring: any race shows up as run-to-run differences."""
+    L, R = fx["Art_L"], fx["Art_R"]
+    p = g.make_params("gf", 9, 64, lr_check=True, median_radius=3)
+    ref_d, ref_m = ctx.stereo_batch(L, R, p)
+    sad = ctx.block_matching(L, R, 5, 64)
+    for _ in range(8):
+        d, m = ctx.stereo_batch(L, R, p)
+        assert np.array_equal(d, ref_d) and np.array_equal(m, ref_m)
+        assert np.array_equal(ctx.block_matching(L, R, 5, 64), sad)
+    Lb = np.stack([L] * 6); Rb = np.stack([R] * 6)
+    db, mb = ctx.stereo_batch(Lb, Rb, p)  # 6 frames > max_batch/2: exercises the two-slot host pipeline
+    for i in range(6):
+        assert np.array_equal(db[i], ref_d) and np.array_equal(mb[i], ref_m)

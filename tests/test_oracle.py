@@ -171,3 +171,31 @@ def test_packed_min_equivalence(fx, orc):
         parts.append(keys)
     disp = (np.minimum.reduce(parts) & 0xFF).astype(np.uint8)
     assert np.array_equal(disp, orc.sad_wta(L, R, r, D))
+
+
+def test_remap_and_cvtcolor_restatements(orc):
+    """CPU_Remap (Utility.cpp:236-264) and kernalCvtColor / cvtColor_cpu, vs float32 numpy."""
+    rng = np.random.default_rng(13)
+    h, w = 37, 53
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    mx = (rng.random((h, w), dtype=np.float32) * (w + 6) - 3).astype(np.float32)
+    my = (rng.random((h, w), dtype=np.float32) * (h + 6) - 3).astype(np.float32)
+    out = orc.remap(img, mx, my)
+    f = np.float32
+    x, y = my, mx  # the interpolator's x is the row coordinate
+    x1 = np.floor(x).astype(np.int64); y1 = np.floor(y).astype(np.int64)
+    ok = ~((x1 < 0) | (x1 + 1 >= h) | (y1 < 0) | (y1 + 1 >= w))
+    xc, yc = np.clip(x1, 0, h - 2), np.clip(y1, 0, w - 2)
+    Q11, Q12 = img[xc, yc].astype(f), img[xc, yc + 1].astype(f)
+    Q21, Q22 = img[xc + 1, yc].astype(f), img[xc + 1, yc + 1].astype(f)
+    wx2 = ((x1 + 1).astype(f) - x).astype(f); wx1 = (x - x1.astype(f)).astype(f)
+    left = ((wx2 * Q11).astype(f) + (wx1 * Q21).astype(f)).astype(f)
+    right = ((wx2 * Q12).astype(f) + (wx1 * Q22).astype(f)).astype(f)
+    res = ((((y1 + 1).astype(f) - y).astype(f) * left).astype(f) + ((y - y1.astype(f)).astype(f) * right).astype(f)).astype(f)
+    ref = np.where(ok, np.clip(np.rint(res), 0, 255), 0).astype(np.uint8)  # np.rint rounds half to even
+    assert np.array_equal(out, ref)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    s = ((f(.299) * rgb[..., 0].astype(f)).astype(f) + (f(.587) * rgb[..., 1].astype(f)).astype(f)).astype(f)
+    s = (s + (f(.114) * rgb[..., 2].astype(f)).astype(f)).astype(f)
+    assert np.array_equal(orc.cvtcolor(rgb, truncate=True), s.astype(np.uint8))
+    assert np.array_equal(orc.cvtcolor(rgb, truncate=False), np.clip(np.rint(s), 0, 255).astype(np.uint8))
