@@ -411,7 +411,7 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   u8* stage_base = smem_raw + 256;
   u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);
   const u32 bar0 = smem_u32(smem_raw);  // two 8-byte mbarriers at the start of shared memory
-  const bool producer = (threadIdx.x == 0);  // lane 0 of every warp issues its share of the bulk copies
+  const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
 
   for (int i = threadIdx.y * WARP + threadIdx.x; i < 6 * planew; i += runs * LPR) exch[i] = 0u;
   if (threadIdx.x == 0 && threadIdx.y == 0) {
@@ -439,38 +439,32 @@ gf_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float*
   // consumer-side byte offset of this thread's first pixel inside a staged O row
   const int ooff = oalign + run * K + (g.view == 0 ? (LPR - 1 - lane) : lane);
 
-  // The 20 bulk copies of a step are spread over the warps (lane 0 of warp w issues copies w, w+NW, ...): issued by a
-  // single thread they serialise (~50 cycles each) on that warp and every other warp waits for it at the barrier.
-  constexpr int NCOPY = 20;
-  constexpr int NW = RUNS * LPR / WARP;
-  const int warp_id = threadIdx.y;
+  // One elected thread issues the 20 bulk copies of a step (uniform-datapath address arithmetic; spreading them
+  // over the warps was measured: same speed, +6 instructions per DE of per-lane address arithmetic).
   auto issue = [&](int t, int s) {
     const u32 bar = bar0 + 8 * s;
     const u32 dst = smem_u32(stage_base + (size_t)s * sg.bytes);
-    if (warp_id == 0) mbar_expect_tx(bar, (u32)sg.bytes);
-    for (int i = warp_id; i < NCOPY; i += NW) {
-      if (i < 6) {  // guide (even) / other-image (odd) rows t+R, t-R-1, t-3R-2
-        const int k = i >> 1;
-        const int row = k == 0 ? t + R : (k == 1 ? t - R - 1 : t - 3 * R - 2);
-        const long long ro = (long long)max(row_lo, min(row_hi, row)) * pitch;
-        if ((i & 1) == 0) bulk_g2s(dst + k * TWt, gsrc + ro, TWt, bar);
-        else bulk_g2s(dst + sg.off_O + k * sg.OW, osrc + ro, sg.OW, bar);
-      } else if (i < 18) {  // per row t / t-2R-1: coefficient row + 5 statistic rows
-        const int k = i - 6, which = k / 6, pl = k - which * 6;
-        const int row = which == 0 ? t : t - 2 * R - 1;
-        const long long ro = (long long)max(row_lo, min(row_hi, row)) * pitch;
-        if (pl == 5) bulk_g2s(dst + sg.off_COEF + which * 4 * TWt, ssrc + ST_COEF * plane_elems + ro, 4 * TWt, bar);
-        else bulk_g2s(dst + sg.off_ST + (which * 5 + pl) * 4 * TWt, ssrc + (size_t)pl * plane_elems + ro, 4 * TWt, bar);
-      } else {  // output row t-R: I-128 and 1/N (18), centres (19)
-        const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
-        if (i == 18) {
-          bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
-          bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
-        } else {
-          bulk_g2s(dst + sg.off_CEN, csrc + ry, TWt, bar);
-        }
-      }
+    mbar_expect_tx(bar, (u32)sg.bytes);
+    const int rows3[3] = {t + R, t - R - 1, t - 3 * R - 2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const long long ro = (long long)max(row_lo, min(row_hi, rows3[i])) * pitch;
+      bulk_g2s(dst + i * TWt, gsrc + ro, TWt, bar);
+      bulk_g2s(dst + sg.off_O + i * sg.OW, osrc + ro, sg.OW, bar);
     }
+    const int rows2[2] = {t, t - 2 * R - 1};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long ro = (long long)max(row_lo, min(row_hi, rows2[i])) * pitch;
+      bulk_g2s(dst + sg.off_COEF + i * 4 * TWt, ssrc + ST_COEF * plane_elems + ro, 4 * TWt, bar);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        bulk_g2s(dst + sg.off_ST + (i * 5 + k) * 4 * TWt, ssrc + (size_t)k * plane_elems + ro, 4 * TWt, bar);
+    }
+    const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
+    bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
+    bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
+    bulk_g2s(dst + sg.off_CEN, csrc + ry, TWt, bar);
   };
 
   const int dd = min(d, MAX_DISP - 1);
