@@ -170,7 +170,32 @@ def _extra_config(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.config == "c4":
+    if args.config == "c2":
+        # all nine Middlebury sets (tests/golden/middlebury_gray.npz), D = 64, GF r = 9 with L-R check; the sets come
+        # in three sizes, so they run as three same-size batches (the batch ABI takes one size per call)
+        fx = np.load(os.path.join(ROOT, "tests", "golden", "middlebury_gray.npz"))
+        sets = ["Art", "Books", "Computer", "Dolls", "Drumsticks", "Dwarves", "Laundry", "Moebius", "Reindeer"]
+        groups = {}
+        for sname in sets:
+            groups.setdefault(fx[sname + "_L"].shape, []).append(sname)
+        p = g.make_params("gf", 9, 64, lr_check=True)
+        ctx = g.StereoContext(370, 463, 64, 6, device=local_rank)
+        bufs = []
+        for shape, names in groups.items():
+            Ld = torch.from_numpy(np.stack([fx[n_ + "_L"] for n_ in names])).cuda()
+            Rd = torch.from_numpy(np.stack([fx[n_ + "_R"] for n_ in names])).cuda()
+            bufs.append((Ld, Rd, torch.empty_like(Ld), torch.empty_like(Ld), len(names), shape))
+
+        def step():
+            for Ld, Rd, Dd_, Md_, k, shape in bufs:
+                ctx.stereo_device(Ld.data_ptr(), Rd.data_ptr(), Dd_.data_ptr(), Md_.data_ptr(), k, shape[0], shape[1], p, sh)
+
+        Dd = bufs[0][2]
+        h, w, d = 370, 463, 64
+        de_step, scaling = sum(b[4] * b[5][0] * b[5][1] for b in bufs) * 64 * world, "weak"
+        workload = "config2: the nine Middlebury third-size sets, 64 disparities, GF r=9 with L-R check (3 same-size batches)"
+        par = f"replicated x{world}" if world > 1 else "1 GPU"
+    elif args.config == "c4":
         h, w, d, n = 1080, 1920, 192, min(args.frames, 16)
         p = g.make_params("gf", 9, d, lr_check=True, median_radius=3)
         f0, _ = shard_frames(n * world, world, rank)
@@ -239,7 +264,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 (default, the contract workload): 720p x128 GF frame batches; c4: 1080p x192 GF+LR+median "
                          "frame batches; c5: one 3840x2160 x256 GF pair split by disparity range across the ranks")
     args = ap.parse_args()
