@@ -10,6 +10,7 @@
 
 #include "gsm_common.cuh"
 #include "gsm_gf.cuh"
+#include "gsm_gf3.cuh"
 #include "gsm_sad.cuh"
 #include "gsm_util.cuh"
 
@@ -56,6 +57,13 @@ struct gsm_ctx {
   std::vector<cudaEvent_t> ev;  // (start, stop) pairs of the fused kernels of the last device call
   size_t ev_used = 0;
 };
+
+// strip halo (columns) a fused kernel needs on each side of its output columns
+#ifdef GSM_GF_V2
+static int stage_halo_of(int mode, int radius) { return mode == GSM_MODE_SAD ? radius : 2 * radius; }
+#else
+static int stage_halo_of(int mode, int radius) { return radius; }  // GF v3: stage 1 needs no exchanged halo
+#endif
 
 static int max_pitch(int cols) { return round_up(PADL_BASE + 16 + cols + PADR, 16); }
 
@@ -307,6 +315,11 @@ static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols
   return GSM_OK;
 }
 
+#ifdef GSM_GF_V2
+#define GF_KERNEL gf_wta_kernel
+#else
+#define GF_KERNEL gf3_wta_kernel
+#endif
 #define GF_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 
 template <bool EXPORT>
@@ -321,8 +334,12 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   constexpr int runs = GSM_GF_RUNS, lpr = 16;
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
-  Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, 2 * R, 6, HL4, lpr);
+  Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, stage_halo_of(GSM_MODE_GF, R), 6, HL4, lpr);
+#ifdef GSM_GF_V2
   pl.smem = gf_smem_bytes(runs, K, HL4, lpr);
+#else
+  pl.smem = gf3_smem_bytes(runs, K, HL4, lpr);
+#endif
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
   pl.g.export_nd = end_;
@@ -340,7 +357,11 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     gf_stats_kernel<<<dim3((cols + GS_T - 1) / GS_T, (rows + GS_T - 1) / GS_T, n), dim3(GS_T, 8), sm, s>>>(G, stats, pg,
                                                                                                           R, eps);
     c->launches++;
+#ifdef GSM_GF_V2
     gf_coef_kernel<<<dim3((cols + 255) / 256, rows + 2 * R + 1, n), 256, 0, s>>>(G, stats, pg, R);
+#else
+    gf_hcoef_kernel<<<dim3((cols + 64 + 255) / 256, pg.plane_rows, n), 256, 0, s>>>(G, stats, pg, R);
+#endif
     c->launches++;
     gf_centre_kernel<<<dim3((pg.pitch / 16 + 63) / 64, rows, n), 64, 0, s>>>(stats, pg);
     c->launches++;
@@ -351,7 +372,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   switch (R) {
 #define X(r)                                                                                  \
   case r: {                                                                                   \
-    auto kfn = gf_wta_kernel<r, K, runs, lpr, EXPORT>;                                        \
+    auto kfn = GF_KERNEL<r, K, runs, lpr, EXPORT>;                                            \
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
     kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                          \
     break;                                                                                    \
@@ -404,7 +425,7 @@ static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int c
                          float eps, int view, const u8* Ltight, const u8* Rtight, i64* keys, cudaStream_t s,
                          void* export_ptr = nullptr, int ed0 = 0, int end_ = 0) {
   const size_t npx = (size_t)n * rows * cols;
-  const int stage_halo = p->mode == GSM_MODE_SAD ? p->radius : 2 * p->radius;
+  const int stage_halo = stage_halo_of(p->mode, p->radius);
   const PlaneGeom pg = make_plane_geom(rows, cols, round_up(stage_halo, 4));
   int rc;
   // guide / other planes.  view 0: guide L, other R (zero pad).  view 1: guide R, other L right-replicated.

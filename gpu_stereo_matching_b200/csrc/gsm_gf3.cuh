@@ -1,0 +1,409 @@
+// gsm_gf3.cuh -- guided-filter fused kernel, third layout: stage 1 HORIZONTAL-FIRST, entirely inside the thread.
+//
+// gsm_gf.cuh (second layout) sums stage 1 vertically in registers and exchanges the vertical sums of four integer
+// quantities through shared memory to slide them horizontally: 4 of its 6 exchange planes, one of its two CTA
+// barriers per row and half of its strip halo exist only for that.  Here a thread builds the HORIZONTAL window
+// sums of p and I*p of its 16 columns directly from the staged image bytes of the 16+2r columns around them
+// (AD is 4 pixels per VABSDIFF4, so the redundant halo pixels are nearly free; the slide is one PRMT + two IDP.2A
+// per column and row, with the (+I_in, -I_out) coefficient word precomputed per pixel), and accumulates them
+// vertically:      S(t) += H(t+r) - H(t-r-1)           (lead)        S'(t') += H(t-r-1) - H(t-3r-2)      (trail)
+// The box sums S_p, S_Ip come out exact without any exchange.  What remains in shared memory is the stage-2
+// exchange of (V_A, V_B) -- double buffered, so ONE barrier per row -- and the asynchronous input stage.
+// Everything else (exact int32 numerator, lead/trail recomputation, local centres, packed-min WTA) is as in
+// gsm_gf.cuh, whose header comment describes the arithmetic.
+#pragma once
+#include "gsm_gf.cuh"
+
+namespace gsm {
+
+// IDP.2A coefficient plane of the horizontal slide: HC[y][x] = I[y][x+R] - 65536 * I[y][x-R-1]
+// (lo16 = +I of the column entering the window of x, hi16 = -I of the column leaving it).  Stored in ST_COEF.
+__global__ void gf_hcoef_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom pg, int R) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x - 32;  // a margin of columns left and right of the image
+  const int y = (int)blockIdx.y - PADV;
+  const int f = blockIdx.z;
+  if (x >= pg.W + 32) return;
+  const u8* row = Ip + (size_t)f * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + pg.xoff;
+  const int in = row[x + R];
+  const int out = row[x - R - 1];
+  int* coef = reinterpret_cast<int*>(stats + ((size_t)f * GF_STAT_PLANES + ST_COEF) * pg.plane_stride);
+  coef[(size_t)(PADV + y) * pg.pitch + pg.xoff + x] = in - 65536 * out;
+}
+
+// Stage of one march step (TWt strip columns):
+//   G[3][TWt+32] u8      guide rows t+R, t-R-1, t-3R-2, columns [xs-16, xs+TWt+16)
+//   O[3][TWt+64] u8      other-image rows, shifted window covering the CTA's LPR disparities and the +-12 halo
+//   HC[3][TWt] i32       slide coefficients of the same three rows
+//   ST[2][5][TWt]        N, S_I, 1/den, mean_I-128, 1/N at rows t (lead) and t-2R-1 (trail)
+//   ICY[TWt], INVNY[TWt] I-128 and 1/N at the output row t-R;  CEN[TWt/4] local centres of the output row
+struct Gf3Stage {
+  int TWt, GW, OW;
+  int off_O, off_HC, off_ST, off_ICY, off_INVNY, off_CEN, bytes;
+  __host__ __device__ constexpr explicit Gf3Stage(int twt)
+      : TWt(twt), GW(twt + 32), OW(twt + 64), off_O(3 * (twt + 32)), off_HC(3 * (twt + 32) + 3 * (twt + 64)),
+        off_ST(3 * (twt + 32) + 3 * (twt + 64) + 12 * twt), off_ICY(3 * (twt + 32) + 3 * (twt + 64) + 52 * twt),
+        off_INVNY(3 * (twt + 32) + 3 * (twt + 64) + 56 * twt), off_CEN(3 * (twt + 32) + 3 * (twt + 64) + 60 * twt),
+        bytes(3 * (twt + 32) + 3 * (twt + 64) + 61 * twt) {}
+};
+
+__host__ __device__ inline size_t gf3_smem_bytes(int runs, int K, int HL4, int LPR) {
+  // barriers + centres | 2 input stages | 2 (double buffer) x 2 (V_A, V_B) exchange planes
+  return 512 + 2 * (size_t)Gf3Stage(runs * K).bytes + 4 * (size_t)LPR * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+}
+
+constexpr int GF3_WB = 40;  // window bytes per thread and row: columns x0-12 .. x0+27 (10 words)
+
+// AD bytes of the thread's 40-column window of one staged row
+__device__ __forceinline__ void gf3_ad_window(const u8* grow16, const u8* orow, int ooff, u32 (&g)[10], u32 (&p)[10]) {
+  // grow16 = staged guide row + run*16: 16-byte aligned, byte 0 is column x0-16
+  const uint4 a = reinterpret_cast<const uint4*>(grow16)[0];
+  const uint4 b = reinterpret_cast<const uint4*>(grow16)[1];
+  const uint4 c = reinterpret_cast<const uint4*>(grow16)[2];
+  g[0] = a.y; g[1] = a.z; g[2] = a.w; g[3] = b.x; g[4] = b.y; g[5] = b.z; g[6] = b.w; g[7] = c.x; g[8] = c.y; g[9] = c.z;
+  u32 ow[10];
+  lds_unaligned<GF3_WB>(orow, ooff, ow);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) p[i] = __vabsdiffu4(g[i], ow[i]);
+}
+
+// byte mask (0xff per valid byte) of window word i: column inside the image and, for the left view, x >= d
+__device__ __forceinline__ u32 gf3_word_mask(int xw, int W, int lo) {
+  u32 m = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) m |= (xw + b < W && xw + b >= lo) ? (0xffu << (8 * b)) : 0u;
+  return m;
+}
+
+// mask of the bytes of window word i (bytes 4i..4i+3) that lie in [LO, HI]
+template <int LO, int HI>
+__host__ __device__ constexpr u32 range_mask(int i) {
+  u32 m = 0;
+  for (int b = 0; b < 4; ++b)
+    if (4 * i + b >= LO && 4 * i + b <= HI) m |= 0xffu << (8 * b);
+  return m;
+}
+
+// window sums of p and I*p over window bytes [12-R, 12+R] (the window of the thread's column 0)
+template <int R>
+__device__ __forceinline__ void gf3_init_sums(const u32 (&g)[10], const u32 (&p)[10], int& hp, int& hip) {
+  constexpr int LO = 12 - R, HI = 12 + R;
+  u32 sp = 0, sip = 0;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const u32 m = range_mask<LO, HI>(i);
+    if (m != 0) {
+      sp = __dp4a(p[i], m & 0x01010101u, sp);
+      sip = __dp4a(g[i] & m, p[i], sip);
+    }
+  }
+  hp = (int)sp;
+  hip = (int)sip;
+}
+
+template <int R, int K, int RUNS, int LPR, bool EXPORT>
+__global__ void __launch_bounds__(RUNS * LPR, 1)
+gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
+               i64* __restrict__ keys, FusedGeom g) {
+  static_assert(K == 16 && R <= 12 && R >= 1, "16-column runs, window halo of at most 12 columns");
+  static_assert(LPR == 32 || LPR == 16, "lanes per run");
+  constexpr int HL4 = (R + 3) / 4 * 4;
+  extern __shared__ __align__(128) u8 smem_raw[];
+
+  const int lane = threadIdx.x & (LPR - 1);
+  const int run = threadIdx.y * (WARP / LPR) + threadIdx.x / LPR;
+  constexpr int runs = RUNS;
+  const int strip = blockIdx.x;
+  const int d0 = g.d_begin + blockIdx.y * LPR;
+  const int d = d0 + lane;
+  const int frame = blockIdx.z / g.bands;
+  const int band = blockIdx.z - frame * g.bands;
+  const int H = g.pg.H, W = g.pg.W, pitch = g.pg.pitch;
+  const int yb0 = band * g.band_rows;
+  const int yb1 = min(H, yb0 + g.band_rows);
+  if (yb0 >= H) return;
+
+  constexpr int TWt = runs * K;
+  constexpr Gf3Stage sg(TWt);
+  constexpr int pitchw = exch_pitch_words(runs, K, HL4);
+  constexpr int planew = LPR * pitchw;
+  float* ccs = reinterpret_cast<float*>(smem_raw + 64);  // [2][<=48] per-run centres, double buffered
+  u8* stage_base = smem_raw + 512;
+  u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);  // [2 buffers][V_A, V_B][LPR][pitchw]
+  const u32 bar0 = smem_u32(smem_raw);
+  const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
+
+  for (int i = threadIdx.y * WARP + threadIdx.x; i < 4 * planew; i += runs * LPR) exch[i] = 0u;
+  if (producer) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  u32* xb = exch + (size_t)lane * pitchw + HL4 + run * K;
+
+  const int xs = strip * g.TW - g.hl;
+  const int x0 = xs + run * K;
+  const size_t plane_elems = g.pg.plane_stride;
+  const int row_lo = -PADV, row_hi = H + PADV - 1;
+
+  const size_t org = (size_t)PADV * pitch + g.pg.xoff + xs;
+  const u8* gsrc = Gp + (size_t)frame * g.pg.plane_stride + org - 16;
+  const int ostart = g.pg.xoff + xs - 12 + (g.view == 0 ? -(d0 + LPR - 1) : d0);
+  const int oalign = ostart & 15;
+  const u8* osrc = Op + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + (ostart - oalign);
+  const float* ssrc = stats + (size_t)frame * GF_STAT_PLANES * plane_elems + org;
+  const float* csrc = stats + ((size_t)frame * GF_STAT_PLANES + ST_CEN) * plane_elems + (size_t)PADV * pitch +
+                      (g.pg.xoff + xs) / 4;
+  const int ooff = oalign + run * K + (g.view == 0 ? (LPR - 1 - lane) : lane);
+
+  auto issue = [&](int t, int s) {
+    const u32 bar = bar0 + 8 * s;
+    const u32 dst = smem_u32(stage_base + (size_t)s * sg.bytes);
+    mbar_expect_tx(bar, (u32)sg.bytes);
+    const int rows3[3] = {t + R, t - R - 1, t - 3 * R - 2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const long long ro = (long long)max(row_lo, min(row_hi, rows3[i])) * pitch;
+      bulk_g2s(dst + i * sg.GW, gsrc + ro, sg.GW, bar);
+      bulk_g2s(dst + sg.off_O + i * sg.OW, osrc + ro, sg.OW, bar);
+      bulk_g2s(dst + sg.off_HC + i * 4 * TWt, ssrc + ST_COEF * plane_elems + ro, 4 * TWt, bar);
+    }
+    const int rows2[2] = {t, t - 2 * R - 1};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long ro = (long long)max(row_lo, min(row_hi, rows2[i])) * pitch;
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        bulk_g2s(dst + sg.off_ST + (i * 5 + k) * 4 * TWt, ssrc + (size_t)k * plane_elems + ro, 4 * TWt, bar);
+    }
+    const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
+    bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
+    bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
+    bulk_g2s(dst + sg.off_CEN, csrc + ry, TWt, bar);
+  };
+
+  // window bytes that may contribute: inside the image and (left view) x >= d  (BlockMatching.cpp:147-149)
+  const int dd = min(d, MAX_DISP - 1);
+  const int col_lo = g.view == 0 ? dd : 0;
+  const bool full = (x0 - 12 >= col_lo) && (x0 + 27 < W);
+  const bool need_mask = __any_sync(0xffffffffu, !full);
+
+  const int out0 = strip * g.TW;
+  const int c_lo = max(0, out0 - x0);
+  int c_hi = min(K - 1, min(out0 + g.TW, W) - 1 - x0);
+  if (d >= g.d_end) c_hi = -1;
+  const bool all_valid = __all_sync(0xffffffffu, c_lo == 0 && c_hi == K - 1);
+  // warp-uniform stage skipping: (a, b) is needed on strip columns [hl-R, hl+TW+R) inside the image (+-R)
+  const bool need_out = __any_sync(0xffffffffu, min(K - 1, min(out0 + g.TW, W) - 1 - x0) >= c_lo);
+  const bool need_ab = __any_sync(
+      0xffffffffu, (run * K < g.hl + g.TW + R) && (run * K + K > g.hl - R) && (x0 < W + R) && (x0 + K > -R));
+
+  int Sp_l[K], SIp_l[K], Sp_t[K], SIp_t[K];
+  float VA[K], VB[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) { Sp_l[c] = SIp_l[c] = Sp_t[c] = SIp_t[c] = 0; VA[c] = VB[c] = 0.f; }
+  float cc = 0.f;
+
+  const int r0 = yb0 - 2 * R;
+  const int a0 = yb0 - R;
+  constexpr int COEF_PM = (int)0xFFFF0001;
+  const int t_begin = yb0 - 3 * R, t_end = yb1 + R;
+
+  if (producer) issue(t_begin, 0);
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int it = t - t_begin;
+    const int s = it & 1;
+    mbar_wait(bar0 + 8 * s, (u32)((it >> 1) & 1));
+    const u8* stg = stage_base + (size_t)s * sg.bytes;
+    const int t2 = t - 2 * R - 1;
+
+    if (need_ab) {
+      // ---------------- stage 1: horizontal window sums of the three rows, folded into the vertical sums
+      u32 pn[10], pm[10], po[10];
+      int hp_n, hip_n, hp_m = 0, hip_m = 0, hp_o = 0, hip_o = 0;
+      const bool has_m = t - R - 1 >= r0, has_o = t - 3 * R - 2 >= r0;
+      {
+        u32 gn[10];
+        gf3_ad_window(stg + run * K, stg + sg.off_O, ooff, gn, pn);
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) pn[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
+        }
+        gf3_init_sums<R>(gn, pn, hp_n, hip_n);
+      }
+      if (has_m) {
+        u32 gm[10];
+        gf3_ad_window(stg + sg.GW + run * K, stg + sg.off_O + sg.OW, ooff, gm, pm);
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) pm[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
+        }
+        gf3_init_sums<R>(gm, pm, hp_m, hip_m);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) pm[i] = 0u;
+      }
+      if (has_o) {
+        u32 go[10];
+        gf3_ad_window(stg + 2 * sg.GW + run * K, stg + sg.off_O + 2 * sg.OW, ooff, go, po);
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) po[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
+        }
+        gf3_init_sums<R>(go, po, hp_o, hip_o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) po[i] = 0u;
+      }
+      const int* hcn = reinterpret_cast<const int*>(stg + sg.off_HC) + run * K;
+      const int* hcm = hcn + TWt;
+      const int* hco = hcm + TWt;
+#pragma unroll
+      for (int g4 = 0; g4 < K; g4 += 4) {
+        const int4 cn4 = *reinterpret_cast<const int4*>(hcn + g4);
+        const int4 cm4 = *reinterpret_cast<const int4*>(hcm + g4);
+        const int4 co4 = *reinterpret_cast<const int4*>(hco + g4);
+        const int cn[4] = {cn4.x, cn4.y, cn4.z, cn4.w}, cm[4] = {cm4.x, cm4.y, cm4.z, cm4.w},
+                  co[4] = {co4.x, co4.y, co4.z, co4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = g4 + j;
+          if (c > 0) {
+            // window byte entering: 12 + c + R, leaving: 12 + c - R - 1
+            const int bi = 12 + c + R, bo = 12 + c - R - 1;
+            const u32 sel = (u32)(bi & 3) | ((4u + (u32)(bo & 3)) << 4);
+            const u32 qn = __byte_perm(pn[bi >> 2], pn[bo >> 2], sel);  // {p_in, p_out, x, x}
+            const u32 qm = __byte_perm(pm[bi >> 2], pm[bo >> 2], sel);
+            const u32 qo = __byte_perm(po[bi >> 2], po[bo >> 2], sel);
+            hp_n = dp2a_lo_su(COEF_PM, qn, hp_n);
+            hip_n = dp2a_lo_su(cn[j], qn, hip_n);
+            hp_m = dp2a_lo_su(COEF_PM, qm, hp_m);
+            hip_m = dp2a_lo_su(cm[j], qm, hip_m);
+            hp_o = dp2a_lo_su(COEF_PM, qo, hp_o);
+            hip_o = dp2a_lo_su(co[j], qo, hip_o);
+          }
+          Sp_l[c] += hp_n - hp_m;
+          SIp_l[c] += hip_n - hip_m;
+          Sp_t[c] += hp_m - hp_o;
+          SIp_t[c] += hip_m - hip_o;
+        }
+      }
+
+      // ---------------- (a, b) of the lead and trail rows folded into the stage-2 vertical sums
+      {
+        const float target = reinterpret_cast<const float*>(stg + sg.off_CEN)[run * (K / 4)];
+        const float dc = target - cc;
+        if (fabsf(dc) > GF_RECENTRE) {
+#pragma unroll
+          for (int c = 0; c < K; ++c) VB[c] = fmaf(dc, VA[c], VB[c]);
+          cc = target;
+        }
+      }
+      const float* st_l = reinterpret_cast<const float*>(stg + sg.off_ST) + run * K;
+#pragma unroll
+      for (int g4 = 0; g4 < K; g4 += 4) {
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          if (which == 0 ? (t >= a0) : (t2 >= a0)) {
+            const float* st = st_l + which * 5 * TWt;
+            const int4 N = *reinterpret_cast<const int4*>(st + ST_N * TWt + g4);
+            const int4 SI = *reinterpret_cast<const int4*>(st + ST_SI * TWt + g4);
+            const float4 invden = *reinterpret_cast<const float4*>(st + ST_INVDEN * TWt + g4);
+            const float4 cmean = *reinterpret_cast<const float4*>(st + ST_CMEAN * TWt + g4);
+            const float4 invn = *reinterpret_cast<const float4*>(st + ST_INVN * TWt + g4);
+            const int Nn[4] = {N.x, N.y, N.z, N.w}, SIi[4] = {SI.x, SI.y, SI.z, SI.w};
+            const float idn[4] = {invden.x, invden.y, invden.z, invden.w}, cmv[4] = {cmean.x, cmean.y, cmean.z, cmean.w},
+                        inn[4] = {invn.x, invn.y, invn.z, invn.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = g4 + j;
+              const int sp = which == 0 ? Sp_l[c] : Sp_t[c];
+              const int sip = which == 0 ? SIp_l[c] : SIp_t[c];
+              const int num = Nn[j] * sip - SIi[j] * sp;  // exact modulo 2^32; true value fits int32 for r <= 9
+              const float a = (float)num * idn[j];
+              const float b = fmaf(-a, cmv[j] - cc, (float)sp * inn[j]);
+              if (which == 0) { VA[c] += a; VB[c] += b; } else { VA[c] -= a; VB[c] -= b; }
+            }
+          }
+        }
+      }
+    }
+
+    const int y = t - R;
+    u32* xbuf = xb + (size_t)(it & 1) * 2 * planew;  // double-buffered (V_A, V_B) planes: one barrier per row
+    float* ccbuf = ccs + (it & 1) * 48;
+    if (need_ab && y >= yb0) {
+      exch_store<K, HL4>(xbuf, reinterpret_cast<u32(&)[K]>(VA));
+      exch_store<K, HL4>(xbuf + planew, reinterpret_cast<u32(&)[K]>(VB));
+      if (lane == 0) ccbuf[run] = cc;
+    }
+    __syncthreads();
+    // every thread has now finished step t-1 completely: its stage can be refilled for step t+1
+    if (producer && t + 1 < t_end) issue(t + 1, s ^ 1);
+    if (y < yb0 || !need_out) continue;
+
+    // ---------------- stage 2, horizontal + q + WTA
+    float A[K], B[K];
+    {
+      u32 winA[HL4 + K + HL4], winB[HL4 + K + HL4];
+      exch_window<K, HL4>(xbuf, reinterpret_cast<u32(&)[K]>(VA), winA);
+      exch_window<K, HL4>(xbuf + planew, reinterpret_cast<u32(&)[K]>(VB), winB);
+      const float dl = run > 0 ? cc - ccbuf[run - 1] : 0.f;
+      const float dr = run + 1 < runs ? cc - ccbuf[run + 1] : 0.f;
+      slide_ab<R, K, HL4>(winA, winB, dl, dr, A, B);
+    }
+    const float* icy = reinterpret_cast<const float*>(stg + sg.off_ICY) + run * K;
+    const float* iny = reinterpret_cast<const float*>(stg + sg.off_INVNY) + run * K;
+    int key[K];
+#pragma unroll
+    for (int g4 = 0; g4 < K; g4 += 4) {
+      const float4 ic = *reinterpret_cast<const float4*>(icy + g4);
+      const float4 in = *reinterpret_cast<const float4*>(iny + g4);
+      key[g4 + 0] = sortable_i32(fmaf(A[g4 + 0], ic.x - cc, B[g4 + 0]) * in.x);
+      key[g4 + 1] = sortable_i32(fmaf(A[g4 + 1], ic.y - cc, B[g4 + 1]) * in.y);
+      key[g4 + 2] = sortable_i32(fmaf(A[g4 + 2], ic.z - cc, B[g4 + 2]) * in.z);
+      key[g4 + 3] = sortable_i32(fmaf(A[g4 + 3], ic.w - cc, B[g4 + 3]) * in.w);
+    }
+    if constexpr (EXPORT) {
+      const int de = d - g.export_d0;
+      if (de >= 0 && de < g.export_nd && d < g.d_end) {
+        float* out = reinterpret_cast<float*>(g.export_ptr) + ((size_t)de * H + y) * W;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const int x = x0 + c;
+          if (x >= out0 && x < min(out0 + g.TW, W)) out[x] = unsortable_f32(key[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < K; ++c) key[c] = (key[c] & ~31) | lane;
+    if (!all_valid) {
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+        if (c < c_lo || c > c_hi) key[c] = 0x7fffffff;
+    }
+    int mine = 0x7fffffff;
+    if (LPR == 32) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const int m = __reduce_min_sync(0xffffffffu, key[c]);
+        if (lane == c) mine = m;
+      }
+    } else {
+      const bool upper = (threadIdx.x & 16) != 0;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const int m0 = __reduce_min_sync(0xffffffffu, upper ? 0x7fffffff : key[c]);
+        const int m1 = __reduce_min_sync(0xffffffffu, upper ? key[c] : 0x7fffffff);
+        if (lane == c) mine = upper ? m1 : m0;
+      }
+    }
+    if (lane < K && mine != 0x7fffffff) {
+      const i64 k64 = (i64)(((unsigned long long)(u32)(mine & ~31) << 32) | (u32)(d0 + (mine & 31)));
+      atomicMin(keys + ((size_t)frame * H + y) * W + x0 + lane, k64);
+    }
+  }
+}
+
+}  // namespace gsm
