@@ -392,7 +392,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {
-                "bound": "alu", "kernel": "gf_wta_kernel<9,16>",
+                "bound": "alu", "kernel": "gf3_wta_kernel<9,16,12,32>",
                 "achieved": GF_OPS_PER_DE * de_s_kernel / 1e12, "peak": alu_peak / 1e12, "unit": "Tlane-op/s",
                 "frac": GF_OPS_PER_DE * de_s_kernel / alu_peak,
                 "peak_source": "FFMA+IADD3 issue-peak microbenchmark run live on this GPU (gsm_measure_alu_peak); "
