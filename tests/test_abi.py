@@ -79,3 +79,19 @@ def test_compat_header_compiles_and_links(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert exe.exists()
+
+
+def test_header_is_valid_c_and_runs(tmp_path):
+    """gsm.h compiles as C99; the C program links libgsm.so and either runs the path (GPU box) or reports the
+    missing device loudly (CPU box) -- never a silent fallback."""
+    exe = tmp_path / "abi_c"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "abi_c.c"), "-o", str(exe),
+           "-L", os.path.join(ROOT, "gpu_stereo_matching_b200"), "-lgsm",
+           "-Wl,-rpath," + os.path.join(ROOT, "gpu_stereo_matching_b200")]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "sm_100a" in run.stdout
+    assert ("no device" in run.stdout and "no CPU fallback" in run.stdout) or "ok " in run.stdout

@@ -302,3 +302,39 @@ def test_determinism_under_repetition(ctx, fx):
     db, mb = ctx.stereo_batch(Lb, Rb, p)  # 6 frames > max_batch/2: exercises the two-slot host pipeline
     for i in range(6):
         assert np.array_equal(db[i], ref_d) and np.array_equal(mb[i], ref_m)
+
+
+def test_disparity_subranges_and_odd_sizes(ctx, fx, orc):
+    """d ranges that are not multiples of the 32-disparity chunk, D not a multiple of 32, batches larger than the
+    context's batch capacity, a non-default eps."""
+    import torch
+    L, R = fx["Laundry_L"], fx["Laundry_R"]
+    h, w = L.shape
+    Ld, Rd = _dev(L), _dev(R)
+    # SAD: arbitrary split points combine to the bit-exact full result
+    parts = []
+    for (a, b) in [(0, 7), (7, 40), (40, 41), (41, 50)]:
+        kt = torch.empty(h * w, dtype=torch.int64, device="cuda")
+        ctx.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), kt.data_ptr(), h, w,
+                                g.make_params("sad", 5, 50, d_begin=a, d_end=b))
+        ctx.sync()
+        parts.append(kt.clone())
+    disp = (torch.stack(parts).min(dim=0).values & 0xFF).to(torch.uint8).cpu().numpy().reshape(h, w)
+    assert np.array_equal(disp, orc.sad_wta(L, R, 5, 50))
+    # GF with D = 50 (not a multiple of 32) and a different eps
+    p = g.make_params("gf", 6, 50, eps=25.0)
+    q = ctx.cost_slices(L, R, p, 0, 50)
+    err = _gf_err(q, orc.gf_cost_slices(L, R, 6, 0, 50, eps=25.0))
+    assert err.max() <= GF_RTOL_SMALL_R, float(err.max())
+    d1, _ = ctx.stereo_batch(L, R, p)
+    same, off = _disp_bar(d1, orc.gf_wta(L, R, 6, 50, eps=25.0), orc.gf_cost_slices(L, R, 6, 0, 50, eps=25.0))
+    assert same >= 0.999 and off == 0, (same, off)
+    # 9 frames through a context whose batch capacity is 4 (same row-band decomposition, so bit-identical;
+    # different band counts may flip fp32 near-ties, which test_full_size_720p_properties bounds)
+    p1 = g.make_params("gf", 6, 50, eps=25.0, row_bands=1)
+    d1b, _ = ctx.stereo_batch(L, R, p1)
+    Lb, Rb = np.stack([L] * 9), np.stack([R] * 9)
+    db, _ = ctx.stereo_batch(Lb, Rb, p1)
+    assert all(np.array_equal(db[i], d1b) for i in range(9))
+    same, off = _disp_bar(d1b, d1)
+    assert same >= 0.9999, same
