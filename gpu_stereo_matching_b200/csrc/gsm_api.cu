@@ -533,11 +533,12 @@ extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const ui
   c->ev_used = 0;
   // Two slots of input / output buffers: while the kernels of chunk i run on the compute stream, chunk i+1 is
   // uploaded and chunk i-1 downloaded on their own streams (asynchronous when the host buffers are pinned).
-  // chunk = half the batch capacity (measured: quarter-size chunks shorten the exposed first upload / last download
-  // but their smaller launches fill the 148 SMs worse: 1455 vs 1587 fps end to end at 32 frames of 720p)
-  const int step = c->slot_frames;
+  // Chunks of half the batch capacity.  Smaller chunks (quarter size, or a half-size first chunk) shorten the
+  // exposed first upload / last download but were measured slower end to end (1455 / 1518 vs 1587 fps at 32 frames
+  // of 720p): their launches fill the 148 SMs worse.
   int chunk = 0;
-  for (int f0 = 0; f0 < n; f0 += step, ++chunk) {
+  for (int f0 = 0; f0 < n; ++chunk) {
+    const int step = c->slot_frames;
     const int nb = std::min(step, n - f0);
     const int slot = chunk & 1;
     u8* tl = c->tightL + slot * slot_stride;
@@ -562,6 +563,7 @@ extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const ui
     CK(cudaMemcpyAsync(disparity + f0 * fpx, dres, nb * fpx, cudaMemcpyDeviceToHost, c->s_d2h));
     if (want_mask) CK(cudaMemcpyAsync(mask + f0 * fpx, mres, nb * fpx, cudaMemcpyDeviceToHost, c->s_d2h));
     CK(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
+    f0 += nb;
   }
   CK(cudaStreamSynchronize(c->s_d2h));
   CK(cudaStreamSynchronize(s));
