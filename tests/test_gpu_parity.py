@@ -338,3 +338,28 @@ def test_disparity_subranges_and_odd_sizes(ctx, fx, orc):
     assert all(np.array_equal(db[i], d1b) for i in range(9))
     same, off = _disp_bar(d1b, d1)
     assert same >= 0.9999, same
+
+
+@pytest.mark.parametrize("r", [1, 3, 7, 8])
+def test_gf_other_radii_and_full_disparity_range(ctx, orc, r):
+    """Every compiled radius instantiation, the full D = 256 range (8 disparity chunks), both views."""
+    L, R, _ = gdata.synthetic_pair(72, 420, 900 + r, dmax=200)
+    p = g.make_params("gf", r, 256)
+    for view in (0, 1):
+        q = ctx.cost_slices(L, R, p, 0, 256, view=view)
+        err = _gf_err(q, orc.gf_cost_slices(L, R, r, 0, 256, view=view))
+        assert err.max() <= GF_RTOL_SMALL_R, (r, view, float(err.max()))
+    d, m = ctx.stereo_batch(L, R, g.make_params("gf", r, 256, lr_check=True))
+    dref, mref = orc.stereo_pipeline(L, R, mode="gf", r=r, D=256, lr=True)
+    assert (d == dref).mean() >= 0.998, float((d == dref).mean())
+
+
+def test_gf_costs_full_size_720p(ctx, orc):
+    """Cost-stage tolerance at the BASELINE config-3 size itself (1280x720, r=9): 16 of the 128 disparity slices of
+    each view against the float64 oracle (the full volume would take the CPU oracle about a minute)."""
+    L, R, _ = gdata.synthetic_pair(720, 1280, 1234)
+    p = g.make_params("gf", 9, 128)
+    for view, d0 in ((0, 0), (0, 112), (1, 48)):
+        q = ctx.cost_slices(L, R, p, d0, 16, view=view)
+        err = _gf_err(q, orc.gf_cost_slices(L, R, 9, d0, 16, view=view))
+        assert err.max() <= GF_RTOL, (view, d0, float(err.max()))
