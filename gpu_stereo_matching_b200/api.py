@@ -97,6 +97,18 @@ class StereoContext:
             return disp[0], (mask[0] if mask is not None else None)
         return disp, mask
 
+    def stereo_batch_async(self, left, right, params: GsmParams, out: np.ndarray, mask_out: Optional[np.ndarray] = None):
+        """Streaming submit (gsm_stereo_batch_async): returns after enqueueing; results are valid after sync().
+        left/right/out(/mask_out) must be C-contiguous uint8 [n, rows, cols], page-locked for real asynchrony, and
+        must stay alive until sync()."""
+        L, R = left, right
+        for name, a in (("left", L), ("right", R), ("out", out)):
+            if a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"] or a.ndim != 3:
+                raise TypeError(f"{name}: C-contiguous uint8 [n, rows, cols] expected")
+        n, rows, cols = L.shape
+        _l.check(self._lib.gsm_stereo_batch_async(self._h, C.byref(params), n, _ptr(L), _ptr(R), _ptr(out),
+                                                  _ptr(mask_out), rows, cols))
+
     def stereo(self, left, right, **kw):
         return self.stereo_batch(left, right, make_params(**kw))
 

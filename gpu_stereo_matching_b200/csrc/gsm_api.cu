@@ -39,6 +39,7 @@ struct gsm_ctx {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // host path: uploads / downloads overlap the kernels
   cudaEvent_t ev_h2d[2] = {}, ev_in_free[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
   int slot_frames = 1;                             // frames per host-path slot (two slots)
+  long long chunk_seq = 0;                         // host-path chunks submitted so far (slot = chunk_seq & 1)
   // device buffers, each sized for max_batch frames
   u8 *tightL = nullptr, *tightR = nullptr;                       // uploads on the host path
   u8 *planeL = nullptr, *planeR = nullptr, *planeLrep = nullptr;  // padded planes
@@ -193,6 +194,8 @@ extern "C" int gsm_sync(gsm_ctx* c) {
   if (!c) return fail(GSM_ERR_INVALID, "null ctx");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->s_h2d));
+  CK(cudaStreamSynchronize(c->s_d2h));
   return GSM_OK;
 }
 
@@ -522,8 +525,8 @@ extern "C" int gsm_stereo_device(gsm_ctx* c, const gsm_params* p, int n, const v
   return GSM_OK;
 }
 
-extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
-                                uint8_t* disparity, uint8_t* mask, int rows, int cols) {
+extern "C" int gsm_stereo_batch_async(gsm_ctx* c, const gsm_params* p, int n, const uint8_t* left,
+                                      const uint8_t* right, uint8_t* disparity, uint8_t* mask, int rows, int cols) {
   int d_begin, d_end, rc;
   float eps;
   if ((rc = check_params(c, p, n, rows, cols, &d_begin, &d_end, &eps))) return rc;
@@ -539,11 +542,11 @@ extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const ui
   // Chunks of half the batch capacity.  Smaller chunks (quarter size, or a half-size first chunk) shorten the
   // exposed first upload / last download but were measured slower end to end (1455 / 1518 vs 1587 fps at 32 frames
   // of 720p): their launches fill the 148 SMs worse.
-  int chunk = 0;
-  for (int f0 = 0; f0 < n; ++chunk) {
+  for (int f0 = 0; f0 < n; ++c->chunk_seq) {
+    const long long chunk = c->chunk_seq;  // persists across calls: back-to-back submissions keep pipelining
     const int step = c->slot_frames;
     const int nb = std::min(step, n - f0);
-    const int slot = chunk & 1;
+    const int slot = (int)(chunk & 1);
     u8* tl = c->tightL + slot * slot_stride;
     u8* tr = c->tightR + slot * slot_stride;
     u8* dres = c->dispOut + slot * slot_stride;
@@ -568,9 +571,14 @@ extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const ui
     CK(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
     f0 += nb;
   }
-  CK(cudaStreamSynchronize(c->s_d2h));
-  CK(cudaStreamSynchronize(s));
   return GSM_OK;
+}
+
+extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
+                                uint8_t* disparity, uint8_t* mask, int rows, int cols) {
+  const int rc = gsm_stereo_batch_async(c, p, n, left, right, disparity, mask, rows, cols);
+  if (rc) return rc;
+  return gsm_sync(c);
 }
 
 extern "C" int gsm_block_matching(gsm_ctx* c, const uint8_t* left, const uint8_t* right, uint8_t* disparity, int rows,
@@ -635,6 +643,7 @@ extern "C" int gsm_ad_volume(gsm_ctx* c, const uint8_t* left, const uint8_t* rig
   if ((rc = check_params(c, &p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
   if (!left || !right || !volume) return fail(GSM_ERR_INVALID, "null pointer");
   CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
   const size_t fpx = (size_t)rows * cols;
   if ((rc = ensure_export(c, fpx * num_disp))) return rc;
   cudaStream_t s = c->stream;
@@ -658,6 +667,7 @@ extern "C" int gsm_cost_slices(gsm_ctx* c, const gsm_params* p, int view, const 
   if (d0 < 0 || nd < 1 || d0 + nd > p->num_disp) return fail(GSM_ERR_INVALID, "slice range [%d,%d)", d0, d0 + nd);
   if (view != 0 && view != 1) return fail(GSM_ERR_INVALID, "view %d", view);
   CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
   const size_t fpx = (size_t)rows * cols;
   const size_t bytes = fpx * nd * 4;
   if ((rc = ensure_export(c, bytes))) return rc;
@@ -687,6 +697,7 @@ extern "C" int gsm_all_sad(gsm_ctx* c, const uint8_t* left, const uint8_t* right
   if ((rc = check_params(c, &p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
   if (!left || !right || !out) return fail(GSM_ERR_INVALID, "null pointer");
   CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
   const size_t fpx = (size_t)rows * cols;
   const size_t slice_bytes = fpx * num_disp * 4;
   if ((rc = ensure_export(c, slice_bytes + fpx * num_disp))) return rc;
@@ -713,6 +724,7 @@ extern "C" int gsm_median(gsm_ctx* c, const uint8_t* src, uint8_t* dst, int rows
   if (rows < 1 || cols < 1 || rows > c->max_rows || cols > c->max_cols) return fail(GSM_ERR_CAPACITY, "shape %dx%d", rows, cols);
   if (radius < 0 || radius > MED_MAXR) return fail(GSM_ERR_INVALID, "median radius %d", radius);
   CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
   const size_t fpx = (size_t)rows * cols;
   cudaStream_t s = c->stream;
   CK(cudaMemcpyAsync(c->dispA, src, fpx, cudaMemcpyHostToDevice, s));
@@ -728,6 +740,7 @@ extern "C" int gsm_lr_check(gsm_ctx* c, const uint8_t* dl, const uint8_t* dr, ui
   if (!c || !dl || !dr) return fail(GSM_ERR_INVALID, "null pointer");
   if (rows < 1 || cols < 1 || rows > c->max_rows || cols > c->max_cols) return fail(GSM_ERR_CAPACITY, "shape %dx%d", rows, cols);
   CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
   const size_t fpx = (size_t)rows * cols;
   cudaStream_t s = c->stream;
   CK(cudaMemcpyAsync(c->dispA, dl, fpx, cudaMemcpyHostToDevice, s));
@@ -747,6 +760,7 @@ extern "C" int gsm_remap(gsm_ctx* c, const uint8_t* src, const float* mapx, cons
   if (!c || !src || !mapx || !mapy || !dst) return fail(GSM_ERR_INVALID, "null pointer");
   if (rows < 1 || cols < 1) return fail(GSM_ERR_INVALID, "bad shape %dx%d", rows, cols);
   CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
   const size_t n = (size_t)rows * cols;
   int rc;
   if ((rc = ensure_export(c, n * 10))) return rc;  // [mapx f32][mapy f32][src u8][dst u8]
@@ -770,6 +784,7 @@ extern "C" int gsm_cvtcolor(gsm_ctx* c, const uint8_t* src3, uint8_t* dst, int r
   if (!c || !src3 || !dst) return fail(GSM_ERR_INVALID, "null pointer");
   if (rows < 1 || cols < 1) return fail(GSM_ERR_INVALID, "bad shape %dx%d", rows, cols);
   CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
   const size_t n = (size_t)rows * cols;
   int rc;
   if ((rc = ensure_export(c, n * 4))) return rc;

@@ -47,6 +47,7 @@ SYMBOLS = {
     "gsm_version": (C.c_char_p, []),
     "gsm_block_matching": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gsm_stereo_batch": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "gsm_stereo_batch_async": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_stereo_device": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gsm_sync": (C.c_int, [_P]),
     "gsm_partial_keys_device": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -86,11 +86,19 @@ int gsm_block_matching(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, 
 int gsm_stereo_batch(gsm_ctx* ctx, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
                      uint8_t* disparity, uint8_t* mask, int rows, int cols);
 
+/* Streaming variant: enqueues uploads, kernels and downloads and returns; the results are in `disparity` / `mask`
+ * after gsm_sync().  Back-to-back submissions keep the two-slot pipeline full across calls (frame k+1 uploads while
+ * frame k computes and frame k-1 downloads) -- what a capture loop (reference: Utility.cpp:198-226) would use.  The
+ * host buffers must be page-locked for the copies to be asynchronous and must stay valid until gsm_sync(). */
+int gsm_stereo_batch_async(gsm_ctx* ctx, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
+                           uint8_t* disparity, uint8_t* mask, int rows, int cols);
+
 /* ---- full path, device-resident buffers ----------------------------------------------------- */
 /* Same computation on DEVICE pointers (tightly packed n x rows x cols), enqueued on `stream`
  * (a cudaStream_t; NULL = the context's own stream).  Asynchronous: returns after enqueueing. */
 int gsm_stereo_device(gsm_ctx* ctx, const gsm_params* p, int n, const void* left_dev, const void* right_dev,
                       void* disparity_dev, void* mask_dev, int rows, int cols, void* stream);
+/* Waits for everything enqueued on the context's own streams (compute, upload, download). */
 int gsm_sync(gsm_ctx* ctx);
 
 /* ---- multi-GPU disparity split -------------------------------------------------- */

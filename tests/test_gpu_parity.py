@@ -363,3 +363,19 @@ def test_gf_costs_full_size_720p(ctx, orc):
         q = ctx.cost_slices(L, R, p, d0, 16, view=view)
         err = _gf_err(q, orc.gf_cost_slices(L, R, 9, d0, 16, view=view))
         assert err.max() <= GF_RTOL, (view, d0, float(err.max()))
+
+
+def test_streaming_submit_matches_blocking_call(ctx, fx):
+    """gsm_stereo_batch_async back to back (pipelined across calls) + gsm_sync == the blocking call."""
+    import torch
+    L, R = fx["Art_L"], fx["Art_R"]
+    p = g.make_params("gf", 9, 64, lr_check=True, median_radius=3)
+    ref_d, ref_m = ctx.stereo_batch(np.stack([L] * 3), np.stack([R] * 3), p)
+    Lh = torch.from_numpy(np.stack([L] * 3)).pin_memory(); Rh = torch.from_numpy(np.stack([R] * 3)).pin_memory()
+    outs = [(torch.empty_like(Lh).pin_memory(), torch.empty_like(Lh).pin_memory()) for _ in range(5)]
+    for d, m in outs:
+        ctx.stereo_batch_async(Lh.numpy(), Rh.numpy(), p, out=d.numpy(), mask_out=m.numpy())
+    ctx.sync()
+    for d, m in outs:
+        assert np.array_equal(d.numpy(), ref_d) and np.array_equal(m.numpy(), ref_m)
+    assert np.array_equal(ctx.block_matching(L, R, 5, 64), ctx.block_matching(L, R, 5, 64))
