@@ -52,7 +52,6 @@ struct gsm_ctx {
   size_t export_bytes = 0;
   u32* peak_buf = nullptr;
   size_t plane_bytes_per_frame = 0;
-  size_t stats_floats_per_frame = 0;
   long long launches = 0;
   bool timing = false;
   std::vector<cudaEvent_t> ev;  // (start, stop) pairs of the fused kernels of the last device call
@@ -60,11 +59,7 @@ struct gsm_ctx {
 };
 
 // strip halo (columns) a fused kernel needs on each side of its output columns
-#ifdef GSM_GF_V2
-static int stage_halo_of(int mode, int radius) { return mode == GSM_MODE_SAD ? radius : 2 * radius; }
-#else
-static int stage_halo_of(int mode, int radius) { return radius; }  // GF v3: stage 1 needs no exchanged halo
-#endif
+static int stage_halo_of(int /*mode*/, int radius) { return radius; }  // GF: stage 1 needs no exchanged halo
 
 static int max_pitch(int cols) { return round_up(PADL_BASE + 16 + cols + PADR, 16); }
 
@@ -130,7 +125,6 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
   c->max_batch = max_batch;
   const size_t px = (size_t)max_rows * max_cols * max_batch;
   c->plane_bytes_per_frame = (size_t)max_pitch(max_cols) * (max_rows + 2 * PADV);
-  c->stats_floats_per_frame = c->plane_bytes_per_frame;  // one float plane with the image's padded geometry
   const size_t plane = c->plane_bytes_per_frame * max_batch;
   cudaError_t st = cudaSuccess;
   auto A = [&](void** p, size_t bytes) {
@@ -327,11 +321,7 @@ static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols
   return GSM_OK;
 }
 
-#ifdef GSM_GF_V2
-#define GF_KERNEL gf_wta_kernel
-#else
 #define GF_KERNEL gf3_wta_kernel
-#endif
 #define GF_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 
 template <bool EXPORT>
@@ -351,11 +341,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, stage_halo_of(GSM_MODE_GF, R), 6, HL4, lpr);
-#ifdef GSM_GF_V2
-  pl.smem = gf_smem_bytes(runs, K, HL4, lpr);
-#else
   pl.smem = gf3_smem_bytes(runs, K, HL4, lpr);
-#endif
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
   pl.g.export_nd = end_;
@@ -373,11 +359,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     gf_stats_kernel<<<dim3((cols + GS_T - 1) / GS_T, (rows + GS_T - 1) / GS_T, n), dim3(GS_T, 8), sm, s>>>(G, stats, pg,
                                                                                                           R, eps);
     c->launches++;
-#ifdef GSM_GF_V2
-    gf_coef_kernel<<<dim3((cols + 255) / 256, rows + 2 * R + 1, n), 256, 0, s>>>(G, stats, pg, R);
-#else
     gf_hcoef_kernel<<<dim3((cols + 64 + 255) / 256, pg.plane_rows, n), 256, 0, s>>>(G, stats, pg, R);
-#endif
     c->launches++;
     gf_centre_kernel<<<dim3((pg.pitch / 16 + 63) / 64, rows, n), 64, 0, s>>>(stats, pg);
     c->launches++;

@@ -1,16 +1,23 @@
-// gsm_gf3.cuh -- guided-filter fused kernel, third layout: stage 1 HORIZONTAL-FIRST, entirely inside the thread.
+// gsm_gf3.cuh -- fused AD -> guided-filter aggregation -> WTA kernel (GSM_MODE_GF).
 //
-// gsm_gf.cuh (second layout) sums stage 1 vertically in registers and exchanges the vertical sums of four integer
-// quantities through shared memory to slide them horizontally: 4 of its 6 exchange planes, one of its two CTA
-// barriers per row and half of its strip halo exist only for that.  Here a thread builds the HORIZONTAL window
-// sums of p and I*p of its 16 columns directly from the staged image bytes of the 16+2r columns around them
-// (AD is 4 pixels per VABSDIFF4, so the redundant halo pixels are nearly free; the slide is one PRMT + two IDP.2A
-// per column and row, with the (+I_in, -I_out) coefficient word precomputed per pixel), and accumulates them
-// vertically:      S(t) += H(t+r) - H(t-r-1)           (lead)        S'(t') += H(t-r-1) - H(t-3r-2)      (trail)
-// The box sums S_p, S_Ip come out exact without any exchange.  What remains in shared memory is the stage-2
-// exchange of (V_A, V_B) -- double buffered, so ONE barrier per row -- and the asynchronous input stage.
-// Everything else (exact int32 numerator, lead/trail recomputation, local centres, packed-min WTA) is as in
-// gsm_gf.cuh, whose header comment describes the arithmetic.
+// Nothing of the D x H x W volume is materialised.  A CTA owns (strip of columns) x (32 disparities) and marches down
+// the rows; thread = run of 16 columns x one disparity.  Because box(a), box(b) need a and b on the 2r+1 rows around
+// the output row, two instances of the exact integer stage-1 pipeline run 2r+1 rows apart ("lead" adds a row of
+// (a,b) to the stage-2 running sums, "trail" recomputes the row that leaves) -- ~30% more arithmetic instead of a
+// (2r+1)-row ring of float (a,b) rows, which would not fit on chip for more than ~8 disparities per CTA.
+//
+// Stage 1 is HORIZONTAL-FIRST and entirely inside the thread: it builds the horizontal window sums of p and I*p of
+// its 16 columns directly from the staged image bytes of the 16+2r columns around them (AD is 4 pixels per
+// VABSDIFF4, so the redundant halo pixels are nearly free; the slide is one PRMT + two IDP.2A per column and row,
+// with the (+I_in, -I_out) coefficient word precomputed per pixel), and accumulates them vertically:
+//      S(t) += H(t+r) - H(t-r-1)           (lead)        S'(t-2r-1) += H(t-r-1) - H(t-3r-2)      (trail)
+// The box sums S_p, S_Ip come out exact without any exchange; the numerator N*S_Ip - S_I*S_p is evaluated modulo
+// 2^32, exact because |N^2 cov| < 2^31 for r <= 9.  (An earlier layout summed vertically first and exchanged four
+// integer planes through shared memory: 6 exchange planes, two barriers per row, strip halo 2r -- see git history.)
+// What remains in shared memory is the stage-2 exchange of (V_A, V_B) -- double buffered, ONE barrier per row -- and
+// the asynchronous input stage (cp.async.bulk + mbarrier, one step ahead).  WTA: lane index in the 5 low bits of the
+// sortable key, REDUX.MIN over the warp's disparities, one 64-bit atomicMin per pixel into the packed-min plane.
+// gsm_gf.cuh describes the stage-2 numerics (local centres).
 #pragma once
 #include "gsm_gf.cuh"
 
