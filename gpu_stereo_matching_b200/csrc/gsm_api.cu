@@ -328,7 +328,10 @@ template <bool EXPORT>
 static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, float eps,
                      int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
                      int end_) {
-  constexpr int K = 16;
+#ifndef GSM_GF_K
+#define GSM_GF_K 16
+#endif
+  constexpr int K = GSM_GF_K;
   // 12 runs of 16 columns x 32 disparities per CTA: a 192-column strip, 160 of them output columns (v3 needs a halo
   // of only r columns).  Measured alternatives at 720p x 128d: 24 runs x 16 disparities 1654 fps, this 1713 fps.
 #ifndef GSM_GF_RUNS
@@ -361,7 +364,10 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     c->launches++;
     gf_hcoef_kernel<<<dim3((cols + 64 + 255) / 256, pg.plane_rows, n), 256, 0, s>>>(G, stats, pg, R);
     c->launches++;
-    gf_centre_kernel<<<dim3((pg.pitch / 16 + 63) / 64, rows, n), 64, 0, s>>>(stats, pg);
+    {
+      const int strips = (int)pl.grid.x, cenw = (runs + 3) / 4 * 4;
+      gf_centre_kernel<<<dim3((strips * cenw + 63) / 64, rows, n), 64, 0, s>>>(stats, pg, pl.g.TW, pl.g.hl, K, runs, strips);
+    }
     c->launches++;
     CK(cudaGetLastError());
   }

@@ -83,25 +83,30 @@ gf_stats_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom 
   }
 }
 
-// Local centre plane: for every image row and every 16-column block of the padded grid (the blocks the fused
-// kernel's runs are aligned to), the rounded mean of (mean_I - 128) over the block's in-image columns.  Stored 4x
-// replicated (one float per 4 columns) so that a strip's centres are a 16-byte aligned, contiguous run.
-__global__ void gf_centre_kernel(float* __restrict__ stats, PlaneGeom pg) {
-  const int blk = blockIdx.x * blockDim.x + threadIdx.x;  // 16-column block of the padded row
+// Local centre plane: for every image row, every strip of the launch and every run of K columns of that strip, the
+// rounded mean of (mean_I - 128) over the run's in-image columns.  Layout [row][strip * CENW + run] inside a plane of
+// the usual row pitch (CENW = runs rounded up to 4), so a strip's centres are one 16-byte aligned bulk copy.
+__global__ void gf_centre_kernel(float* __restrict__ stats, PlaneGeom pg, int TW, int hl, int K, int runs, int strips) {
+  const int cenw = (runs + 3) / 4 * 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // strip * cenw + run
   const int y = blockIdx.y;
   const int f = blockIdx.z;
-  if (blk * 16 >= pg.pitch) return;
+  if (i >= strips * cenw) return;
+  const int strip = i / cenw, run = i - strip * cenw;
   float* base = stats + (size_t)f * GF_STAT_PLANES * pg.plane_stride;
-  const float* cm = base + ST_CMEAN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + blk * 16;
-  float sum = 0.f;
-  int n = 0;
-  for (int i = 0; i < 16; ++i) {
-    const int x = blk * 16 + i - pg.xoff;
-    if (x >= 0 && x < pg.W) { sum += cm[i]; ++n; }
+  float c = 0.f;
+  if (run < runs) {
+    const int xa = strip * TW - hl + run * K;
+    const float* cm = base + ST_CMEAN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + pg.xoff;
+    float sum = 0.f;
+    int n = 0;
+    for (int j = 0; j < K; ++j) {
+      const int x = xa + j;
+      if (x >= 0 && x < pg.W) { sum += cm[x]; ++n; }
+    }
+    c = n ? rintf(sum / (float)n) : 0.f;
   }
-  const float c = n ? rintf(sum / (float)n) : 0.f;
-  float* cen = base + ST_CEN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + blk * 4;
-  cen[0] = cen[1] = cen[2] = cen[3] = c;
+  base[ST_CEN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + i] = c;
 }
 
 // publish K words at buf, then (after the CTA barrier) gather the window [-HL4, K+HL4) around them
@@ -179,7 +184,7 @@ __device__ __forceinline__ void lds_unaligned(const u8* row, int off, u32 (&w)[K
 template <int R, int K, int HL4>
 __device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const u32 (&winB)[HL4 + K + HL4], float dl,
                                          float dr, float (&A)[K], float (&B)[K]) {
-  static_assert(R < K && K == 16, "window must not reach beyond the adjacent runs");
+  static_assert(R < K && K % 2 == 0, "window must not reach beyond the adjacent runs");
   constexpr int H = K / 2;
   // chain starting at column c0: window [c0-R, c0+R]; parts: left halo (< 0), own [0, K), right halo (>= K)
   float aL[2], aO[2], aR[2], b[2];

@@ -42,35 +42,44 @@ __global__ void gf_hcoef_kernel(const u8* __restrict__ Ip, float* __restrict__ s
 //   O[3][TWt+64] u8      other-image rows, shifted window covering the CTA's LPR disparities and the +-12 halo
 //   HC[3][TWt] i32       slide coefficients of the same three rows
 //   ST[2][5][TWt]        N, S_I, 1/den, mean_I-128, 1/N at rows t (lead) and t-2R-1 (trail)
-//   ICY[TWt], INVNY[TWt] I-128 and 1/N at the output row t-R;  CEN[TWt/4] local centres of the output row
+//   ICY[TWt], INVNY[TWt] I-128 and 1/N at the output row t-R;  CEN[runs] local centres of the output row
 struct Gf3Stage {
-  int TWt, GW, OW;
+  int TWt, GW, OW, CENB;
   int off_O, off_HC, off_ST, off_ICY, off_INVNY, off_CEN, bytes;
-  __host__ __device__ constexpr explicit Gf3Stage(int twt)
-      : TWt(twt), GW(twt + 32), OW(twt + 64), off_O(3 * (twt + 32)), off_HC(3 * (twt + 32) + 3 * (twt + 64)),
-        off_ST(3 * (twt + 32) + 3 * (twt + 64) + 12 * twt), off_ICY(3 * (twt + 32) + 3 * (twt + 64) + 52 * twt),
-        off_INVNY(3 * (twt + 32) + 3 * (twt + 64) + 56 * twt), off_CEN(3 * (twt + 32) + 3 * (twt + 64) + 60 * twt),
-        bytes(3 * (twt + 32) + 3 * (twt + 64) + 61 * twt) {}
+  __host__ __device__ constexpr Gf3Stage(int twt, int runs)
+      : TWt(twt), GW(twt + 32), OW(twt + 64), CENB(4 * ((runs + 3) / 4 * 4)), off_O(3 * (twt + 32)),
+        off_HC(3 * (twt + 32) + 3 * (twt + 64)), off_ST(3 * (twt + 32) + 3 * (twt + 64) + 12 * twt),
+        off_ICY(3 * (twt + 32) + 3 * (twt + 64) + 52 * twt), off_INVNY(3 * (twt + 32) + 3 * (twt + 64) + 56 * twt),
+        off_CEN(3 * (twt + 32) + 3 * (twt + 64) + 60 * twt),
+        bytes(3 * (twt + 32) + 3 * (twt + 64) + 60 * twt + 4 * ((runs + 3) / 4 * 4)) {}  // == sum of the bulk copies
 };
 
 __host__ __device__ inline size_t gf3_smem_bytes(int runs, int K, int HL4, int LPR) {
   // barriers + centres | 2 input stages | 2 (double buffer) x 2 (V_A, V_B) exchange planes
-  return 512 + 2 * (size_t)Gf3Stage(runs * K).bytes + 4 * (size_t)LPR * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+  return 512 + 2 * (size_t)Gf3Stage(runs * K, runs).bytes + 4 * (size_t)LPR * exch_pitch_words(runs, K, HL4) * sizeof(u32);
 }
 
-constexpr int GF3_WB = 40;  // window bytes per thread and row: columns x0-12 .. x0+27 (10 words)
+// window of a thread per staged row: columns x0-12 .. x0+K+11, i.e. K+24 bytes = WW words (K = 16: 10, K = 12: 9)
 
-// AD bytes of the thread's 40-column window of one staged row
-__device__ __forceinline__ void gf3_ad_window(const u8* grow16, const u8* orow, int ooff, u32 (&g)[10], u32 (&p)[10]) {
-  // grow16 = staged guide row + run*16: 16-byte aligned, byte 0 is column x0-16
-  const uint4 a = reinterpret_cast<const uint4*>(grow16)[0];
-  const uint4 b = reinterpret_cast<const uint4*>(grow16)[1];
-  const uint4 c = reinterpret_cast<const uint4*>(grow16)[2];
-  g[0] = a.y; g[1] = a.z; g[2] = a.w; g[3] = b.x; g[4] = b.y; g[5] = b.z; g[6] = b.w; g[7] = c.x; g[8] = c.y; g[9] = c.z;
-  u32 ow[10];
-  lds_unaligned<GF3_WB>(orow, ooff, ow);
+// AD bytes of the thread's window of one staged row.  growk = staged guide row + run*K (byte 0 is column x0-16).
+template <int K>
+__device__ __forceinline__ void gf3_ad_window(const u8* growk, const u8* orow, int ooff, u32 (&g)[(K + 24) / 4],
+                                              u32 (&p)[(K + 24) / 4]) {
+  constexpr int WW = (K + 24) / 4;
+  if constexpr (K == 16) {  // 16-byte aligned: three 128-bit loads
+    const uint4 a = reinterpret_cast<const uint4*>(growk)[0];
+    const uint4 b = reinterpret_cast<const uint4*>(growk)[1];
+    const uint4 c = reinterpret_cast<const uint4*>(growk)[2];
+    g[0] = a.y; g[1] = a.z; g[2] = a.w; g[3] = b.x; g[4] = b.y; g[5] = b.z; g[6] = b.w; g[7] = c.x; g[8] = c.y; g[9] = c.z;
+  } else {  // run*K is only 4-byte aligned: word loads (broadcast within the warp)
+    const u32* w = reinterpret_cast<const u32*>(growk + 4);
 #pragma unroll
-  for (int i = 0; i < 10; ++i) p[i] = __vabsdiffu4(g[i], ow[i]);
+    for (int i = 0; i < WW; ++i) g[i] = w[i];
+  }
+  u32 ow[WW];
+  lds_unaligned<K + 24>(orow, ooff, ow);
+#pragma unroll
+  for (int i = 0; i < WW; ++i) p[i] = __vabsdiffu4(g[i], ow[i]);
 }
 
 // byte mask (0xff per valid byte) of window word i: column inside the image and, for the left view, x >= d
@@ -91,12 +100,12 @@ __host__ __device__ constexpr u32 range_mask(int i) {
 }
 
 // window sums of p and I*p over window bytes [12-R, 12+R] (the window of the thread's column 0)
-template <int R>
-__device__ __forceinline__ void gf3_init_sums(const u32 (&g)[10], const u32 (&p)[10], int& hp, int& hip) {
+template <int R, int WW>
+__device__ __forceinline__ void gf3_init_sums(const u32 (&g)[WW], const u32 (&p)[WW], int& hp, int& hip) {
   constexpr int LO = 12 - R, HI = 12 + R;
   u32 sp = 0, sip = 0;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < WW; ++i) {
     const u32 m = range_mask<LO, HI>(i);
     if (m != 0) {
       sp = __dp4a(p[i], m & 0x01010101u, sp);
@@ -111,7 +120,8 @@ template <int R, int K, int RUNS, int LPR, bool EXPORT>
 __global__ void __launch_bounds__(RUNS * LPR, 1)
 gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
                i64* __restrict__ keys, FusedGeom g) {
-  static_assert(K == 16 && R <= 12 && R >= 1, "16-column runs, window halo of at most 12 columns");
+  static_assert((K == 16 || K == 12) && R <= 12 && R >= 1 && R < K, "12/16-column runs, halo of at most 12 columns");
+  constexpr int WW = (K + 24) / 4;
   static_assert(LPR == 32 || LPR == 16, "lanes per run");
   constexpr int HL4 = (R + 3) / 4 * 4;
   extern __shared__ __align__(128) u8 smem_raw[];
@@ -130,7 +140,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   if (yb0 >= H) return;
 
   constexpr int TWt = runs * K;
-  constexpr Gf3Stage sg(TWt);
+  constexpr Gf3Stage sg(TWt, runs);
   constexpr int pitchw = exch_pitch_words(runs, K, HL4);
   constexpr int planew = LPR * pitchw;
   float* ccs = reinterpret_cast<float*>(smem_raw + 64);  // [2][<=48] per-run centres, double buffered
@@ -159,8 +169,9 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   const int oalign = ostart & 15;
   const u8* osrc = Op + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + (ostart - oalign);
   const float* ssrc = stats + (size_t)frame * GF_STAT_PLANES * plane_elems + org;
+  constexpr int CENW = (RUNS + 3) / 4 * 4;  // centres of one strip: RUNS floats padded to 16 bytes
   const float* csrc = stats + ((size_t)frame * GF_STAT_PLANES + ST_CEN) * plane_elems + (size_t)PADV * pitch +
-                      (g.pg.xoff + xs) / 4;
+                      (size_t)strip * CENW;
   const int ooff = oalign + run * K + (g.view == 0 ? (LPR - 1 - lane) : lane);
 
   auto issue = [&](int t, int s) {
@@ -186,13 +197,13 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
     const long long ry = (long long)max(row_lo, min(row_hi, t - R)) * pitch;
     bulk_g2s(dst + sg.off_ICY, ssrc + ST_IC * plane_elems + ry, 4 * TWt, bar);
     bulk_g2s(dst + sg.off_INVNY, ssrc + ST_INVN * plane_elems + ry, 4 * TWt, bar);
-    bulk_g2s(dst + sg.off_CEN, csrc + ry, TWt, bar);
+    bulk_g2s(dst + sg.off_CEN, csrc + ry, sg.CENB, bar);
   };
 
   // window bytes that may contribute: inside the image and (left view) x >= d  (BlockMatching.cpp:147-149)
   const int dd = min(d, MAX_DISP - 1);
   const int col_lo = g.view == 0 ? dd : 0;
-  const bool full = (x0 - 12 >= col_lo) && (x0 + 27 < W);
+  const bool full = (x0 - 12 >= col_lo) && (x0 + K + 11 < W);
   const bool need_mask = __any_sync(0xffffffffu, !full);
 
   const int out0 = strip * g.TW;
@@ -227,41 +238,41 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
 
     if (need_ab) {
       // ---------------- stage 1: horizontal window sums of the three rows, folded into the vertical sums
-      u32 pn[10], pm[10], po[10];
+      u32 pn[WW], pm[WW], po[WW];
       int hp_n, hip_n, hp_m = 0, hip_m = 0, hp_o = 0, hip_o = 0;
       const bool has_m = t - R - 1 >= r0, has_o = t - 3 * R - 2 >= r0;
       {
-        u32 gn[10];
-        gf3_ad_window(stg + run * K, stg + sg.off_O, ooff, gn, pn);
+        u32 gn[WW];
+        gf3_ad_window<K>(stg + run * K, stg + sg.off_O, ooff, gn, pn);
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 10; ++i) pn[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
+          for (int i = 0; i < WW; ++i) pn[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
         }
-        gf3_init_sums<R>(gn, pn, hp_n, hip_n);
+        gf3_init_sums<R, WW>(gn, pn, hp_n, hip_n);
       }
       if (has_m) {
-        u32 gm[10];
-        gf3_ad_window(stg + sg.GW + run * K, stg + sg.off_O + sg.OW, ooff, gm, pm);
+        u32 gm[WW];
+        gf3_ad_window<K>(stg + sg.GW + run * K, stg + sg.off_O + sg.OW, ooff, gm, pm);
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 10; ++i) pm[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
+          for (int i = 0; i < WW; ++i) pm[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
         }
-        gf3_init_sums<R>(gm, pm, hp_m, hip_m);
+        gf3_init_sums<R, WW>(gm, pm, hp_m, hip_m);
       } else {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) pm[i] = 0u;
+        for (int i = 0; i < WW; ++i) pm[i] = 0u;
       }
       if (has_o) {
-        u32 go[10];
-        gf3_ad_window(stg + 2 * sg.GW + run * K, stg + sg.off_O + 2 * sg.OW, ooff, go, po);
+        u32 go[WW];
+        gf3_ad_window<K>(stg + 2 * sg.GW + run * K, stg + sg.off_O + 2 * sg.OW, ooff, go, po);
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 10; ++i) po[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
+          for (int i = 0; i < WW; ++i) po[i] &= gf3_word_mask(x0 - 12 + 4 * i, W, col_lo);
         }
-        gf3_init_sums<R>(go, po, hp_o, hip_o);
+        gf3_init_sums<R, WW>(go, po, hp_o, hip_o);
       } else {
 #pragma unroll
-        for (int i = 0; i < 10; ++i) po[i] = 0u;
+        for (int i = 0; i < WW; ++i) po[i] = 0u;
       }
       const int* hcn = reinterpret_cast<const int*>(stg + sg.off_HC) + run * K;
       const int* hcm = hcn + TWt;
@@ -299,7 +310,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
 
       // ---------------- (a, b) of the lead and trail rows folded into the stage-2 vertical sums
       {
-        const float target = reinterpret_cast<const float*>(stg + sg.off_CEN)[run * (K / 4)];
+        const float target = reinterpret_cast<const float*>(stg + sg.off_CEN)[run];
         const float dc = target - cc;
         if (fabsf(dc) > GF_RECENTRE) {
 #pragma unroll
