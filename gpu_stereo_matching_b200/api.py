@@ -25,10 +25,10 @@ GF_EPS_DEFAULT = 6.5025  # 1e-4 * 255^2
 
 
 def make_params(mode="sad", radius=5, num_disp=64, eps=0.0, lr_check=False, median_radius=0, row_bands=0,
-                d_begin=0, d_end=0) -> GsmParams:
+                d_begin=0, d_end=0, rectify=False) -> GsmParams:
     m = {"sad": GSM_MODE_SAD, "gf": GSM_MODE_GF}[mode] if isinstance(mode, str) else int(mode)
     return GsmParams(m, int(radius), int(num_disp), float(eps), int(bool(lr_check)), int(median_radius),
-                     int(row_bands), int(d_begin), int(d_end))
+                     int(row_bands), int(d_begin), int(d_end), int(bool(rectify)))
 
 
 def _u8c(a, name):
@@ -191,6 +191,19 @@ class StereoContext:
         out = np.empty(a.shape[:2], np.uint8)
         _l.check(self._lib.gsm_cvtcolor(self._h, _ptr(a), _ptr(out), a.shape[0], a.shape[1], int(truncate)))
         return out
+
+    def set_rectification(self, mapx_left, mapy_left, mapx_right, mapy_right):
+        """Upload the four CV_32FC1 maps Rectify() builds (Utility.cpp:228-234); params.rectify=True then feeds RAW
+        frames, rectified on the device inside the plane packer.  Pass None four times to drop the maps."""
+        if mapx_left is None:
+            _l.check(self._lib.gsm_set_rectification(self._h, None, None, None, None, 0, 0))
+            return
+        maps = [np.ascontiguousarray(m, np.float32) for m in (mapx_left, mapy_left, mapx_right, mapy_right)]
+        rows, cols = maps[0].shape
+        if any(m.shape != (rows, cols) for m in maps):
+            raise ValueError("the four maps must have the same shape")
+        _l.check(self._lib.gsm_set_rectification(self._h, _ptr(maps[0]), _ptr(maps[1]), _ptr(maps[2]), _ptr(maps[3]),
+                                                 rows, cols))
 
     # ---- introspection -----------------------------------------------------------------------
     @property

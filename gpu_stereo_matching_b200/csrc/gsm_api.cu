@@ -39,6 +39,8 @@ struct gsm_ctx {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // host path: uploads / downloads overlap the kernels
   cudaEvent_t ev_h2d[2] = {}, ev_in_free[2] = {}, ev_done[2] = {}, ev_d2h[2] = {};
   int slot_frames = 1;                             // frames per host-path slot (two slots)
+  float* rect_maps = nullptr;                      // [mapx_L][mapy_L][mapx_R][mapy_R], tight rows x cols each
+  int rect_rows = 0, rect_cols = 0;
   long long chunk_seq = 0;                         // host-path chunks submitted so far (slot = chunk_seq & 1)
   // device buffers, each sized for max_batch frames
   u8 *tightL = nullptr, *tightR = nullptr;                       // uploads on the host path
@@ -83,7 +85,7 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   void* bufs[] = {c->tightL, c->tightR, c->planeL, c->planeR, c->planeLrep, c->stats[0], c->stats[1], c->keysL,
-                  c->keysR,  c->dispA,  c->dispB,  c->dispC,  c->dispD,     c->maskD,    c->export_buf, c->peak_buf, c->dispOut};
+                  c->keysR,  c->dispA,  c->dispB,  c->dispC,  c->dispD,     c->maskD,    c->export_buf, c->peak_buf, c->dispOut, c->rect_maps};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -217,6 +219,8 @@ static int check_params(const gsm_ctx* c, const gsm_params* p, int n, int rows, 
   int b = p->d_begin, e = p->d_end;
   if (b == 0 && e == 0) e = p->num_disp;
   if (b < 0 || e > p->num_disp || b >= e) return fail(GSM_ERR_INVALID, "d range [%d,%d) not inside [0,%d)", b, e, p->num_disp);
+  if (p->rectify && (!c->rect_maps || c->rect_rows != rows || c->rect_cols != cols))
+    return fail(GSM_ERR_INVALID, "rectify: no maps set for %dx%d (gsm_set_rectification)", rows, cols);
   *d_begin = b;
   *d_end = e;
   *eps = p->eps > 0.f ? p->eps : 6.5025f;
@@ -392,10 +396,11 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   return GSM_OK;
 }
 
-static int pack_planes(gsm_ctx* c, const PlaneGeom& pg, int n, const u8* src, u8* dst, int fill, cudaStream_t s) {
+static int pack_planes(gsm_ctx* c, const PlaneGeom& pg, int n, const u8* src, u8* dst, int fill, cudaStream_t s,
+                       const float* mapx = nullptr, const float* mapy = nullptr) {
   dim3 block(128);
   dim3 grid((pg.pitch / 4 + 127) / 128, pg.plane_rows, n);
-  pack_plane_kernel<<<grid, block, 0, s>>>(src, dst, pg, fill);
+  pack_plane_kernel<<<grid, block, 0, s>>>(src, dst, pg, fill, mapx, mapy);
   c->launches++;
   CK(cudaGetLastError());
   return GSM_OK;
@@ -435,8 +440,17 @@ static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int c
   // guide / other planes.  view 0: guide L, other R (zero pad).  view 1: guide R, other L right-replicated.
   u8* Gp = view == 0 ? c->planeL : c->planeR;
   u8* Op = view == 0 ? c->planeR : c->planeLrep;
-  if ((rc = pack_planes(c, pg, n, view == 0 ? Ltight : Rtight, Gp, 0, s))) return rc;
-  if ((rc = pack_planes(c, pg, n, view == 0 ? Rtight : Ltight, Op, view == 0 ? 0 : 1, s))) return rc;
+  // with p->rectify the planes receive remap(raw frame): left frames through the left maps, right through the right
+  const size_t mpx = (size_t)rows * cols;
+  const float* mL = p->rectify ? c->rect_maps : nullptr;
+  const float* mR = p->rectify ? c->rect_maps + 2 * mpx : nullptr;
+  if (view == 0) {
+    if ((rc = pack_planes(c, pg, n, Ltight, Gp, 0, s, mL, mL ? mL + mpx : nullptr))) return rc;
+    if ((rc = pack_planes(c, pg, n, Rtight, Op, 0, s, mR, mR ? mR + mpx : nullptr))) return rc;
+  } else {
+    if ((rc = pack_planes(c, pg, n, Rtight, Gp, 0, s, mR, mR ? mR + mpx : nullptr))) return rc;
+    if ((rc = pack_planes(c, pg, n, Ltight, Op, 1, s, mL, mL ? mL + mpx : nullptr))) return rc;
+  }
   if ((rc = fill_keys(c, keys, npx, key_init(p), s))) return rc;
   if (p->mode == GSM_MODE_SAD) {
     if ((rc = timing_begin(c, s))) return rc;
@@ -785,6 +799,28 @@ extern "C" int gsm_cvtcolor(gsm_ctx* c, const uint8_t* src3, uint8_t* dst, int r
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(dst, ddst, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_set_rectification(gsm_ctx* c, const float* mxl, const float* myl, const float* mxr, const float* myr,
+                                     int rows, int cols) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;
+  if (c->rect_maps) {
+    cudaFree(c->rect_maps);
+    c->rect_maps = nullptr;
+    c->rect_rows = c->rect_cols = 0;
+  }
+  if (!mxl && !myl && !mxr && !myr) return GSM_OK;
+  if (!mxl || !myl || !mxr || !myr) return fail(GSM_ERR_INVALID, "all four maps or none");
+  if (rows < 1 || cols < 1 || rows > c->max_rows || cols > c->max_cols) return fail(GSM_ERR_CAPACITY, "maps %dx%d", rows, cols);
+  const size_t n = (size_t)rows * cols;
+  CK(cudaMalloc((void**)&c->rect_maps, 4 * n * sizeof(float)));
+  const float* srcs[4] = {mxl, myl, mxr, myr};
+  for (int i = 0; i < 4; ++i) CK(cudaMemcpy(c->rect_maps + i * n, srcs[i], n * sizeof(float), cudaMemcpyHostToDevice));
+  c->rect_rows = rows;
+  c->rect_cols = cols;
   return GSM_OK;
 }
 

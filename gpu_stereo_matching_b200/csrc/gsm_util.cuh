@@ -5,10 +5,38 @@
 
 namespace gsm {
 
+// round-to-nearest-even + saturate to u8: the reference's float2uchar (Device.cu:145-150)
+__device__ __forceinline__ u8 float2uchar_rni_sat(float a) {
+  u32 res;
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(res) : "f"(a));
+  return (u8)res;
+}
+
+// BilinearInterpolation + float2uchar (Device.cu:145-167) of src at (row = my, col = mx).  Products and sums are
+// rounded separately (__fmul_rn/__fadd_rn: no FMA contraction) so the result equals the reference's CPU twin
+// (CPU_BilinearInterpolation, Utility.cpp:248-264) bit for bit.
+__device__ __forceinline__ u8 remap_sample(const u8* __restrict__ src, int rows, int cols, float mx, float my) {
+  const float x = my, y = mx;  // the reference calls the interpolator as (src, ycoo, xcoo): x is the row coordinate
+  const int x1 = (int)floorf(x), y1 = (int)floorf(y), x2 = x1 + 1, y2 = y1 + 1;
+  float result = 0.f;
+  if (!(x1 < 0 || x2 >= rows || y1 < 0 || y2 >= cols)) {
+    const size_t b = (size_t)x1 * cols + y1;
+    const float Q11 = src[b], Q12 = src[b + 1], Q21 = src[b + cols], Q22 = src[b + cols + 1];
+    const float wx2 = __fsub_rn((float)x2, x), wx1 = __fsub_rn(x, (float)x1);
+    const float left = __fadd_rn(__fmul_rn(wx2, Q11), __fmul_rn(wx1, Q21));
+    const float right = __fadd_rn(__fmul_rn(wx2, Q12), __fmul_rn(wx1, Q22));
+    result = __fadd_rn(__fmul_rn(__fsub_rn((float)y2, y), left), __fmul_rn(__fsub_rn(y, (float)y1), right));
+  }
+  return float2uchar_rni_sat(result);
+}
+
 // tight [n][H][W] u8  ->  padded plane (see gsm_common.cuh).  fill 0: zero pad everywhere;
 // fill 1: columns >= W of image rows replicate src[y][W-1] (right-view "other" image,
 // STMatching/StereoHelper.cpp:170-176: x+d >= W falls back to the last valid disparity).
-__global__ void pack_plane_kernel(const u8* __restrict__ src, u8* __restrict__ dst, PlaneGeom pg, int fill) {
+// mapx/mapy (optional, tight float [H][W]): rectification fused into the packer -- the plane receives
+// remap(src) (raw frames in, disparity out) instead of a copy of src.
+__global__ void pack_plane_kernel(const u8* __restrict__ src, u8* __restrict__ dst, PlaneGeom pg, int fill,
+                                  const float* __restrict__ mapx, const float* __restrict__ mapy) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;  // 4-byte group within a padded row
   const int prow = blockIdx.y;
   const int frame = blockIdx.z;
@@ -21,8 +49,15 @@ __global__ void pack_plane_kernel(const u8* __restrict__ src, u8* __restrict__ d
     for (int b = 0; b < 4; ++b) {
       int x = q * 4 + b - pg.xoff;
       u32 px = 0;
-      if (x >= 0 && x < pg.W) px = s[x];
-      else if (fill == 1 && x >= pg.W) px = s[pg.W - 1];
+      if (fill == 1 && x >= pg.W) x = pg.W - 1;
+      if (x >= 0 && x < pg.W) {
+        if (mapx) {
+          const size_t mi = (size_t)y * pg.W + x;
+          px = remap_sample(s - (size_t)y * pg.W, pg.H, pg.W, mapx[mi], mapy[mi]);
+        } else {
+          px = s[x];
+        }
+      }
       v |= px << (8 * b);
     }
   }
@@ -121,33 +156,14 @@ __global__ void all_sad_pack_kernel(const int* __restrict__ slices, u8* __restri
   out[i * D + d] = (x + d > W) ? (u8)255 : (u8)slices[(size_t)k * H * W + i];
 }
 
-// round-to-nearest-even + saturate to u8: the reference's float2uchar (Device.cu:145-150)
-__device__ __forceinline__ u8 float2uchar_rni_sat(float a) {
-  u32 res;
-  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(res) : "f"(a));
-  return (u8)res;
-}
-
-// kernalRemap + BilinearInterpolation (Device.cu:127-134,152-167).  Products and sums are rounded separately
-// (__fmul_rn/__fadd_rn: no FMA contraction) so the result equals the reference's CPU twin bit for bit.
+// kernalRemap (Device.cu:127-134): one image through one pair of maps
 __global__ void remap_kernel(const u8* __restrict__ src, const float* __restrict__ mapx, const float* __restrict__ mapy,
                              u8* __restrict__ dst, int rows, int cols) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;
   if (col >= cols) return;
   const size_t i = (size_t)row * cols + col;
-  const float x = mapy[i], y = mapx[i];  // called as (src, ycoo, xcoo): x is the row coordinate
-  const int x1 = (int)floorf(x), y1 = (int)floorf(y), x2 = x1 + 1, y2 = y1 + 1;
-  float result = 0.f;
-  if (!(x1 < 0 || x2 >= rows || y1 < 0 || y2 >= cols)) {
-    const size_t b = (size_t)x1 * cols + y1;
-    const float Q11 = src[b], Q12 = src[b + 1], Q21 = src[b + cols], Q22 = src[b + cols + 1];
-    const float wx2 = __fsub_rn((float)x2, x), wx1 = __fsub_rn(x, (float)x1);
-    const float left = __fadd_rn(__fmul_rn(wx2, Q11), __fmul_rn(wx1, Q21));
-    const float right = __fadd_rn(__fmul_rn(wx2, Q12), __fmul_rn(wx1, Q22));
-    result = __fadd_rn(__fmul_rn(__fsub_rn((float)y2, y), left), __fmul_rn(__fsub_rn(y, (float)y1), right));
-  }
-  dst[i] = float2uchar_rni_sat(result);
+  dst[i] = remap_sample(src, rows, cols, mapx[i], mapy[i]);
 }
 
 // kernalCvtColor (Device.cu:136-143) / cvtColor_cpu (Utility.cpp:289-298)

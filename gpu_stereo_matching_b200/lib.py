@@ -28,6 +28,7 @@ class GsmParams(C.Structure):
         ("row_bands", C.c_int),
         ("d_begin", C.c_int),
         ("d_end", C.c_int),
+        ("rectify", C.c_int),
     ]
 
 
@@ -59,6 +60,7 @@ SYMBOLS = {
     "gsm_lr_check": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_remap": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_cvtcolor": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "gsm_set_rectification": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_launch_count": (C.c_longlong, [_P]),
     "gsm_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "gsm_last_kernel_ms": (C.c_float, [_P]),

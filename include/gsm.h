@@ -64,6 +64,8 @@ typedef struct gsm_params {
                         single-frame latency); 0 = automatic */
   int d_begin;       /* disparity sub-range [d_begin, d_end) evaluated by this call; 0/0 = all.  Used by the */
   int d_end;         /* multi-GPU disparity split: partial results combine through the packed-min plane. */
+  int rectify;       /* 1: left/right are RAW (unrectified) frames; they are rectified on the device through the maps
+                        given to gsm_set_rectification, fused into the plane packer. */
 } gsm_params;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -142,6 +144,12 @@ int gsm_remap(gsm_ctx* ctx, const uint8_t* src, const float* mapx, const float* 
  * rounded to nearest-even (truncate = 0, the GPU kernel) or truncated (truncate = 1, cvtColor_cpu,
  * Utility.cpp:289-298). */
 int gsm_cvtcolor(gsm_ctx* ctx, const uint8_t* src3, uint8_t* dst, int rows, int cols, int truncate);
+
+/* Rectification maps for gsm_params.rectify (float32 rows x cols each, host pointers; copied to the device).  They
+ * are what Rectify() builds (initUndistortRectifyMap CV_32FC1, Utility.cpp:228-234); sampling follows gsm_remap.
+ * Pass NULL maps to drop them. */
+int gsm_set_rectification(gsm_ctx* ctx, const float* mapx_left, const float* mapy_left, const float* mapx_right,
+                          const float* mapy_right, int rows, int cols);
 
 /* ---- introspection for benches -------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

@@ -60,7 +60,7 @@ def test_product_never_imports_oracle():
 
 def test_params_struct_layout():
     from gpu_stereo_matching_b200 import lib, make_params
-    assert ctypes.sizeof(lib.GsmParams) == 9 * 4
+    assert ctypes.sizeof(lib.GsmParams) == 10 * 4
     p = make_params("gf", 9, 128, lr_check=True, median_radius=3)
     assert (p.mode, p.radius, p.num_disp, p.lr_check, p.median_radius) == (1, 9, 128, 1, 3)
 

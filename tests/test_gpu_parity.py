@@ -379,3 +379,27 @@ def test_streaming_submit_matches_blocking_call(ctx, fx):
     for d, m in outs:
         assert np.array_equal(d.numpy(), ref_d) and np.array_equal(m.numpy(), ref_m)
     assert np.array_equal(ctx.block_matching(L, R, 5, 64), ctx.block_matching(L, R, 5, 64))
+
+
+def test_fused_rectification_equals_remap_then_stereo(ctx, orc):
+    """SURVEY 8f-1 fused: raw frames + the rig's rectification maps in, disparity out == remap (bit-exact to the CPU
+    twin) followed by the same stereo pass."""
+    Lraw, Rraw, _ = gdata.synthetic_pair(720, 1280, 4242)
+    m1x, m1y, m2x, m2y = gdata.rectify_maps(1280, 720)
+    Lrec, Rrec = orc.remap(Lraw, m1x, m1y), orc.remap(Rraw, m2x, m2y)
+    ctx.set_rectification(m1x, m1y, m2x, m2y)
+    try:
+        for kw in (dict(mode="sad", radius=5, num_disp=64), dict(mode="gf", radius=9, num_disp=64, lr_check=True, median_radius=3)):
+            fused, mf = ctx.stereo_batch(Lraw, Rraw, g.make_params(rectify=True, row_bands=1, **kw))
+            twostep, mt = ctx.stereo_batch(Lrec, Rrec, g.make_params(row_bands=1, **kw))
+            assert np.array_equal(fused, twostep)
+            if mf is not None:
+                assert np.array_equal(mf, mt)
+        assert np.array_equal(ctx.stereo_batch(Lraw, Rraw, g.make_params("sad", 5, 64, rectify=True))[0],
+                              orc.sad_wta(Lrec, Rrec, 5, 64))
+        with pytest.raises(g.GsmError):  # maps are for 720p only
+            ctx.stereo_batch(Lraw[:100], Rraw[:100], g.make_params("sad", 5, 64, rectify=True))
+    finally:
+        ctx.set_rectification(None, None, None, None)
+    with pytest.raises(g.GsmError):
+        ctx.stereo_batch(Lraw, Rraw, g.make_params("sad", 5, 64, rectify=True))
