@@ -300,7 +300,10 @@ template <bool EXPORT>
 static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, int view,
                       const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0, int end_) {
   constexpr int K = 16;
-  const int runs = 13;
+#ifndef GSM_SAD_RUNS
+#define GSM_SAD_RUNS 16
+#endif
+  const int runs = GSM_SAD_RUNS;
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, R, 2, HL4);

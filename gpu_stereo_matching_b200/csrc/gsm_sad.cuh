@@ -89,21 +89,24 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
   const int r0 = yb0 - R;  // first image row that may enter a window of this band
   constexpr int COEF = (int)0xFF000100;  // lo16 = +256, hi16 = -256: V holds 256 * (vertical sum)
 
-  for (int y = yb0 - 2 * R; y < yb1; ++y) {
+  // running row pointers (one add per row instead of a 64-bit multiply per load)
+  const u8* g_new = gbase + (long long)(yb0 - R) * pitch;                   // row y + R
+  const u8* o_new = reinterpret_cast<const u8*>(obase) + (long long)(yb0 - R) * pitch;
+  const u8* g_old = gbase + (long long)(yb0 - 3 * R - 1) * pitch;           // row y - R - 1
+  const u8* o_old = reinterpret_cast<const u8*>(obase) + (long long)(yb0 - 3 * R - 1) * pitch;
+  for (int y = yb0 - 2 * R; y < yb1; ++y, g_new += pitch, o_new += pitch, g_old += pitch, o_old += pitch) {
     u32 pn[KW], po[KW];
     {
       u32 gw[KW], ow[KW];
-      const size_t ro = (size_t)(y + R) * pitch;
-      load_aligned<K>(gbase + ro, gw);
-      load_unaligned<K>(reinterpret_cast<const u32*>(reinterpret_cast<const u8*>(obase) + ro), osel, ow);
+      load_aligned<K>(g_new, gw);
+      load_unaligned<K>(reinterpret_cast<const u32*>(o_new), osel, ow);
 #pragma unroll
       for (int w = 0; w < KW; ++w) pn[w] = __vabsdiffu4(gw[w], ow[w]);
     }
     if (y - R - 1 >= r0) {
       u32 gw[KW], ow[KW];
-      const size_t ro = (size_t)(y - R - 1) * pitch;
-      load_aligned<K>(gbase + ro, gw);
-      load_unaligned<K>(reinterpret_cast<const u32*>(reinterpret_cast<const u8*>(obase) + ro), osel, ow);
+      load_aligned<K>(g_old, gw);
+      load_unaligned<K>(reinterpret_cast<const u32*>(o_old), osel, ow);
 #pragma unroll
       for (int w = 0; w < KW; ++w) po[w] = __vabsdiffu4(gw[w], ow[w]);
     } else {
