@@ -371,29 +371,33 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       const float dr = run + 1 < runs ? cc - ccbuf[run + 1] : 0.f;
       slide_ab<R, K, HL4>(winA, winB, dl, dr, A, B);
     }
+    // The WTA compares N(x)*q_d(x): N > 0 does not depend on d, so the argmin is that of q (the packed-min plane
+    // therefore carries the un-normalised cost); only the exported slices are divided by N.
     const float* icy = reinterpret_cast<const float*>(stg + sg.off_ICY) + run * K;
-    const float* iny = reinterpret_cast<const float*>(stg + sg.off_INVNY) + run * K;
-    int key[K];
+    float qn[K];
 #pragma unroll
     for (int g4 = 0; g4 < K; g4 += 4) {
       const float4 ic = *reinterpret_cast<const float4*>(icy + g4);
-      const float4 in = *reinterpret_cast<const float4*>(iny + g4);
-      key[g4 + 0] = sortable_i32(fmaf(A[g4 + 0], ic.x - cc, B[g4 + 0]) * in.x);
-      key[g4 + 1] = sortable_i32(fmaf(A[g4 + 1], ic.y - cc, B[g4 + 1]) * in.y);
-      key[g4 + 2] = sortable_i32(fmaf(A[g4 + 2], ic.z - cc, B[g4 + 2]) * in.z);
-      key[g4 + 3] = sortable_i32(fmaf(A[g4 + 3], ic.w - cc, B[g4 + 3]) * in.w);
+      qn[g4 + 0] = fmaf(A[g4 + 0], ic.x - cc, B[g4 + 0]);
+      qn[g4 + 1] = fmaf(A[g4 + 1], ic.y - cc, B[g4 + 1]);
+      qn[g4 + 2] = fmaf(A[g4 + 2], ic.z - cc, B[g4 + 2]);
+      qn[g4 + 3] = fmaf(A[g4 + 3], ic.w - cc, B[g4 + 3]);
     }
     if constexpr (EXPORT) {
+      const float* iny = reinterpret_cast<const float*>(stg + sg.off_INVNY) + run * K;
       const int de = d - g.export_d0;
       if (de >= 0 && de < g.export_nd && d < g.d_end) {
         float* out = reinterpret_cast<float*>(g.export_ptr) + ((size_t)de * H + y) * W;
 #pragma unroll
         for (int c = 0; c < K; ++c) {
           const int x = x0 + c;
-          if (x >= out0 && x < min(out0 + g.TW, W)) out[x] = unsortable_f32(key[c]);
+          if (x >= out0 && x < min(out0 + g.TW, W)) out[x] = qn[c] * iny[c];
         }
       }
     }
+    int key[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) key[c] = sortable_i32(qn[c]);
 #pragma unroll
     for (int c = 0; c < K; ++c) key[c] = (key[c] & ~31) | lane;
     if (!all_valid) {
@@ -403,11 +407,18 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
     }
     int mine = 0x7fffffff;
     if (LPR == 32) {
+      // lane c keeps the minimum of column c: a 4-level select tree on the (loop-invariant) lane bits instead of a
+      // compare + select per column
+      int m[16];
 #pragma unroll
-      for (int c = 0; c < K; ++c) {
-        const int m = __reduce_min_sync(0xffffffffu, key[c]);
-        if (lane == c) mine = m;
-      }
+      for (int c = 0; c < 16; ++c) m[c] = c < K ? __reduce_min_sync(0xffffffffu, key[c < K ? c : 0]) : 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = (lane & 1) ? m[2 * i + 1] : m[2 * i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = (lane & 2) ? m[2 * i + 1] : m[2 * i];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) m[i] = (lane & 4) ? m[2 * i + 1] : m[2 * i];
+      mine = (lane & 8) ? m[1] : m[0];
     } else {
       const bool upper = (threadIdx.x & 16) != 0;
 #pragma unroll

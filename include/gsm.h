@@ -106,7 +106,8 @@ int gsm_sync(gsm_ctx* ctx);
 /* ---- multi-GPU disparity split -------------------------------------------------- */
 /* Evaluate only d in [p->d_begin, p->d_end) for ONE frame and leave the per-pixel packed minimum in
  * keys_dev (int64[rows*cols], device).  Packed word: SAD  (int64)((SAD << 8) | d);
- * GF  ((int64)sortable_int32(q) << 32) | d  -- both order like (cost, d) under a SIGNED 64-bit min,
+ * GF  ((int64)sortable_int32(N*q) << 32) | d  (N = window pixel count of the pixel, so the argmin over d is that
+ * of q; the 5 low bits of the cost word are cleared) -- both order like (cost, d) under a SIGNED 64-bit min,
  * so ranks combine with ncclAllReduce(ncclInt64, ncclMin) / torch.distributed ReduceOp.MIN and ties
  * resolve to the lowest d exactly like the reference's strict '<' (BlockMatching.cpp:178).
  * view: 0 = left disparity, 1 = right-view disparity (for the LR check). */
