@@ -180,16 +180,19 @@ __device__ __forceinline__ void lds_unaligned(const u8* row, int off, u32 (&w)[K
 // Stage-2 horizontal pass.  winA / winB: [left halo HL4 | own K | right halo HL4].  The A window sum is kept as
 // three partial sums (columns owned by the left neighbour, by this run, by the right neighbour) because the
 // neighbours' B' sums are relative to THEIR centres: B'(x) = sum(winB) + dl * A_L(x) + dr * A_R(x).
-// Two independent chains (columns 0..7 and 8..15), see slide_i32.
 template <int R, int K, int HL4>
 __device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const u32 (&winB)[HL4 + K + HL4], float dl,
                                          float dr, float (&A)[K], float (&B)[K]) {
   static_assert(R < K && K % 2 == 0, "window must not reach beyond the adjacent runs");
-  constexpr int H = K / 2;
+#ifndef GSM_GF_CHAINS
+#define GSM_GF_CHAINS 1  // 1: one sliding chain over the K columns (fewest instructions); 2: two chains of K/2
+#endif
+  constexpr int NCH = GSM_GF_CHAINS;
+  constexpr int H = K / NCH;
   // chain starting at column c0: window [c0-R, c0+R]; parts: left halo (< 0), own [0, K), right halo (>= K)
-  float aL[2], aO[2], aR[2], b[2];
+  float aL[NCH], aO[NCH], aR[NCH], b[NCH];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < NCH; ++h) {
     const int c0 = h * H;
     float l = 0.f, o = 0.f, r = 0.f;
 #pragma unroll
@@ -200,18 +203,22 @@ __device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const
     }
     aL[h] = l; aO[h] = o; aR[h] = r;
   }
-  if constexpr (2 * R + 1 > H) {
-    const float mid = wsum_f<H - R, R>(winB, HL4);
-    b[0] = mid + wsum_f<-R, H - R - 1>(winB, HL4);
-    b[1] = mid + wsum_f<R + 1, H + R>(winB, HL4);
+  if constexpr (NCH == 2) {
+    if constexpr (2 * R + 1 > H) {
+      const float mid = wsum_f<H - R, R>(winB, HL4);
+      b[0] = mid + wsum_f<-R, H - R - 1>(winB, HL4);
+      b[NCH - 1] = mid + wsum_f<R + 1, H + R>(winB, HL4);
+    } else {
+      b[0] = wsum_f<-R, R>(winB, HL4);
+      b[NCH - 1] = wsum_f<H - R, H + R>(winB, HL4);
+    }
   } else {
     b[0] = wsum_f<-R, R>(winB, HL4);
-    b[1] = wsum_f<H - R, H + R>(winB, HL4);
   }
 #pragma unroll
   for (int c = 0; c < H; ++c) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NCH; ++h) {
       const int col = h * H + c;
       if (c > 0) {
         const int in = col + R, out = col - R - 1;
