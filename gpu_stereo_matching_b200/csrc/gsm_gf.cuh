@@ -183,53 +183,28 @@ __device__ __forceinline__ void lds_unaligned(const u8* row, int off, u32 (&w)[K
 template <int R, int K, int HL4>
 __device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const u32 (&winB)[HL4 + K + HL4], float dl,
                                          float dr, float (&A)[K], float (&B)[K]) {
-  static_assert(R < K && K % 2 == 0, "window must not reach beyond the adjacent runs");
-#ifndef GSM_GF_CHAINS
-#define GSM_GF_CHAINS 1  // 1: one sliding chain over the K columns (fewest instructions); 2: two chains of K/2
-#endif
-  constexpr int NCH = GSM_GF_CHAINS;
-  constexpr int H = K / NCH;
-  // chain starting at column c0: window [c0-R, c0+R]; parts: left halo (< 0), own [0, K), right halo (>= K)
-  float aL[NCH], aO[NCH], aR[NCH], b[NCH];
+  static_assert(R < K, "window must not reach beyond the adjacent runs");
+  // One sliding chain over the K columns.  a: whole window sum of V_A; aL / aR: the part of it owned by the left /
+  // right neighbour run (aL only shrinks, aR only grows as the window moves right); b: window sum of V_B.
+  float aL = 0.f, aO = 0.f, b = wsum_f<-R, R>(winB, HL4);
 #pragma unroll
-  for (int h = 0; h < NCH; ++h) {
-    const int c0 = h * H;
-    float l = 0.f, o = 0.f, r = 0.f;
-#pragma unroll
-    for (int j = -R; j <= R; ++j) {
-      const int idx = c0 + j;
-      const float va = __uint_as_float(winA[HL4 + idx]);
-      if (idx < 0) l += va; else if (idx < K) o += va; else r += va;
-    }
-    aL[h] = l; aO[h] = o; aR[h] = r;
+  for (int j = -R; j <= R; ++j) {
+    const float va = __uint_as_float(winA[HL4 + j]);
+    if (j < 0) aL += va; else aO += va;
   }
-  if constexpr (NCH == 2) {
-    if constexpr (2 * R + 1 > H) {
-      const float mid = wsum_f<H - R, R>(winB, HL4);
-      b[0] = mid + wsum_f<-R, H - R - 1>(winB, HL4);
-      b[NCH - 1] = mid + wsum_f<R + 1, H + R>(winB, HL4);
-    } else {
-      b[0] = wsum_f<-R, R>(winB, HL4);
-      b[NCH - 1] = wsum_f<H - R, H + R>(winB, HL4);
-    }
-  } else {
-    b[0] = wsum_f<-R, R>(winB, HL4);
-  }
+  float a = aL + aO, aR = 0.f;
+  A[0] = a;
+  B[0] = fmaf(dl, aL, b);
 #pragma unroll
-  for (int c = 0; c < H; ++c) {
-#pragma unroll
-    for (int h = 0; h < NCH; ++h) {
-      const int col = h * H + c;
-      if (c > 0) {
-        const int in = col + R, out = col - R - 1;
-        const float vin = __uint_as_float(winA[HL4 + in]), vout = __uint_as_float(winA[HL4 + out]);
-        if (in < K) aO[h] += vin; else aR[h] += vin;
-        if (out < 0) aL[h] -= vout; else aO[h] -= vout;
-        b[h] = (b[h] + __uint_as_float(winB[HL4 + in])) - __uint_as_float(winB[HL4 + out]);
-      }
-      A[col] = (aL[h] + aO[h]) + aR[h];
-      B[col] = fmaf(dr, aR[h], fmaf(dl, aL[h], b[h]));
-    }
+  for (int c = 1; c < K; ++c) {
+    const int in = c + R, out = c - R - 1;
+    const float vin = __uint_as_float(winA[HL4 + in]), vout = __uint_as_float(winA[HL4 + out]);
+    a = (a + vin) - vout;
+    if (in >= K) aR += vin;
+    if (out < 0) aL -= vout;
+    b = (b + __uint_as_float(winB[HL4 + in])) - __uint_as_float(winB[HL4 + out]);
+    A[c] = a;
+    B[c] = fmaf(dr, aR, fmaf(dl, aL, b));
   }
 }
 
