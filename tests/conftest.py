@@ -11,6 +11,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The built libraries are git-ignored: on a fresh checkout build them once (nvcc cross-compiles sm_100a without a
+    # GPU).  This is test set-up, not a fallback: the package itself never builds or substitutes anything.
+    lib = os.path.join(ROOT, "gpu_stereo_matching_b200", "libgsm.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "gpu_stereo_matching_b200", "csrc")], check=False,
+                       capture_output=True)
 
 
 @pytest.fixture(scope="session")
