@@ -170,12 +170,18 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
       for (int c = 0; c < K; ++c)
         if (c < c_lo || c > c_hi) key[c] = 0xffffffffu;
     }
-    u32 mine = 0xffffffffu;
+    // lane c keeps the minimum of column c: select tree on the lane bits (loop-invariant predicates)
+    static_assert(K == 16, "select tree below assumes 16 columns per thread");
+    u32 m[16];
 #pragma unroll
-    for (int c = 0; c < K; ++c) {
-      const u32 m = __reduce_min_sync(0xffffffffu, key[c]);
-      if (lane == c) mine = m;
-    }
+    for (int c = 0; c < 16; ++c) m[c] = __reduce_min_sync(0xffffffffu, key[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = (lane & 1) ? m[2 * i + 1] : m[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = (lane & 2) ? m[2 * i + 1] : m[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) m[i] = (lane & 4) ? m[2 * i + 1] : m[2 * i];
+    const u32 mine = (lane & 8) ? m[1] : m[0];
     if (lane < K && mine != 0xffffffffu)
       atomicMin(keys + ((size_t)frame * H + y) * W + x0 + lane, (i64)mine);
   }
