@@ -23,7 +23,7 @@ __host__ __device__ constexpr int exch_pitch_words(int runs, int K, int HL4) {
 }
 
 template <int R, int K, bool EXPORT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)  // two CTAs of 16 warps per SM: at most 64 registers
 sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __restrict__ keys, FusedGeom g) {
   constexpr int HL4 = (R + 3) / 4 * 4;
   constexpr int KW = K / 4;
