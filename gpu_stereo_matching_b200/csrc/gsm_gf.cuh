@@ -22,9 +22,6 @@ constexpr int GF_STAT_PLANES = 8;
 enum { ST_N = 0, ST_SI = 1, ST_INVDEN = 2, ST_CMEAN = 3, ST_INVN = 4, ST_IC = 5, ST_COEF = 6, ST_CEN = 7 };
 constexpr float GF_CENTRE = 128.0f;
 constexpr float GF_RECENTRE = 8.0f;
-#ifndef GSM_GF_FRESH
-#define GSM_GF_FRESH 0  // 1: add-only shadow accumulators swapped in every 2R+1 rows (bounds stage-2 drift; ~15% slower)
-#endif
 
 // N, S_I, 1/(N*S_II - S_I^2 + eps*N^2), S_I/N - 128, 1/N, I - 128 for every image pixel.
 constexpr int GS_T = 32;

@@ -17,7 +17,7 @@
  *   - every entry point returns 0 on success, a negative gsm_status otherwise;
  *     gsm_last_error() returns a thread-local description.  (The reference ignores every
  *     CUDA status; this ABI never does.)
- *   - a gsm_ctx owns all device memory, streams and pinned staging for ONE GPU and is used by
+ *   - a gsm_ctx owns all device memory and streams for ONE GPU and is used by
  *     one host thread at a time.  Nothing is allocated per call once the context is warm
  *     (reference: 6 cudaMalloc per call, never freed, Device.cu:187-194).
  *   - There is NO CPU fallback: without a CUDA device every call fails with GSM_ERR_CUDA.
@@ -84,7 +84,8 @@ int gsm_block_matching(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, 
 
 /* ---- full path, host buffers (the e2e path) ------------------------------------------------- */
 /* n frames of identical size, frame i at left + i*rows*cols.  mask may be NULL (written only with
- * lr_check).  Pipelined internally: pinned staging, H2D / kernels / D2H overlapped across frames. */
+ * lr_check).  Pipelined internally (uploads, kernels and downloads of consecutive chunks overlap on three streams);
+ * fully asynchronous only when the host buffers are page-locked. */
 int gsm_stereo_batch(gsm_ctx* ctx, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
                      uint8_t* disparity, uint8_t* mask, int rows, int cols);
 
