@@ -196,10 +196,10 @@ __device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const
   for (int c = 1; c < K; ++c) {
     const int in = c + R, out = c - R - 1;
     const float vin = __uint_as_float(winA[HL4 + in]), vout = __uint_as_float(winA[HL4 + out]);
-    a = (a + vin) - vout;
+    a += vin - vout;  // difference first: one rounding at the magnitude of the window sum instead of two
     if (in >= K) aR += vin;
     if (out < 0) aL -= vout;
-    b = (b + __uint_as_float(winB[HL4 + in])) - __uint_as_float(winB[HL4 + out]);
+    b += __uint_as_float(winB[HL4 + in]) - __uint_as_float(winB[HL4 + out]);
     A[c] = a;
     B[c] = fmaf(dr, aR, fmaf(dl, aL, b));
   }

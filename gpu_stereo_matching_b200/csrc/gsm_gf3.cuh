@@ -319,11 +319,13 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
         }
       }
       const float* st_l = reinterpret_cast<const float*>(stg + sg.off_ST) + run * K;
+      const bool has_lead = t >= a0, has_trail = t2 >= a0;
 #pragma unroll
       for (int g4 = 0; g4 < K; g4 += 4) {
+        float da[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-          if (which == 0 ? (t >= a0) : (t2 >= a0)) {
+          if (which == 0 ? has_lead : has_trail) {
             const float* st = st_l + which * 5 * TWt;
             const int4 N = *reinterpret_cast<const int4*>(st + ST_N * TWt + g4);
             const int4 SI = *reinterpret_cast<const int4*>(st + ST_SI * TWt + g4);
@@ -341,10 +343,14 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
               const int num = Nn[j] * sip - SIi[j] * sp;  // exact modulo 2^32; true value fits int32 for r <= 9
               const float a = (float)num * idn[j];
               const float b = fmaf(-a, cmv[j] - cc, (float)sp * inn[j]);
-              if (which == 0) { VA[c] += a; VB[c] += b; } else { VA[c] -= a; VB[c] -= b; }
+              // lead row enters, trail row leaves: form the small difference first, then ONE rounding at the
+              // magnitude of the running sum
+              if (which == 0) { da[j] = a; db[j] = b; } else { da[j] -= a; db[j] -= b; }
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { VA[g4 + j] += da[j]; VB[g4 + j] += db[j]; }
       }
     }
 
