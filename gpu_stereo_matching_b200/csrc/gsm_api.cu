@@ -63,6 +63,27 @@ struct gsm_ctx {
 // strip halo (columns) a fused kernel needs on each side of its output columns
 static int stage_halo_of(int /*mode*/, int radius) { return radius; }  // GF: stage 1 needs no exchanged halo
 
+// CTA shape of the fused kernels (compile-time in the kernels, mirrored here for the plane geometry)
+#ifndef GSM_SAD_RUNS
+#define GSM_SAD_RUNS 16
+#endif
+#ifndef GSM_GF_K
+#define GSM_GF_K 16
+#endif
+#ifndef GSM_GF_RUNS
+#define GSM_GF_RUNS 12
+#endif
+#ifndef GSM_GF_LPR
+#define GSM_GF_LPR 32
+#endif
+static int strip_columns(int mode) { return mode == GSM_MODE_SAD ? GSM_SAD_RUNS * 16 : GSM_GF_RUNS * GSM_GF_K; }
+// left halo of a strip: a multiple of 4 >= the stage halo; a whole 16-column run when that costs no output column
+// (then the first run, like the last, only feeds its neighbours and skips the output stage)
+static int strip_left_halo(int TWt, int stage_halo) {
+  const int hl = round_up(stage_halo, 4);
+  return ((TWt - 16 - stage_halo) / 16 == (TWt - hl - stage_halo) / 16) ? 16 : hl;
+}
+
 static int max_pitch(int cols) { return round_up(PADL_BASE + 16 + cols + PADR, 16); }
 
 static PlaneGeom make_plane_geom(int rows, int cols, int hl) {
@@ -237,8 +258,8 @@ struct Plan {
 static Plan make_plan(const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, int view, int K,
                       int runs, int stage_halo, int exch_planes, int HL4, int lpr = WARP) {
   Plan pl;
-  const int hl = round_up(stage_halo, 4);
   const int TWt = runs * K;
+  const int hl = strip_left_halo(TWt, stage_halo);
   int TW = (TWt - hl - stage_halo) / 16 * 16;
   pl.g.pg = make_plane_geom(rows, cols, hl);
   pl.g.D = p->num_disp;
@@ -300,9 +321,6 @@ template <bool EXPORT>
 static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, int view,
                       const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0, int end_) {
   constexpr int K = 16;
-#ifndef GSM_SAD_RUNS
-#define GSM_SAD_RUNS 16
-#endif
   const int runs = GSM_SAD_RUNS;
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
@@ -335,18 +353,9 @@ template <bool EXPORT>
 static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, float eps,
                      int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
                      int end_) {
-#ifndef GSM_GF_K
-#define GSM_GF_K 16
-#endif
   constexpr int K = GSM_GF_K;
   // 12 runs of 16 columns x 32 disparities per CTA: a 192-column strip, 160 of them output columns (v3 needs a halo
   // of only r columns).  Measured alternatives at 720p x 128d: 24 runs x 16 disparities 1654 fps, this 1713 fps.
-#ifndef GSM_GF_RUNS
-#define GSM_GF_RUNS 12
-#endif
-#ifndef GSM_GF_LPR
-#define GSM_GF_LPR 32
-#endif
   constexpr int runs = GSM_GF_RUNS, lpr = GSM_GF_LPR;
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
@@ -438,7 +447,7 @@ static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int c
                          void* export_ptr = nullptr, int ed0 = 0, int end_ = 0) {
   const size_t npx = (size_t)n * rows * cols;
   const int stage_halo = stage_halo_of(p->mode, p->radius);
-  const PlaneGeom pg = make_plane_geom(rows, cols, round_up(stage_halo, 4));
+  const PlaneGeom pg = make_plane_geom(rows, cols, strip_left_halo(strip_columns(p->mode), stage_halo));
   int rc;
   // guide / other planes.  view 0: guide L, other R (zero pad).  view 1: guide R, other L right-replicated.
   u8* Gp = view == 0 ? c->planeL : c->planeR;
