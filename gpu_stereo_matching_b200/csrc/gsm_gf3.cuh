@@ -54,9 +54,19 @@ struct Gf3Stage {
         bytes(3 * (twt + 32) + 3 * (twt + 64) + 60 * twt + 4 * ((runs + 3) / 4 * 4)) {}  // == sum of the bulk copies
 };
 
+// Input stages in flight: the copies of step t + GF3_NST - 1 are issued during step t (right after its barrier), so
+// with 3 stages the bulk copies have a whole march step to land.  (With 2 stages they had only the stage-2 + WTA
+// part of a step: ncu showed 11.5% of all warp samples waiting on the stage mbarrier.)
+#ifndef GSM_GF_STAGES
+#define GSM_GF_STAGES 3
+#endif
+constexpr int GF3_NST = GSM_GF_STAGES;
+static_assert(GF3_NST >= 2 && GF3_NST <= 4, "2..4 input stages");
+
 __host__ __device__ inline size_t gf3_smem_bytes(int runs, int K, int HL4, int LPR) {
-  // barriers + centres | 2 input stages | 2 (double buffer) x 2 (V_A, V_B) exchange planes
-  return 512 + 2 * (size_t)Gf3Stage(runs * K, runs).bytes + 4 * (size_t)LPR * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+  // barriers + centres | GF3_NST input stages | 2 (double buffer) x 2 (V_A, V_B) exchange planes
+  return 512 + GF3_NST * (size_t)Gf3Stage(runs * K, runs).bytes +
+         4 * (size_t)LPR * exch_pitch_words(runs, K, HL4) * sizeof(u32);
 }
 
 // window of a thread per staged row: columns x0-12 .. x0+K+11, i.e. K+24 bytes = WW words (K = 16: 10, K = 12: 9)
@@ -145,14 +155,14 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   constexpr int planew = LPR * pitchw;
   float* ccs = reinterpret_cast<float*>(smem_raw + 64);  // [2][<=48] per-run centres, double buffered
   u8* stage_base = smem_raw + 512;
-  u32* exch = reinterpret_cast<u32*>(stage_base + 2 * sg.bytes);  // [2 buffers][V_A, V_B][LPR][pitchw]
+  u32* exch = reinterpret_cast<u32*>(stage_base + GF3_NST * sg.bytes);  // [2 buffers][V_A, V_B][LPR][pitchw]
   const u32 bar0 = smem_u32(smem_raw);
   const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
 
   for (int i = threadIdx.y * WARP + threadIdx.x; i < 4 * planew; i += runs * LPR) exch[i] = 0u;
   if (producer) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+#pragma unroll
+    for (int i = 0; i < GF3_NST; ++i) mbar_init(bar0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -227,12 +237,17 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   constexpr int COEF_PM = (int)0xFFFF0001;
   const int t_begin = yb0 - 3 * R, t_end = yb1 + R;
 
-  if (producer) issue(t_begin, 0);
+  if (producer) {
+#pragma unroll
+    for (int i = 0; i < GF3_NST - 1; ++i)
+      if (t_begin + i < t_end) issue(t_begin + i, i);
+  }
 
+  int s = 0;       // stage of step t: it % GF3_NST
+  u32 sphase = 0;  // its mbarrier parity: (it / GF3_NST) & 1
   for (int t = t_begin; t < t_end; ++t) {
     const int it = t - t_begin;
-    const int s = it & 1;
-    mbar_wait(bar0 + 8 * s, (u32)((it >> 1) & 1));
+    mbar_wait(bar0 + 8 * s, sphase);
     const u8* stg = stage_base + (size_t)s * sg.bytes;
     const int t2 = t - 2 * R - 1;
 
@@ -363,8 +378,9 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       if (lane == 0) ccbuf[run] = cc;
     }
     __syncthreads();
-    // every thread has now finished step t-1 completely: its stage can be refilled for step t+1
-    if (producer && t + 1 < t_end) issue(t + 1, s ^ 1);
+    // every thread has now finished step t-1 completely: its stage is refilled for step t + GF3_NST - 1
+    if (producer && t + GF3_NST - 1 < t_end) issue(t + GF3_NST - 1, s == 0 ? GF3_NST - 1 : s - 1);
+    if (++s == GF3_NST) { s = 0; sphase ^= 1u; }
     if (y < yb0 || !need_out) continue;
 
     // ---------------- stage 2, horizontal + q + WTA
