@@ -61,6 +61,9 @@ struct Gf3Stage {
 #define GSM_GF_STAGES 3
 #endif
 constexpr int GF3_NST = GSM_GF_STAGES;
+#ifndef GSM_GF_MINB
+#define GSM_GF_MINB 1  // CTAs per SM the register allocation is sized for
+#endif
 static_assert(GF3_NST >= 2 && GF3_NST <= 4, "2..4 input stages");
 
 __host__ __device__ inline size_t gf3_smem_bytes(int runs, int K, int HL4, int LPR) {
@@ -127,7 +130,7 @@ __device__ __forceinline__ void gf3_init_sums(const u32 (&g)[WW], const u32 (&p)
 }
 
 template <int R, int K, int RUNS, int LPR, bool EXPORT>
-__global__ void __launch_bounds__(RUNS * LPR, 1)
+__global__ void __launch_bounds__(RUNS * LPR, GSM_GF_MINB)
 gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
                i64* __restrict__ keys, FusedGeom g) {
   static_assert((K == 16 || K == 12) && R <= 12 && R >= 1 && R < K, "12/16-column runs, halo of at most 12 columns");
@@ -243,10 +246,9 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       if (t_begin + i < t_end) issue(t_begin + i, i);
   }
 
-  int s = 0;       // stage of step t: it % GF3_NST
-  u32 sphase = 0;  // its mbarrier parity: (it / GF3_NST) & 1
-  for (int t = t_begin; t < t_end; ++t) {
-    const int it = t - t_begin;
+  // ================ part A of row `it` (input stage s): stage 1, (a, b), publish (V_A, V_B)
+  auto part_a = [&](int it, int s, u32 sphase) {
+    const int t = t_begin + it;
     mbar_wait(bar0 + 8 * s, sphase);
     const u8* stg = stage_base + (size_t)s * sg.bytes;
     const int t2 = t - 2 * R - 1;
@@ -377,13 +379,15 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       exch_store<K, HL4>(xbuf + planew, reinterpret_cast<u32(&)[K]>(VB));
       if (lane == 0) ccbuf[run] = cc;
     }
-    __syncthreads();
-    // every thread has now finished step t-1 completely: its stage is refilled for step t + GF3_NST - 1
-    if (producer && t + GF3_NST - 1 < t_end) issue(t + GF3_NST - 1, s == 0 ? GF3_NST - 1 : s - 1);
-    if (++s == GF3_NST) { s = 0; sphase ^= 1u; }
-    if (y < yb0 || !need_out) continue;
+  };
 
-    // ---------------- stage 2, horizontal + q + WTA
+  // ================ part B of row `it` (after the barrier that publishes it): stage 2 horizontal, q, WTA
+  auto part_b = [&](int it, int s) {
+    const int y = t_begin + it - R;
+    if (y < yb0 || !need_out) return;
+    const u8* stg = stage_base + (size_t)s * sg.bytes;
+    const u32* xbuf = xb + (size_t)(it & 1) * 2 * planew;
+    const float* ccbuf = ccs + (it & 1) * 48;
     float A[K], B[K];
     {
       u32 winA[HL4 + K + HL4], winB[HL4 + K + HL4];
@@ -454,6 +458,18 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       const i64 k64 = (i64)(((unsigned long long)(u32)(mine & ~31) << 32) | (u32)(d0 + (mine & 31)));
       atomicMin(keys + ((size_t)frame * H + y) * W + x0 + lane, k64);
     }
+  };
+
+  const int T = t_end - t_begin;
+  int s = 0;       // stage of row it: it % GF3_NST
+  u32 sphase = 0;  // its mbarrier parity: (it / GF3_NST) & 1
+  for (int it = 0; it < T; ++it) {
+    part_a(it, s, sphase);
+    __syncthreads();
+    // every thread has now finished row it-1 completely: its stage is refilled for row it + GF3_NST - 1
+    if (producer && it + GF3_NST - 1 < T) issue(t_begin + it + GF3_NST - 1, s == 0 ? GF3_NST - 1 : s - 1);
+    part_b(it, s);
+    if (++s == GF3_NST) { s = 0; sphase ^= 1u; }
   }
 }
 
