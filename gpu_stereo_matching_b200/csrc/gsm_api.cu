@@ -373,17 +373,11 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     c->stat_key[view] = key;
   }
   {
-    const int tw = GS_T + 2 * R;
-    const size_t sm = (size_t)((tw * tw + 3) / 4 + 2 * tw * GS_T) * sizeof(int);
-    gf_stats_kernel<<<dim3((cols + GS_T - 1) / GS_T, (rows + GS_T - 1) / GS_T, n), dim3(GS_T, 8), sm, s>>>(G, stats, pg,
-                                                                                                          R, eps);
-    c->launches++;
-    gf_hcoef_kernel<<<dim3((cols + 64 + 255) / 256, pg.plane_rows, n), 256, 0, s>>>(G, stats, pg, R);
-    c->launches++;
-    {
-      const int strips = (int)pl.grid.x, cenw = (runs + 3) / 4 * 4;
-      gf_centre_kernel<<<dim3((strips * cenw + 63) / 64, rows, n), 64, 0, s>>>(stats, pg, pl.g.TW, pl.g.hl, K, runs, strips);
-    }
+    static_assert(K == 16, "gf_prepass_kernel assumes one global grid of 16-column runs");
+    const int strips = (int)pl.grid.x;
+    const int nbx = (cols + R + 1 + pl.g.hl + PP_HALO + PP_TX - 1) / PP_TX;
+    gf_prepass_kernel<<<dim3(nbx, (rows + PP_ROWS - 1) / PP_ROWS, n), PP_THREADS, 0, s>>>(G, stats, pg, R, eps, pl.g.TW,
+                                                                                         pl.g.hl, runs, strips);
     c->launches++;
     CK(cudaGetLastError());
   }

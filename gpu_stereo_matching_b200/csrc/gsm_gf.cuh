@@ -23,87 +23,107 @@ enum { ST_N = 0, ST_SI = 1, ST_INVDEN = 2, ST_CMEAN = 3, ST_INVN = 4, ST_IC = 5,
 constexpr float GF_CENTRE = 128.0f;
 constexpr float GF_RECENTRE = 8.0f;
 
-// N, S_I, 1/(N*S_II - S_I^2 + eps*N^2), S_I/N - 128, 1/N, I - 128 for every image pixel.
-constexpr int GS_T = 32;
-__global__ void __launch_bounds__(GS_T * 8)
-gf_stats_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom pg, int R, float eps) {
-  extern __shared__ int gs_smem[];
-  const int tw = GS_T + 2 * R;
-  u8* tile = reinterpret_cast<u8*>(gs_smem);                       // [tw][tw] (padded to 4)
-  int* hsI = gs_smem + (tw * tw + 3) / 4;                          // [tw][GS_T]
-  int* hsII = hsI + tw * GS_T;
+// ---- fused guide pre-pass -----------------------------------------------------------------------------------
+// One kernel writes every disparity-independent plane of a frame: N, S_I, 1/(N*S_II - S_I^2 + eps*N^2),
+// mean_I - 128, 1/N, I - 128 (image pixels), the horizontal-slide coefficient word of gsm_gf3.cuh (image columns
+// and R + 1 margin columns) and the per-run local centres.  A block owns PP_TX columns (PP_HALO more on each side
+// feed the window sums) and marches down PP_ROWS rows: thread = column, vertical running sums of I and I^2 in
+// registers, horizontal window sums from per-warp prefix sums (shuffle scan + shared memory), one barrier per row.
+// The 16-column runs of all strips lie on one global grid (TW is a multiple of 16, every strip starts hl columns
+// left of a multiple of TW), so a block's columns start on a run boundary and a run's centre is written to the
+// (strip, run) slots of the one or two strips that contain it.
+constexpr int PP_TX = 128, PP_HALO = 16, PP_THREADS = PP_TX + 2 * PP_HALO, PP_ROWS = 32;
+__global__ void __launch_bounds__(PP_THREADS)
+gf_prepass_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom pg, int R, float eps, int TW, int hl,
+                  int runs, int strips) {
+  __shared__ int PW1[2][PP_THREADS], PW2[2][PP_THREADS], PIX[2][PP_THREADS];
+  __shared__ float CM[2][PP_THREADS];
+  const int tid = threadIdx.x, lane = tid & 31;
   const int f = blockIdx.z;
-  const int bx = blockIdx.x * GS_T, by = blockIdx.y * GS_T;
-  const u8* src = Ip + (size_t)f * pg.plane_stride + (size_t)(PADV + by - R) * pg.pitch + pg.xoff + bx - R;
-  const int tid = threadIdx.y * GS_T + threadIdx.x;
-  for (int i = tid; i < tw * tw; i += GS_T * 8) {
-    const int ty = i / tw, tx = i - ty * tw;
-    // rows beyond the bottom pad can only be reached by tiles hanging below the image; clamp the read
-    const int prow = min(PADV + by - R + ty, pg.plane_rows - 1) - (PADV + by - R);
-    tile[i] = src[(size_t)prow * pg.pitch + tx];
-  }
-  __syncthreads();
-  for (int i = tid; i < tw * GS_T; i += GS_T * 8) {
-    const int ty = i / GS_T, tx = i - ty * GS_T;
-    int s = 0, s2 = 0;
-    for (int j = 0; j <= 2 * R; ++j) {
-      const int v = tile[ty * tw + tx + j];
-      s += v;
-      s2 += v * v;
-    }
-    hsI[i] = s;
-    hsII[i] = s2;
-  }
-  __syncthreads();
-  const size_t plane_elems = pg.plane_stride;  // elements per statistic plane
+  const int x = -hl - PP_HALO + (int)blockIdx.x * PP_TX + tid - PP_HALO;  // output threads: tid in [PP_HALO, PP_HALO + PP_TX)
+  const int yb = blockIdx.y * PP_ROWS, ye = min(pg.H, yb + PP_ROWS);
+  const int H = pg.H, W = pg.W;
+  const size_t plane_elems = pg.plane_stride;
+  const u8* col = Ip + (size_t)f * pg.plane_stride + (size_t)PADV * pg.pitch + pg.xoff + x;
   float* base = stats + (size_t)f * GF_STAT_PLANES * plane_elems;
-  for (int ry = threadIdx.y; ry < GS_T; ry += 8) {
-    const int x = bx + threadIdx.x, y = by + ry;
-    if (x >= pg.W || y >= pg.H) continue;
-    int SI = 0, SII = 0;
-    for (int j = 0; j <= 2 * R; ++j) {
-      SI += hsI[(ry + j) * GS_T + threadIdx.x];
-      SII += hsII[(ry + j) * GS_T + threadIdx.x];
-    }
-    const int nx = min(pg.W - 1, x + R) - max(0, x - R) + 1;
-    const int ny = min(pg.H - 1, y + R) - max(0, y - R) + 1;
-    const int N = nx * ny;
-    const long long den = (long long)N * SII - (long long)SI * SI;
-    const double dden = (double)den + (double)eps * (double)N * (double)N;
-    const size_t o = (size_t)(PADV + y) * pg.pitch + pg.xoff + x;
-    reinterpret_cast<int*>(base + ST_N * plane_elems)[o] = N;
-    reinterpret_cast<int*>(base + ST_SI * plane_elems)[o] = SI;
-    base[ST_INVDEN * plane_elems + o] = (float)(1.0 / dden);
-    base[ST_CMEAN * plane_elems + o] = (float)((double)SI / N - (double)GF_CENTRE);
-    base[ST_INVN * plane_elems + o] = 1.0f / (float)N;
-    base[ST_IC * plane_elems + o] = (float)tile[(ry + R) * tw + threadIdx.x + R] - GF_CENTRE;
-  }
-}
+  const bool outp = tid >= PP_HALO && tid < PP_HALO + PP_TX;
+  const bool inimg = outp && x >= 0 && x < W;
+  const int cenw = (runs + 3) / 4 * 4, rps = TW / 16;
+  const bool leader = outp && (tid & 15) == 0;
+  const int gb = (x + hl) >> 4;  // global run index of a leader's run (x + hl is a multiple of 16 there)
 
-// Local centre plane: for every image row, every strip of the launch and every run of K columns of that strip, the
-// rounded mean of (mean_I - 128) over the run's in-image columns.  Layout [row][strip * CENW + run] inside a plane of
-// the usual row pitch (CENW = runs rounded up to 4), so a strip's centres are one 16-byte aligned bulk copy.
-__global__ void gf_centre_kernel(float* __restrict__ stats, PlaneGeom pg, int TW, int hl, int K, int runs, int strips) {
-  const int cenw = (runs + 3) / 4 * 4;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // strip * cenw + run
-  const int y = blockIdx.y;
-  const int f = blockIdx.z;
-  if (i >= strips * cenw) return;
-  const int strip = i / cenw, run = i - strip * cenw;
-  float* base = stats + (size_t)f * GF_STAT_PLANES * pg.plane_stride;
-  float c = 0.f;
-  if (run < runs) {
-    const int xa = strip * TW - hl + run * K;
-    const float* cm = base + ST_CMEAN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + pg.xoff;
+  auto write_centre = [&](int y) {  // centre of row y of the leader's run, from the row's CM buffer
+    if (!leader || gb < 0) return;
+    const float* cm = CM[y & 1] + tid;
     float sum = 0.f;
     int n = 0;
-    for (int j = 0; j < K; ++j) {
-      const int x = xa + j;
-      if (x >= 0 && x < pg.W) { sum += cm[x]; ++n; }
+    for (int j = 0; j < 16; ++j)
+      if (x + j >= 0 && x + j < W) { sum += cm[j]; ++n; }
+    const float c = n ? rintf(sum / (float)n) : 0.f;
+    float* cen = base + ST_CEN * plane_elems + (size_t)(PADV + y) * pg.pitch;
+    const int s0 = gb / rps;
+    for (int s = s0; s >= s0 - 1; --s) {
+      const int run = gb - s * rps;
+      if (s >= 0 && s < strips && run < runs) cen[s * cenw + run] = c;
     }
-    c = n ? rintf(sum / (float)n) : 0.f;
+  };
+
+  int v1 = 0, v2 = 0;
+  for (int yy = yb - R; yy < yb + R; ++yy) {
+    const int p = col[(long long)yy * pg.pitch];
+    v1 += p;
+    v2 += p * p;
   }
-  base[ST_CEN * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + i] = c;
+  // the three pixels of a row (entering, centre, leaving) are fetched one row ahead
+  int n_in = col[(long long)(yb + R) * pg.pitch], n_pc = col[(long long)yb * pg.pitch],
+      n_out = col[(long long)(yb - R) * pg.pitch];
+  for (int y = yb; y < ye; ++y) {
+    const int b = y & 1;
+    const int pin = n_in, pc = n_pc, pout = n_out;
+    n_in = col[(long long)(y + 1 + R) * pg.pitch];  // rows up to H + R: inside the bottom pad
+    n_pc = col[(long long)(y + 1) * pg.pitch];
+    n_out = col[(long long)(y + 1 - R) * pg.pitch];
+    v1 += pin;  // v = column sums over rows y-R .. y+R (zero pad rows outside the image)
+    v2 += pin * pin;
+    int s1 = v1, s2 = v2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
+      if (lane >= o) { s1 += t1; s2 += t2; }
+    }
+    PW1[b][tid] = s1;
+    PW2[b][tid] = s2;
+    PIX[b][tid] = pc;
+    __syncthreads();
+    if (y > yb) write_centre(y - 1);
+    if (outp) {
+      const int lo = tid - R - 1, hi = tid + R;  // window = (lo, hi]; it spans at most two warps
+      int SI = PW1[b][hi] - PW1[b][lo], SII = PW2[b][hi] - PW2[b][lo];
+      if ((lo >> 5) != (hi >> 5)) { SI += PW1[b][lo | 31]; SII += PW2[b][lo | 31]; }
+      const size_t o = (size_t)(PADV + y) * pg.pitch + pg.xoff + x;
+      reinterpret_cast<int*>(base + ST_COEF * plane_elems)[o] = PIX[b][tid + R] - 65536 * PIX[b][tid - R - 1];
+      float cmv = 0.f;
+      if (inimg) {
+        const int nx = min(W - 1, x + R) - max(0, x - R) + 1;
+        const int ny = min(H - 1, y + R) - max(0, y - R) + 1;
+        const int N = nx * ny;
+        const long long den = (long long)N * SII - (long long)SI * SI;
+        const double dden = (double)den + (double)eps * (double)N * (double)N;
+        cmv = (float)((double)SI / N - (double)GF_CENTRE);
+        reinterpret_cast<int*>(base + ST_N * plane_elems)[o] = N;
+        reinterpret_cast<int*>(base + ST_SI * plane_elems)[o] = SI;
+        base[ST_INVDEN * plane_elems + o] = (float)(1.0 / dden);
+        base[ST_CMEAN * plane_elems + o] = cmv;
+        base[ST_INVN * plane_elems + o] = 1.0f / (float)N;
+        base[ST_IC * plane_elems + o] = (float)pc - GF_CENTRE;
+      }
+      CM[b][tid] = cmv;
+    }
+    v1 -= pout;
+    v2 -= pout * pout;
+  }
+  __syncthreads();
+  if (ye > yb) write_centre(ye - 1);
 }
 
 // publish K words at buf, then (after the CTA barrier) gather the window [-HL4, K+HL4) around them

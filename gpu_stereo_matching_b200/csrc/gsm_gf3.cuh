@@ -24,18 +24,8 @@
 namespace gsm {
 
 // IDP.2A coefficient plane of the horizontal slide: HC[y][x] = I[y][x+R] - 65536 * I[y][x-R-1]
-// (lo16 = +I of the column entering the window of x, hi16 = -I of the column leaving it).  Stored in ST_COEF.
-__global__ void gf_hcoef_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom pg, int R) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x - 32;  // a margin of columns left and right of the image
-  const int y = (int)blockIdx.y - PADV;
-  const int f = blockIdx.z;
-  if (x >= pg.W + 32) return;
-  const u8* row = Ip + (size_t)f * pg.plane_stride + (size_t)(PADV + y) * pg.pitch + pg.xoff;
-  const int in = row[x + R];
-  const int out = row[x - R - 1];
-  int* coef = reinterpret_cast<int*>(stats + ((size_t)f * GF_STAT_PLANES + ST_COEF) * pg.plane_stride);
-  coef[(size_t)(PADV + y) * pg.pitch + pg.xoff + x] = in - 65536 * out;
-}
+// (lo16 = +I of the column entering the window of x, hi16 = -I of the column leaving it).  Stored in ST_COEF by
+// gf_prepass_kernel (gsm_gf.cuh).
 
 // Stage of one march step (TWt strip columns):
 //   G[3][TWt+32] u8      guide rows t+R, t-R-1, t-3R-2, columns [xs-16, xs+TWt+16)
