@@ -62,23 +62,18 @@ __host__ __device__ inline size_t gf3_smem_bytes(int runs, int K, int HL4, int L
          4 * (size_t)LPR * exch_pitch_words(runs, K, HL4) * sizeof(u32);
 }
 
-// window of a thread per staged row: columns x0-12 .. x0+K+11, i.e. K+24 bytes = WW words (K = 16: 10, K = 12: 9)
+// window of a thread per staged row: columns x0-12 .. x0+K+11, i.e. K+24 bytes = WW = 10 words
 
 // AD bytes of the thread's window of one staged row.  growk = staged guide row + run*K (byte 0 is column x0-16).
 template <int K>
 __device__ __forceinline__ void gf3_ad_window(const u8* growk, const u8* orow, int ooff, u32 (&g)[(K + 24) / 4],
                                               u32 (&p)[(K + 24) / 4]) {
   constexpr int WW = (K + 24) / 4;
-  if constexpr (K == 16) {  // 16-byte aligned: three 128-bit loads
-    const uint4 a = reinterpret_cast<const uint4*>(growk)[0];
-    const uint4 b = reinterpret_cast<const uint4*>(growk)[1];
-    const uint4 c = reinterpret_cast<const uint4*>(growk)[2];
-    g[0] = a.y; g[1] = a.z; g[2] = a.w; g[3] = b.x; g[4] = b.y; g[5] = b.z; g[6] = b.w; g[7] = c.x; g[8] = c.y; g[9] = c.z;
-  } else {  // run*K is only 4-byte aligned: word loads (broadcast within the warp)
-    const u32* w = reinterpret_cast<const u32*>(growk + 4);
-#pragma unroll
-    for (int i = 0; i < WW; ++i) g[i] = w[i];
-  }
+  static_assert(K == 16, "16-byte aligned runs: three 128-bit loads");
+  const uint4 a = reinterpret_cast<const uint4*>(growk)[0];
+  const uint4 b = reinterpret_cast<const uint4*>(growk)[1];
+  const uint4 c = reinterpret_cast<const uint4*>(growk)[2];
+  g[0] = a.y; g[1] = a.z; g[2] = a.w; g[3] = b.x; g[4] = b.y; g[5] = b.z; g[6] = b.w; g[7] = c.x; g[8] = c.y; g[9] = c.z;
   u32 ow[WW];
   lds_unaligned<K + 24>(orow, ooff, ow);
 #pragma unroll
@@ -123,7 +118,7 @@ template <int R, int K, int RUNS, int LPR, bool EXPORT>
 __global__ void __launch_bounds__(RUNS * LPR, GSM_GF_MINB)
 gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
                i64* __restrict__ keys, FusedGeom g) {
-  static_assert((K == 16 || K == 12) && R <= 12 && R >= 1 && R < K, "12/16-column runs, halo of at most 12 columns");
+  static_assert(K == 16 && R <= 12 && R >= 1 && R < K, "16-column runs, halo of at most 12 columns");
   constexpr int WW = (K + 24) / 4;
   static_assert(LPR == 32 || LPR == 16, "lanes per run");
   constexpr int HL4 = (R + 3) / 4 * 4;
