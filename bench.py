@@ -254,9 +254,21 @@ def _extra_config(args, rank, world, local_rank):
             ctx.finalize_keys_device(a.data_ptr(), 0, Dd.data_ptr(), 0, h, w, p, sh)
 
         step = lambda: dsplit_stereo(partial, finalize, kl, None, p, world, rank)
+        par = f"disparity-split x{world}, one all-reduce(MIN) of the int64 packed (cost,d) plane over NCCL/NVLink"
+        if world > 1 and args.combine == "p2p":
+            # the combine fused over peer memory: reduce-scatter + finalize + all-gather of the u8 map in ONE kernel
+            # of P2P loads / stores (gsm_reduce_keys_p2p); falls back to the NCCL all-reduce when symmetric memory
+            # cannot be set up on this box
+            try:
+                from gpu_stereo_matching_b200.dist import PeerPlanes, dsplit_stereo_p2p
+                planes = PeerPlanes(h * w)
+                step = lambda: dsplit_stereo_p2p(ctx, partial, planes, p, sh)
+                par = (f"disparity-split x{world}, packed (cost,d) planes combined over NVLink peer memory "
+                       "(one reduce-scatter + finalize + all-gather kernel, gsm_reduce_keys_p2p)")
+            except Exception as e:  # noqa: BLE001
+                par += f" [peer memory unavailable: {type(e).__name__}: {e}]"
         de_step, scaling = h * w * d, "strong"
         workload = "config5: one synthetic 3840x2160 pair, 256 disparities, GF r=9, split by disparity range"
-        par = f"disparity-split x{world}, one all-reduce(MIN) of the int64 packed (cost,d) plane over NCCL/NVLink"
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             step()
@@ -293,6 +305,8 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl"],
+                    help="config c5, N > 1: combine the ranks' planes over peer memory (default) or with an NCCL all-reduce")
     ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
                     help="c3 (default, the contract workload): 720p x128 GF frame batches; c4: 1080p x192 GF+LR+median "
                          "frame batches; c5: one 3840x2160 x256 GF pair split by disparity range across the ranks")

@@ -136,6 +136,14 @@ class StereoContext:
                                                     C.c_void_p(stream or None)))
 
     # ---- cost-stage exports ------------------------------------------------------------------
+    def reduce_keys_p2p(self, key_ptrs, disp_ptrs, rank: int, npx: int, stream=0):
+        """Peer-memory combine of a disparity split (gsm_reduce_keys_p2p): key_ptrs / disp_ptrs are the device
+        pointers of every rank's packed-min plane / disparity map as mapped into this process."""
+        world = len(key_ptrs)
+        ka = (C.c_void_p * world)(*[int(x) for x in key_ptrs])
+        da = (C.c_void_p * world)(*[int(x) for x in disp_ptrs])
+        _l.check(self._lib.gsm_reduce_keys_p2p(self._h, ka, da, world, rank, npx, C.c_void_p(stream or None)))
+
     def ad_volume(self, left, right, num_disp: int) -> np.ndarray:
         """== PreCal (BlockMatching.cpp:89-109): u8 [D][rows][cols]."""
         L, R = _u8c(left, "left"), _u8c(right, "right")

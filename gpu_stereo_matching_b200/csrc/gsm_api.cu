@@ -628,6 +628,35 @@ extern "C" int gsm_finalize_keys_device(gsm_ctx* c, const gsm_params* p, const v
                         (u8*)mask_dev, s);
 }
 
+extern "C" int gsm_reduce_keys_p2p(gsm_ctx* c, const void* const* key_ptrs, void* const* disp_ptrs, int world,
+                                   int rank, long long npx, void* stream) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  if (!key_ptrs || !disp_ptrs || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || npx < 1)
+    return fail(GSM_ERR_INVALID, "gsm_reduce_keys_p2p: world=%d rank=%d npx=%lld", world, rank, npx);
+  PeerPlanes pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int w = 0; w < world; ++w) {
+    if (!key_ptrs[w] || !disp_ptrs[w]) return fail(GSM_ERR_INVALID, "gsm_reduce_keys_p2p: null plane of rank %d", w);
+    if (((uintptr_t)key_ptrs[w] | (uintptr_t)disp_ptrs[w]) & 15)
+      return fail(GSM_ERR_INVALID, "gsm_reduce_keys_p2p: planes must be 16-byte aligned");
+    pp.keys[w] = (const i64*)key_ptrs[w];
+    pp.disp[w] = (u8*)disp_ptrs[w];
+  }
+  // slice boundaries on multiples of 16 pixels (128-byte runs of keys, 16-byte stores of disparities)
+  auto cut = [&](int r) { return r >= world ? (size_t)npx : (size_t)((long long)npx * r / world) / 16 * 16; };
+  const size_t begin = cut(rank), end = cut(rank + 1);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  if (end > begin) {
+    const size_t groups = (end - begin + 15) / 16;
+    const unsigned blocks = (unsigned)std::min<size_t>((groups + 255) / 256, 148 * 8);
+    reduce_keys_p2p_kernel<<<blocks, 256, 0, s>>>(pp, world, rank, begin, end);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  return GSM_OK;
+}
+
 // ---- cost-stage exports ------------------------------------------------------------------------
 static int ensure_export(gsm_ctx* c, size_t bytes) {
   if (c->export_bytes >= bytes) return GSM_OK;

@@ -72,3 +72,48 @@ def dsplit_stereo(partial_keys: Callable, finalize: Callable, keys_left, keys_ri
         if world > 1:
             all_reduce(keys)
     return finalize(keys_left, keys_right if params.lr_check else None)
+
+
+class PeerPlanes:
+    """Per-rank packed-min plane and disparity map in symmetric (peer-mapped) device memory, for dsplit_stereo_p2p.
+
+    Allocated with torch.distributed._symmetric_memory (CUDA IPC over NVLink / NVSwitch): after the rendezvous every
+    rank holds device pointers to every other rank's planes.  Raises if peer memory is unavailable -- callers fall
+    back to dsplit_stereo (NCCL all-reduce).
+    """
+
+    def __init__(self, npx: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        self.npx = int(npx)
+        self.keys = symm.empty(self.npx, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        self.disp = symm.empty(self.npx, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.keys_h = symm.rendezvous(self.keys, grp)
+        self.disp_h = symm.rendezvous(self.disp, grp)
+        self.world, self.rank = self.keys_h.world_size, self.keys_h.rank
+        self.key_ptrs = [int(p) for p in self.keys_h.buffer_ptrs]
+        self.disp_ptrs = [int(p) for p in self.disp_h.buffer_ptrs]
+
+
+def dsplit_stereo_p2p(ctx, partial_keys: Callable, planes: PeerPlanes, params, stream_handle: int = 0):
+    """Disparity-split evaluation of ONE frame with the combine fused over peer memory (no LR check / median).
+
+    partial_keys(view, d_begin, d_end, keys_tensor) as in dsplit_stereo.  Every rank ends with the full u8 map in
+    planes.disp.  Must run with torch's current stream == the stream behind stream_handle: the two cross-rank
+    barriers (symmetric-memory signal pads) are enqueued on the current stream.
+      barrier 1: every rank's plane is complete before anybody reads it over NVLink;
+      barrier 2: every slice has landed in every map, and nobody still reads a plane the next frame overwrites.
+    """
+    if params.lr_check or params.median_radius:
+        raise ValueError("dsplit_stereo_p2p combines the left view only; use dsplit_stereo for LR check / median")
+    d0, d1 = shard_disparities(params.num_disp, planes.world, planes.rank)
+    if d1 > d0:
+        partial_keys(0, d0, d1, planes.keys)
+    else:
+        planes.keys.fill_(key_init(params.mode, params.radius))
+    planes.keys_h.barrier(channel=0)
+    ctx.reduce_keys_p2p(planes.key_ptrs, planes.disp_ptrs, planes.rank, planes.npx, stream_handle)
+    planes.keys_h.barrier(channel=1)
+    return planes.disp

@@ -119,6 +119,15 @@ int gsm_finalize_keys_device(gsm_ctx* ctx, const gsm_params* p, const void* keys
                              const void* keys_right_dev, void* disparity_dev, void* mask_dev, int rows,
                              int cols, void* stream);
 
+/* Combine the ranks' packed-min planes over PEER MEMORY (NVLink P2P) instead of an all-reduce: rank `rank` of `world`
+ * reduces its 1/world slice of the npx pixels over all planes (key_ptrs[w] = rank w's int64 plane, mapped into this
+ * process, e.g. CUDA IPC / torch symmetric memory), turns it into u8 disparities and stores that slice into every
+ * rank's map disp_ptrs[w].  All planes 16-byte aligned.  The caller orders it across ranks: a barrier after every
+ * rank's gsm_partial_keys_device and one after this call (gpu_stereo_matching_b200/dist.py: dsplit_stereo_p2p).
+ * Replaces nothing in the reference (it is single-GPU); SURVEY 8e. */
+int gsm_reduce_keys_p2p(gsm_ctx* ctx, const void* const* key_ptrs, void* const* disp_ptrs, int world, int rank,
+                        long long npx, void* stream);
+
 /* ---- cost-stage exports (keep the reference's compareDiff / compareSAD checks possible) ------ */
 /* AD volume u8 [D][rows][cols] == PreCal, BlockMatching.cpp:89-109 (what compareDiff :263-276 checks). */
 int gsm_ad_volume(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, uint8_t* volume, int rows, int cols,
