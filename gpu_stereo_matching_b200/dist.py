@@ -7,6 +7,9 @@ Two strategies, nothing else:
                       leaves a per-pixel packed (cost, d) int64 word; ONE exchange step, an all-reduce(MIN)
                       over NCCL/NVLink, combines the ranks exactly (lowest d wins ties, like the reference's
                       strict '<', BlockMatching.cpp:178), independent of the number of ranks (dsplit_stereo).
+                      dsplit_stereo_p2p does the same exchange WITHOUT a collective library: the planes live in
+                      symmetric (peer-mapped) memory and one kernel per rank reduces its slice of all planes over
+                      NVLink P2P loads, finalizes it and stores it into every rank's map (gsm_reduce_keys_p2p).
 """
 from __future__ import annotations
 
