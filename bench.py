@@ -346,7 +346,10 @@ def main():
     Lh = torch.from_numpy(np.tile(Lu, (reps, 1, 1))[:n]).pin_memory()
     Rh = torch.from_numpy(np.tile(Ru, (reps, 1, 1))[:n]).pin_memory()
     Dh = torch.empty_like(Lh).pin_memory()
-    ctx = g.StereoContext(H, W, D, min(n, 32), device=local_rank)
+    # capacity of two submissions: the host path double-buffers HALF the capacity per chunk, so a submission of n
+    # frames is uploaded, computed (one launch of n frames, like the device-resident step) and downloaded as one chunk
+    # while the previous / next submission's copies run on their own streams
+    ctx = g.StereoContext(H, W, D, 2 * min(n, 32), device=local_rank)
     p = g.make_params("gf", R_GF, D, row_bands=0)
     Ld, Rd = Lh.cuda(non_blocking=True), Rh.cuda(non_blocking=True)
     Dd = torch.empty_like(Ld)
