@@ -54,6 +54,14 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t seed) {
       else if (OP == 26) { sm[(threadIdx.x + i * 32) & 1023] = a[i]; a[i] += c; }                 // STS.32
       else if (OP == 27) { f[i] = __uint_as_float(__byte_perm(a[i], 0x4b000000u, 0x7440)) - 8388608.0f; a[i] = __float_as_uint(f[i]) ^ a[j]; } // PRMT+FADD byte->float
       else if (OP == 28) { a[i] = __vimin3_s32(a[i], a[j], (int)c); }                              // VIMNMX3
+      else if (OP == 30) { a[i] = __reduce_min_sync(0xffffffffu, (int)(a[i] + c)) + a[j]; }          // REDUX.MIN + IADD
+      else if (OP == 31) { a[i] = __reduce_min_sync(0xffffffffu, (int)(a[i] + c)) + threadIdx.x; }     // REDUX.MIN (independent chains)
+      else if (OP == 32) { int bb = (int)a[i]; a[i] = (uint32_t)(bb ^ ((bb >> 31) & 0x7fffffff)) + a[j]; } // sortable + IADD
+      else if (OP == 33) { a[i] = a[i] ^ a[j]; }                                                        // LOP3 (xor)
+      else if (OP == 34) { int bb = (int)a[i]; int k = bb ^ ((bb >> 31) & 0x7fffffff); a[i] = (uint32_t)((k & ~31) | (int)(threadIdx.x & 31)) + a[j]; } // key prep + IADD
+      else if (OP == 35) { int bb = (int)a[i]; int sg = (int)__byte_perm((uint32_t)bb, 0u, 0xBBBB); int k = bb ^ (sg & 0x7fffffff); a[i] = (uint32_t)((k & ~31) | (int)(threadIdx.x & 31)) + a[j]; } // key prep, PRMT sign
+      else if (OP == 36) { a[i] = (a[i] >> 3) + a[j]; }                                                 // SHF + IADD
+      else if (OP == 37) { a[i] = (a[i] > a[j]) ? c : b; }                                              // ISETP + SEL
       else if (OP == 29) { f[i] = (float)((a[i] >> 8) & 0xff); a[i] = __float_as_uint(f[i]) + a[j]; } // I2F.U8.B1
     }
   }
@@ -122,6 +130,14 @@ int main() {
   run<27>("PRMT+FADD(b2f)+LOP", 3, d, sms, mhz);
   run<28>("VIMNMX3", 1, d, sms, mhz);
   run<29>("I2F.U8.B1+IADD(+shift?)", 2, d, sms, mhz);
+  run<30>("REDUX.MIN+IADD", 1, d, sms, mhz);
+  run<31>("REDUX.MIN+IADD(lane)", 1, d, sms, mhz);
+  run<32>("sortable(SHF+LOP3)+IADD", 1, d, sms, mhz);
+  run<33>("LOP3xor", 1, d, sms, mhz);
+  run<34>("keyprep(SHF+LOP3+LOP3)+IADD", 1, d, sms, mhz);
+  run<35>("keyprep(PRMT+LOP3+LOP3)+IADD", 1, d, sms, mhz);
+  run<36>("SHF+IADD", 1, d, sms, mhz);
+  run<37>("ISETP+SEL", 1, d, sms, mhz);
   cudaError_t e = cudaDeviceSynchronize();
   printf("{\"status\": \"%s\"}\n", cudaGetErrorString(e));
   return e != cudaSuccess;
