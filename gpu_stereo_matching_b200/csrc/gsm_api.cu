@@ -325,6 +325,7 @@ static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, R, 2, HL4);
+  pl.smem = sad_smem_bytes(runs, K, HL4);
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
   pl.g.export_nd = end_;

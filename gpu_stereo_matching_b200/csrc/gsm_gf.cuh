@@ -158,42 +158,6 @@ __device__ __forceinline__ float wsum_f(const u32 (&win)[N], int base) {
   return (p0 + p1) + p2;
 }
 
-// ---- asynchronous row staging (cp.async.bulk == TMA 1-D, completion on an mbarrier) -------------------------
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
-  u32 done;
-  do {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-
-// K bytes at byte offset `off` (any alignment) of a shared-memory row
-template <int K>
-__device__ __forceinline__ void lds_unaligned(const u8* row, int off, u32 (&w)[K / 4]) {
-  const u32* pa = reinterpret_cast<const u32*>(row + (off & ~3));
-  const u32 sel = 0x3210u + 0x1111u * (u32)(off & 3);
-  u32 t[K / 4 + 1];
-#pragma unroll
-  for (int i = 0; i <= K / 4; ++i) t[i] = pa[i];
-#pragma unroll
-  for (int i = 0; i < K / 4; ++i) w[i] = __byte_perm(t[i], t[i + 1], sel);
-}
-
 // Stage-2 horizontal pass.  winA / winB: [left halo HL4 | own K | right halo HL4].  The A window sum is kept as
 // three partial sums (columns owned by the left neighbour, by this run, by the right neighbour) because the
 // neighbours' B' sums are relative to THEIR centres: B'(x) = sum(winB) + dl * A_L(x) + dr * A_R(x).

@@ -11,6 +11,9 @@
 //             -> V rows exchanged through shared memory (halo of R columns from the neighbour runs)
 //             -> horizontal sliding sums, seeded with d so that the sum IS the packed key (SAD<<8)|d
 //             -> warp min over the 32 disparities (REDUX) -> one atomicMin per pixel on the packed plane
+// The four image rows of a step (guide and other image, entering and leaving row) are staged in shared memory two
+// steps ahead by one elected thread with cp.async.bulk + mbarrier (three stages), like the guided-filter kernel:
+// with direct LDGs 27% of the warp samples waited on the long scoreboard (profiles/r01_sad_*).
 // Algorithmic HBM traffic: 2 B/pixel read + 8 B/pixel packed-min plane traffic (L2 resident).
 #pragma once
 #include "gsm_common.cuh"
@@ -22,12 +25,20 @@ __host__ __device__ constexpr int exch_pitch_words(int runs, int K, int HL4) {
   return (HL4 + runs * K + HL4) + (((((HL4 + runs * K + HL4) / 4) & 1) == 0) ? 4 : 0);
 }
 
+// Input stage of one march step: G[2][TWt] guide rows y+R and y-R-1, O[2][TWt+64] the other image's rows, window
+// covering the CTA's 32 disparities.  SAD_NST stages, copies issued SAD_NST-1 steps ahead.
+constexpr int SAD_NST = 3, SAD_HDR = 64;
+__host__ __device__ constexpr int sad_stage_bytes(int twt) { return 2 * twt + 2 * (twt + 64); }
+__host__ __device__ inline size_t sad_smem_bytes(int runs, int K, int HL4) {
+  return SAD_HDR + SAD_NST * (size_t)sad_stage_bytes(runs * K) + 2 * (size_t)WARP * exch_pitch_words(runs, K, HL4) * sizeof(u32);
+}
+
 template <int R, int K, bool EXPORT>
 __global__ void __launch_bounds__(512, 2)  // two CTAs of 16 warps per SM: at most 64 registers
 sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __restrict__ keys, FusedGeom g) {
   constexpr int HL4 = (R + 3) / 4 * 4;
   constexpr int KW = K / 4;
-  extern __shared__ __align__(16) u32 smem[];
+  extern __shared__ __align__(128) u8 smem_raw[];
 
   const int lane = threadIdx.x;
   const int run = threadIdx.y;
@@ -42,18 +53,44 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
   if (yb0 >= H) return;
 
   const int pitchw = exch_pitch_words(runs, K, HL4);
+  const int TWt = runs * K;
+  const int GW = TWt, OW = TWt + 64, stage_bytes = sad_stage_bytes(TWt);
+  u8* stage_base = smem_raw + SAD_HDR;
+  u32* smem = reinterpret_cast<u32*>(stage_base + SAD_NST * stage_bytes);  // exchange planes [2][WARP][pitchw]
+  const u32 bar0 = smem_u32(smem_raw);
+  const bool producer = (threadIdx.x == 0 && threadIdx.y == 0);
   for (int i = threadIdx.y * WARP + threadIdx.x; i < 2 * WARP * pitchw; i += runs * WARP) smem[i] = 0u;
+  if (producer) {
+#pragma unroll
+    for (int i = 0; i < SAD_NST; ++i) mbar_init(bar0 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
-  const int x0 = strip * g.TW - g.hl + run * K;  // image column of this thread's first pixel
-  const int dd = min(d, MAX_DISP - 1);           // lanes past d_end compute in-bounds garbage, never submitted
-  const int osh = (g.view == 0) ? -dd : dd;       // "other" image is sampled at x - d (left) or x + d (right view)
+  const int xs = strip * g.TW - g.hl;
+  const int x0 = xs + run * K;            // image column of this thread's first pixel
+  const int d0 = g.d_begin + blockIdx.y * WARP;
+  const int dd = min(d, MAX_DISP - 1);    // lanes past d_end compute in-bounds garbage, never submitted
 
-  const u8* gbase = Gp + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + g.pg.xoff + x0;
-  const u8* obase_b = Op + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + g.pg.xoff + x0 + osh;
-  const u32 omis = (u32)(reinterpret_cast<uintptr_t>(obase_b) & 3u);
-  const u32* obase = reinterpret_cast<const u32*>(obase_b - omis);
-  const u32 osel = 0x3210u + 0x1111u * omis;
+  // "other" image is sampled at x - d (left) or x + d (right view): staged window of the CTA's 32 disparities
+  const u8* gsrc = Gp + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + g.pg.xoff + xs;
+  const int ostart = g.pg.xoff + xs + (g.view == 0 ? -(min(d0, MAX_DISP - 1) + WARP - 1) : min(d0, MAX_DISP - 1));
+  const int oalign = ostart & 15;
+  const u8* osrc = Op + (size_t)frame * g.pg.plane_stride + (size_t)PADV * pitch + (ostart - oalign);
+  const int ooff = oalign + run * K + (g.view == 0 ? (min(d0, MAX_DISP - 1) + WARP - 1 - dd) : dd - min(d0, MAX_DISP - 1));
+  const int row_lo = -PADV, row_hi = H + PADV - 1;
+  auto issue = [&](int y, int s) {  // rows y + R (entering) and y - R - 1 (leaving) of march step y
+    const u32 bar = bar0 + 8 * s;
+    const u32 dst = smem_u32(stage_base + (size_t)s * stage_bytes);
+    mbar_expect_tx(bar, (u32)stage_bytes);
+    const int rows2[2] = {y + R, y - R - 1};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long ro = (long long)max(row_lo, min(row_hi, rows2[i])) * pitch;
+      bulk_g2s(dst + i * GW, gsrc + ro, GW, bar);
+      bulk_g2s(dst + 2 * GW + i * OW, osrc + ro, OW, bar);
+    }
+  };
 
   // byte masks: a pixel contributes iff it is inside the image and (left view) x >= d:
   // BlockMatching.cpp:147-149 leaves dif_ at its memset 0 for c = x - d < 0.
@@ -89,24 +126,31 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
   const int r0 = yb0 - R;  // first image row that may enter a window of this band
   constexpr int COEF = (int)0xFF000100;  // lo16 = +256, hi16 = -256: V holds 256 * (vertical sum)
 
-  // running row pointers (one add per row instead of a 64-bit multiply per load)
-  const u8* g_new = gbase + (long long)(yb0 - R) * pitch;                   // row y + R
-  const u8* o_new = reinterpret_cast<const u8*>(obase) + (long long)(yb0 - R) * pitch;
-  const u8* g_old = gbase + (long long)(yb0 - 3 * R - 1) * pitch;           // row y - R - 1
-  const u8* o_old = reinterpret_cast<const u8*>(obase) + (long long)(yb0 - 3 * R - 1) * pitch;
-  for (int y = yb0 - 2 * R; y < yb1; ++y, g_new += pitch, o_new += pitch, g_old += pitch, o_old += pitch) {
+  const int y_begin = yb0 - 2 * R;
+  if (producer) {
+#pragma unroll
+    for (int i = 0; i < SAD_NST - 1; ++i)
+      if (y_begin + i < yb1) issue(y_begin + i, i);
+  }
+  int s = 0;       // stage of step y
+  u32 sphase = 0;  // its mbarrier parity
+  for (int y = y_begin; y < yb1; ++y) {
+    mbar_wait(bar0 + 8 * s, sphase);
+    const u8* stg = stage_base + (size_t)s * stage_bytes;
     u32 pn[KW], po[KW];
     {
       u32 gw[KW], ow[KW];
-      load_aligned<K>(g_new, gw);
-      load_unaligned<K>(reinterpret_cast<const u32*>(o_new), osel, ow);
+      const uint4 gv = *reinterpret_cast<const uint4*>(stg + run * K);
+      gw[0] = gv.x; gw[1] = gv.y; gw[2] = gv.z; gw[3] = gv.w;
+      lds_unaligned<K>(stg + 2 * GW, ooff, ow);
 #pragma unroll
       for (int w = 0; w < KW; ++w) pn[w] = __vabsdiffu4(gw[w], ow[w]);
     }
     if (y - R - 1 >= r0) {
       u32 gw[KW], ow[KW];
-      load_aligned<K>(g_old, gw);
-      load_unaligned<K>(reinterpret_cast<const u32*>(o_old), osel, ow);
+      const uint4 gv = *reinterpret_cast<const uint4*>(stg + GW + run * K);
+      gw[0] = gv.x; gw[1] = gv.y; gw[2] = gv.z; gw[3] = gv.w;
+      lds_unaligned<K>(stg + 2 * GW + OW, ooff, ow);
 #pragma unroll
       for (int w = 0; w < KW; ++w) po[w] = __vabsdiffu4(gw[w], ow[w]);
     } else {
@@ -122,14 +166,18 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
       const u32 pair = __byte_perm(pn[c / 4], po[c / 4], (c & 3) | ((4 + (c & 3)) << 4));  // {p_new, p_old, x, x}
       V[c] = dp2a_lo_su(COEF, pair, V[c]);
     }
-    if (y < yb0) continue;
-
     // ---- horizontal pass: publish V, read the neighbours' halo, slide ----
     u32* buf = smem + (size_t)(y & 1) * WARP * pitchw + (size_t)lane * pitchw + HL4 + run * K;
+    if (y >= yb0) {
 #pragma unroll
-    for (int w = 0; w < KW; ++w)
-      reinterpret_cast<uint4*>(buf)[w] = make_uint4(V[4 * w], V[4 * w + 1], V[4 * w + 2], V[4 * w + 3]);
+      for (int w = 0; w < KW; ++w)
+        reinterpret_cast<uint4*>(buf)[w] = make_uint4(V[4 * w], V[4 * w + 1], V[4 * w + 2], V[4 * w + 3]);
+    }
     __syncthreads();
+    // every thread has finished step y-1 completely: its stage is refilled for step y + SAD_NST - 1
+    if (producer && y + SAD_NST - 1 < yb1) issue(y + SAD_NST - 1, s == 0 ? SAD_NST - 1 : s - 1);
+    if (++s == SAD_NST) { s = 0; sphase ^= 1u; }
+    if (y < yb0) continue;
     int win[HL4 + K + HL4];
 #pragma unroll
     for (int w = 0; w < HL4 / 4; ++w) {
