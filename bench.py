@@ -254,6 +254,7 @@ def _extra_config(args, rank, world, local_rank):
             ctx.finalize_keys_device(a.data_ptr(), 0, Dd.data_ptr(), 0, h, w, p, sh)
 
         step = lambda: dsplit_stereo(partial, finalize, kl, None, p, world, rank)
+        p2p_planes = None
         par = f"disparity-split x{world}, one all-reduce(MIN) of the int64 packed (cost,d) plane over NCCL/NVLink"
         if world > 1 and args.combine == "p2p":
             # the combine fused over peer memory: reduce-scatter + finalize + all-gather of the u8 map in ONE kernel
@@ -263,6 +264,7 @@ def _extra_config(args, rank, world, local_rank):
                 from gpu_stereo_matching_b200.dist import PeerPlanes, dsplit_stereo_p2p
                 planes = PeerPlanes(h * w)
                 step = lambda: dsplit_stereo_p2p(ctx, partial, planes, p, sh)
+                p2p_planes = planes
                 par = (f"disparity-split x{world}, packed (cost,d) planes combined over NVLink peer memory "
                        "(one reduce-scatter + finalize + all-gather kernel, gsm_reduce_keys_p2p)")
             except Exception as e:  # noqa: BLE001
@@ -286,13 +288,25 @@ def _extra_config(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    cfg_extra = {}
+    if args.config == "c5" and p2p_planes is not None:
+        # outside the timed region: the peer-memory combine must give the map of the NCCL all-reduce path on every rank
+        with torch.cuda.stream(stream):
+            dsplit_stereo(partial, finalize, kl, None, p, world, rank)
+        stream.synchronize()
+        same = torch.tensor([int(torch.equal(p2p_planes.disp.view(-1), Dd.view(-1)))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        cfg_extra["combine_check"] = ("peer-memory map == all-reduce map on all ranks" if int(same.item()) == 1
+                                      else "MISMATCH between the peer-memory and the all-reduce combine")
+        Dd.copy_(p2p_planes.disp.view_as(Dd))
     if rank == 0:
         v = de_step / (ms * 1e-3) / 1e6
         print(json.dumps({"metric": "MDE/s", "value": v, "unit": "MDE/s", "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
                           "vs_baseline": None, "dtype": "u8/int32+fp32", "data": "synthetic",
                           "fps": v * 1e6 / (h * w * d) * (1 if args.config == "c5" else 1),
-                          "config": {"workload": workload, "parallelism": par, "l2": "inputs + statistic planes exceed L2"},
+                          "config": {"workload": workload, "parallelism": par, "l2": "inputs + statistic planes exceed L2",
+                                     **cfg_extra},
                           "result_checksum": int(Dd.to(torch.int64).sum().item()), "clocks": clk.summary()}))
     ctx.close()
 
