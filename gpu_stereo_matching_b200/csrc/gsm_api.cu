@@ -315,6 +315,14 @@ static int timing_end(gsm_ctx* c, cudaStream_t s) {
   return GSM_OK;
 }
 
+static i64 key_init(const gsm_params* p) {
+  if (p->mode == GSM_MODE_SAD) {
+    const int w = 2 * p->radius + 1;
+    return ((i64)(50 * w * w) << 8);  // BlockMatching.cpp:157-158: min = 50 * dNum, dm = -256 -> (uchar)0
+  }
+  return (i64)0x7fffffffffffff00LL;  // +inf cost, d = 0
+}
+
 #define SAD_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
 
 template <bool EXPORT>
@@ -377,8 +385,8 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     static_assert(K == 16, "gf_prepass_kernel assumes one global grid of 16-column runs");
     const int strips = (int)pl.grid.x;
     const int nbx = (cols + R + 1 + pl.g.hl + PP_HALO + PP_TX - 1) / PP_TX;
-    gf_prepass_kernel<<<dim3(nbx, (rows + PP_ROWS - 1) / PP_ROWS, n), PP_THREADS, 0, s>>>(G, stats, pg, R, eps, pl.g.TW,
-                                                                                         pl.g.hl, runs, strips);
+    gf_prepass_kernel<<<dim3(nbx, (rows + PP_ROWS - 1) / PP_ROWS, n), PP_THREADS, 0, s>>>(
+        G, stats, pg, R, eps, pl.g.TW, pl.g.hl, runs, strips, keys, key_init(p));
     c->launches++;
     CK(cudaGetLastError());
   }
@@ -420,13 +428,6 @@ static int fill_keys(gsm_ctx* c, i64* keys, size_t npx, i64 v, cudaStream_t s) {
   return GSM_OK;
 }
 
-static i64 key_init(const gsm_params* p) {
-  if (p->mode == GSM_MODE_SAD) {
-    const int w = 2 * p->radius + 1;
-    return ((i64)(50 * w * w) << 8);  // BlockMatching.cpp:157-158: min = 50 * dNum, dm = -256 -> (uchar)0
-  }
-  return (i64)0x7fffffffffffff00LL;  // +inf cost, d = 0
-}
 
 static int median_launch(gsm_ctx* c, const u8* src, u8* dst, int n, int rows, int cols, int m, cudaStream_t s) {
   dim3 grid((cols + MED_TX - 1) / MED_TX, (rows + MED_TY - 1) / MED_TY, n);
@@ -458,7 +459,8 @@ static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int c
     if ((rc = pack_planes(c, pg, n, Rtight, Gp, 0, s, mR, mR ? mR + mpx : nullptr))) return rc;
     if ((rc = pack_planes(c, pg, n, Ltight, Op, 1, s, mL, mL ? mL + mpx : nullptr))) return rc;
   }
-  if ((rc = fill_keys(c, keys, npx, key_init(p), s))) return rc;
+  // GF: the guide pre-pass also initialises the packed-min plane (it visits every pixel anyway)
+  if (p->mode == GSM_MODE_SAD && (rc = fill_keys(c, keys, npx, key_init(p), s))) return rc;
   if (p->mode == GSM_MODE_SAD) {
     if ((rc = timing_begin(c, s))) return rc;
     if (export_ptr)

@@ -26,7 +26,7 @@ constexpr float GF_RECENTRE = 8.0f;
 // ---- fused guide pre-pass -----------------------------------------------------------------------------------
 // One kernel writes every disparity-independent plane of a frame: N, S_I, 1/(N*S_II - S_I^2 + eps*N^2),
 // mean_I - 128, 1/N, I - 128 (image pixels), the horizontal-slide coefficient word of gsm_gf3.cuh (image columns
-// and R + 1 margin columns) and the per-run local centres.  A block owns PP_TX columns (PP_HALO more on each side
+// and R + 1 margin columns) and the per-run local centres; it also initialises the frame's packed-min plane.  A block owns PP_TX columns (PP_HALO more on each side
 // feed the window sums) and marches down PP_ROWS rows: thread = column, vertical running sums of I and I^2 in
 // registers, horizontal window sums from per-warp prefix sums (shuffle scan + shared memory), one barrier per row.
 // The 16-column runs of all strips lie on one global grid (TW is a multiple of 16, every strip starts hl columns
@@ -35,7 +35,7 @@ constexpr float GF_RECENTRE = 8.0f;
 constexpr int PP_TX = 128, PP_HALO = 16, PP_THREADS = PP_TX + 2 * PP_HALO, PP_ROWS = 32;
 __global__ void __launch_bounds__(PP_THREADS)
 gf_prepass_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom pg, int R, float eps, int TW, int hl,
-                  int runs, int strips) {
+                  int runs, int strips, i64* __restrict__ keys, i64 key_init) {
   __shared__ int PW1[2][PP_THREADS], PW2[2][PP_THREADS], PIX[2][PP_THREADS];
   __shared__ float CM[2][PP_THREADS];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -107,15 +107,17 @@ gf_prepass_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeo
         const int nx = min(W - 1, x + R) - max(0, x - R) + 1;
         const int ny = min(H - 1, y + R) - max(0, y - R) + 1;
         const int N = nx * ny;
+        // N^2 var and the mean offset are formed exactly in integers and rounded once
         const long long den = (long long)N * SII - (long long)SI * SI;
-        const double dden = (double)den + (double)eps * (double)N * (double)N;
-        cmv = (float)((double)SI / N - (double)GF_CENTRE);
+        const float dden = (float)den + eps * (float)(N * N);
+        cmv = (float)(SI - (int)GF_CENTRE * N) / (float)N;
         reinterpret_cast<int*>(base + ST_N * plane_elems)[o] = N;
         reinterpret_cast<int*>(base + ST_SI * plane_elems)[o] = SI;
-        base[ST_INVDEN * plane_elems + o] = (float)(1.0 / dden);
+        base[ST_INVDEN * plane_elems + o] = 1.0f / dden;
         base[ST_CMEAN * plane_elems + o] = cmv;
         base[ST_INVN * plane_elems + o] = 1.0f / (float)N;
         base[ST_IC * plane_elems + o] = (float)pc - GF_CENTRE;
+        keys[((size_t)f * H + y) * W + x] = key_init;  // packed-min plane: +inf cost, d = 0
       }
       CM[b][tid] = cmv;
     }
