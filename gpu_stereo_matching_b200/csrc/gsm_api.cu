@@ -385,8 +385,11 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     static_assert(K == 16, "gf_prepass_kernel assumes one global grid of 16-column runs");
     const int strips = (int)pl.grid.x;
     const int nbx = (cols + R + 1 + pl.g.hl + PP_HALO + PP_TX - 1) / PP_TX;
-    gf_prepass_kernel<<<dim3(nbx, (rows + PP_ROWS - 1) / PP_ROWS, n), PP_THREADS, 0, s>>>(
-        G, stats, pg, R, eps, pl.g.TW, pl.g.hl, runs, strips, keys, key_init(p));
+    // rows per block: 32 when that already gives two blocks per SM, else fewer rows (more, shorter blocks)
+    int rpb = PP_ROWS;
+    while (rpb > 8 && (long long)nbx * ((rows + rpb - 1) / rpb) * n < 2 * 148) rpb /= 2;
+    gf_prepass_kernel<<<dim3(nbx, (rows + rpb - 1) / rpb, n), PP_THREADS, 0, s>>>(
+        G, stats, pg, R, eps, pl.g.TW, pl.g.hl, runs, strips, keys, key_init(p), rpb);
     c->launches++;
     CK(cudaGetLastError());
   }

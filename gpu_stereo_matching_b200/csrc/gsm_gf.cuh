@@ -26,35 +26,42 @@ constexpr float GF_RECENTRE = 8.0f;
 // ---- fused guide pre-pass -----------------------------------------------------------------------------------
 // One kernel writes every disparity-independent plane of a frame: N, S_I, 1/(N*S_II - S_I^2 + eps*N^2),
 // mean_I - 128, 1/N, I - 128 (image pixels), the horizontal-slide coefficient word of gsm_gf3.cuh (image columns
-// and R + 1 margin columns) and the per-run local centres; it also initialises the frame's packed-min plane.  A block owns PP_TX columns (PP_HALO more on each side
-// feed the window sums) and marches down PP_ROWS rows: thread = column, vertical running sums of I and I^2 in
-// registers, horizontal window sums from per-warp prefix sums (shuffle scan + shared memory), one barrier per row.
-// The 16-column runs of all strips lie on one global grid (TW is a multiple of 16, every strip starts hl columns
-// left of a multiple of TW), so a block's columns start on a run boundary and a run's centre is written to the
-// (strip, run) slots of the one or two strips that contain it.
-constexpr int PP_TX = 128, PP_HALO = 16, PP_THREADS = PP_TX + 2 * PP_HALO, PP_ROWS = 32;
+// and R + 1 margin columns) and the per-run local centres; it also initialises the frame's packed-min plane.
+// A block owns PP_TX columns (PP_HALO more on each side feed the window sums) and marches down PP_ROWS rows:
+// thread = 4 adjacent columns (one 32-bit load per image row, one 128-bit store per plane and row), vertical running
+// sums of I and I^2 in registers, horizontal window sums from per-warp prefix sums (in-thread prefix + one shuffle scan
+// per 4 columns + shared memory), one barrier per row.  The 16-column runs of all strips lie on one global grid (TW
+// is a multiple of 16, every strip starts hl columns left of a multiple of TW), so a block's columns start on a run
+// boundary and a run's centre is written to the (strip, run) slots of the one or two strips that contain it.
+constexpr int PP_C = 4, PP_THREADS = 96, PP_COLS = PP_THREADS * PP_C, PP_HALO = 16, PP_TX = PP_COLS - 2 * PP_HALO,
+              PP_ROWS = 32;  // rows per block of a large launch; small launches use fewer (more blocks)
+static_assert(PP_TX % 16 == 0 && PP_HALO % PP_C == 0, "tiles start on run boundaries");
 __global__ void __launch_bounds__(PP_THREADS)
 gf_prepass_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom pg, int R, float eps, int TW, int hl,
-                  int runs, int strips, i64* __restrict__ keys, i64 key_init) {
-  __shared__ int PW1[2][PP_THREADS], PW2[2][PP_THREADS], PIX[2][PP_THREADS];
-  __shared__ float CM[2][PP_THREADS];
+                  int runs, int strips, i64* __restrict__ keys, i64 key_init, int rows_per_block) {
+  __shared__ __align__(16) int PW1[2][PP_COLS], PW2[2][PP_COLS], PIX[2][PP_COLS];
+  __shared__ __align__(16) float CM[2][PP_COLS];
   const int tid = threadIdx.x, lane = tid & 31;
   const int f = blockIdx.z;
-  const int x = -hl - PP_HALO + (int)blockIdx.x * PP_TX + tid - PP_HALO;  // output threads: tid in [PP_HALO, PP_HALO + PP_TX)
-  const int yb = blockIdx.y * PP_ROWS, ye = min(pg.H, yb + PP_ROWS);
+  const int c0 = PP_C * tid;                                                   // first column of the thread in the tile
+  const int x = -hl - PP_HALO + (int)blockIdx.x * PP_TX + c0 - PP_HALO;        // its image column
+  const int yb = blockIdx.y * rows_per_block, ye = min(pg.H, yb + rows_per_block);
   const int H = pg.H, W = pg.W;
   const size_t plane_elems = pg.plane_stride;
-  const u8* col = Ip + (size_t)f * pg.plane_stride + (size_t)PADV * pg.pitch + pg.xoff + x;
+  const u8* col = Ip + (size_t)f * pg.plane_stride + (size_t)PADV * pg.pitch + pg.xoff + x;  // 4-byte aligned
   float* base = stats + (size_t)f * GF_STAT_PLANES * plane_elems;
-  const bool outp = tid >= PP_HALO && tid < PP_HALO + PP_TX;
-  const bool inimg = outp && x >= 0 && x < W;
+  const bool outp = c0 >= PP_HALO && c0 < PP_HALO + PP_TX;
+  const bool anyimg = outp && x + PP_C > 0 && x < W;
   const int cenw = (runs + 3) / 4 * 4, rps = TW / 16;
-  const bool leader = outp && (tid & 15) == 0;
+  const bool leader = outp && (c0 & 15) == 0;
   const int gb = (x + hl) >> 4;  // global run index of a leader's run (x + hl is a multiple of 16 there)
+  int nx[PP_C];
+#pragma unroll
+  for (int k = 0; k < PP_C; ++k) nx[k] = min(W - 1, x + k + R) - max(0, x + k - R) + 1;
 
   auto write_centre = [&](int y) {  // centre of row y of the leader's run, from the row's CM buffer
     if (!leader || gb < 0) return;
-    const float* cm = CM[y & 1] + tid;
+    const float* cm = CM[y & 1] + c0;
     float sum = 0.f;
     int n = 0;
     for (int j = 0; j < 16; ++j)
@@ -67,62 +74,91 @@ gf_prepass_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeo
       if (s >= 0 && s < strips && run < runs) cen[s * cenw + run] = c;
     }
   };
+  auto row4 = [&](int yy) { return *reinterpret_cast<const u32*>(col + (long long)yy * pg.pitch); };
 
-  int v1 = 0, v2 = 0;
+  int v1[PP_C], v2[PP_C];
+#pragma unroll
+  for (int k = 0; k < PP_C; ++k) v1[k] = v2[k] = 0;
   for (int yy = yb - R; yy < yb + R; ++yy) {
-    const int p = col[(long long)yy * pg.pitch];
-    v1 += p;
-    v2 += p * p;
+    const u32 p4 = row4(yy);
+#pragma unroll
+    for (int k = 0; k < PP_C; ++k) {
+      const int p = (p4 >> (8 * k)) & 0xff;
+      v1[k] += p;
+      v2[k] += p * p;
+    }
   }
-  // the three pixels of a row (entering, centre, leaving) are fetched one row ahead
-  int n_in = col[(long long)(yb + R) * pg.pitch], n_pc = col[(long long)yb * pg.pitch],
-      n_out = col[(long long)(yb - R) * pg.pitch];
+  // the three pixel groups of a row (entering, centre, leaving) are fetched one row ahead
+  u32 n_in = row4(yb + R), n_pc = row4(yb), n_out = row4(yb - R);
   for (int y = yb; y < ye; ++y) {
     const int b = y & 1;
-    const int pin = n_in, pc = n_pc, pout = n_out;
-    n_in = col[(long long)(y + 1 + R) * pg.pitch];  // rows up to H + R: inside the bottom pad
-    n_pc = col[(long long)(y + 1) * pg.pitch];
-    n_out = col[(long long)(y + 1 - R) * pg.pitch];
-    v1 += pin;  // v = column sums over rows y-R .. y+R (zero pad rows outside the image)
-    v2 += pin * pin;
-    int s1 = v1, s2 = v2;
+    const u32 pin = n_in, pc = n_pc, pout = n_out;
+    n_in = row4(y + 1 + R);  // rows up to H + R: inside the bottom pad
+    n_pc = row4(y + 1);
+    n_out = row4(y + 1 - R);
+    int a1[PP_C], a2[PP_C];  // in-thread inclusive prefix of the column sums over rows y-R .. y+R
+#pragma unroll
+    for (int k = 0; k < PP_C; ++k) {
+      const int p = (pin >> (8 * k)) & 0xff;
+      v1[k] += p;
+      v2[k] += p * p;
+      a1[k] = v1[k] + (k ? a1[k - 1] : 0);
+      a2[k] = v2[k] + (k ? a2[k - 1] : 0);
+    }
+    int s1 = a1[PP_C - 1], s2 = a2[PP_C - 1];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
       if (lane >= o) { s1 += t1; s2 += t2; }
     }
-    PW1[b][tid] = s1;
-    PW2[b][tid] = s2;
-    PIX[b][tid] = pc;
+    const int o1 = s1 - a1[PP_C - 1], o2 = s2 - a2[PP_C - 1];  // exclusive warp offsets
+    *reinterpret_cast<int4*>(&PW1[b][c0]) = make_int4(o1 + a1[0], o1 + a1[1], o1 + a1[2], o1 + a1[3]);
+    *reinterpret_cast<int4*>(&PW2[b][c0]) = make_int4(o2 + a2[0], o2 + a2[1], o2 + a2[2], o2 + a2[3]);
+    *reinterpret_cast<int4*>(&PIX[b][c0]) =
+        make_int4((int)(pc & 0xff), (int)((pc >> 8) & 0xff), (int)((pc >> 16) & 0xff), (int)(pc >> 24));
     __syncthreads();
     if (y > yb) write_centre(y - 1);
     if (outp) {
-      const int lo = tid - R - 1, hi = tid + R;  // window = (lo, hi]; it spans at most two warps
-      int SI = PW1[b][hi] - PW1[b][lo], SII = PW2[b][hi] - PW2[b][lo];
-      if ((lo >> 5) != (hi >> 5)) { SI += PW1[b][lo | 31]; SII += PW2[b][lo | 31]; }
-      const size_t o = (size_t)(PADV + y) * pg.pitch + pg.xoff + x;
-      reinterpret_cast<int*>(base + ST_COEF * plane_elems)[o] = PIX[b][tid + R] - 65536 * PIX[b][tid - R - 1];
-      float cmv = 0.f;
-      if (inimg) {
-        const int nx = min(W - 1, x + R) - max(0, x - R) + 1;
-        const int ny = min(H - 1, y + R) - max(0, y - R) + 1;
-        const int N = nx * ny;
+      const int ny = min(H - 1, y + R) - max(0, y - R) + 1;
+      int Nn[PP_C], SIv[PP_C], coef[PP_C];
+      float invden[PP_C], cmv[PP_C], invn[PP_C], ic[PP_C];
+#pragma unroll
+      for (int k = 0; k < PP_C; ++k) {
+        const int ci = c0 + k, lo = ci - R - 1, hi = ci + R;  // window = (lo, hi]; it spans at most two warps
+        int SI = PW1[b][hi] - PW1[b][lo], SII = PW2[b][hi] - PW2[b][lo];
+        if ((lo >> 7) != (hi >> 7)) { SI += PW1[b][lo | 127]; SII += PW2[b][lo | 127]; }
+        coef[k] = PIX[b][ci + R] - 65536 * PIX[b][ci - R - 1];
+        const bool in = x + k >= 0 && x + k < W;
+        const int N = nx[k] * ny;
         // N^2 var and the mean offset are formed exactly in integers and rounded once
         const long long den = (long long)N * SII - (long long)SI * SI;
         const float dden = (float)den + eps * (float)(N * N);
-        cmv = (float)(SI - (int)GF_CENTRE * N) / (float)N;
-        reinterpret_cast<int*>(base + ST_N * plane_elems)[o] = N;
-        reinterpret_cast<int*>(base + ST_SI * plane_elems)[o] = SI;
-        base[ST_INVDEN * plane_elems + o] = 1.0f / dden;
-        base[ST_CMEAN * plane_elems + o] = cmv;
-        base[ST_INVN * plane_elems + o] = 1.0f / (float)N;
-        base[ST_IC * plane_elems + o] = (float)pc - GF_CENTRE;
-        keys[((size_t)f * H + y) * W + x] = key_init;  // packed-min plane: +inf cost, d = 0
+        Nn[k] = in ? N : 0;
+        SIv[k] = in ? SI : 0;
+        invden[k] = in ? 1.0f / dden : 0.f;
+        cmv[k] = in ? (float)(SI - (int)GF_CENTRE * N) / (float)N : 0.f;
+        invn[k] = in ? 1.0f / (float)N : 0.f;
+        ic[k] = in ? (float)((pc >> (8 * k)) & 0xff) - GF_CENTRE : 0.f;
+        if (in) keys[((size_t)f * H + y) * W + x + k] = key_init;  // packed-min plane: +inf cost, d = 0
       }
-      CM[b][tid] = cmv;
+      const size_t o = (size_t)(PADV + y) * pg.pitch + pg.xoff + x;  // multiple of 4: 16-byte aligned stores
+      *reinterpret_cast<int4*>(base + ST_COEF * plane_elems + o) = make_int4(coef[0], coef[1], coef[2], coef[3]);
+      if (anyimg) {
+        *reinterpret_cast<int4*>(base + ST_N * plane_elems + o) = make_int4(Nn[0], Nn[1], Nn[2], Nn[3]);
+        *reinterpret_cast<int4*>(base + ST_SI * plane_elems + o) = make_int4(SIv[0], SIv[1], SIv[2], SIv[3]);
+        *reinterpret_cast<float4*>(base + ST_INVDEN * plane_elems + o) = make_float4(invden[0], invden[1], invden[2], invden[3]);
+        *reinterpret_cast<float4*>(base + ST_CMEAN * plane_elems + o) = make_float4(cmv[0], cmv[1], cmv[2], cmv[3]);
+        *reinterpret_cast<float4*>(base + ST_INVN * plane_elems + o) = make_float4(invn[0], invn[1], invn[2], invn[3]);
+        *reinterpret_cast<float4*>(base + ST_IC * plane_elems + o) = make_float4(ic[0], ic[1], ic[2], ic[3]);
+      }
+      *reinterpret_cast<float4*>(&CM[b][c0]) = make_float4(cmv[0], cmv[1], cmv[2], cmv[3]);
     }
-    v1 -= pout;
-    v2 -= pout * pout;
+#pragma unroll
+    for (int k = 0; k < PP_C; ++k) {
+      const int p = (pout >> (8 * k)) & 0xff;
+      v1[k] -= p;
+      v2[k] -= p * p;
+    }
   }
   __syncthreads();
   if (ye > yb) write_centre(ye - 1);
