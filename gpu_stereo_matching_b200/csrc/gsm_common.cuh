@@ -3,7 +3,8 @@
 // HBM layout ("padded plane"): every u8 image the fused kernels read lives in a plane of
 //   plane_rows = H + 2*PADV rows x pitch bytes,  image pixel (y, x) at  (PADV + y) * pitch + xoff + x.
 // The pad is zero (or right-replicated for the right-view "other" image), pitch and xoff are chosen so
-// that every thread's run of K columns starts 16-byte aligned: one LDG.128 per guide row per thread.
+// that every thread's run of K columns starts 16-byte aligned: rows move as 16-byte aligned bulk copies into shared
+// memory and are read from there with 128-bit loads.
 // Zero pad rows/cols make out-of-image absolute differences vanish without per-row predicates.
 #pragma once
 #include <cstdint>
@@ -52,33 +53,6 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 __device__ __forceinline__ int sortable_i32(float f) {
   int b = __float_as_int(f);
   return b ^ ((b >> 31) & 0x7fffffff);
-}
-__device__ __forceinline__ float unsortable_f32(int s) {
-  return __int_as_float(s ^ ((s >> 31) & 0x7fffffff));
-}
-
-// K bytes from a 16/8-byte aligned address
-template <int K>
-__device__ __forceinline__ void load_aligned(const u8* p, u32 (&w)[K / 4]) {
-  if constexpr (K == 16) {
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-  } else {
-    static_assert(K == 8, "K must be 8 or 16");
-    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-    w[0] = v.x; w[1] = v.y;
-  }
-}
-
-// K bytes from an arbitrary byte address: pa = address rounded down to 4, sel = PRMT selector for the
-// byte misalignment (0x3210 + 0x1111 * (addr & 3)); the misalignment is row-independent (pitch % 16 == 0).
-template <int K>
-__device__ __forceinline__ void load_unaligned(const u32* pa, u32 sel, u32 (&w)[K / 4]) {
-  u32 t[K / 4 + 1];
-#pragma unroll
-  for (int i = 0; i <= K / 4; ++i) t[i] = __ldg(pa + i);
-#pragma unroll
-  for (int i = 0; i < K / 4; ++i) w[i] = __byte_perm(t[i], t[i + 1], sel);
 }
 
 // acc + a.lo16 * b.byte0 + a.hi16 * b.byte1   (IDP.2A, signed 16-bit x unsigned 8-bit)
