@@ -889,3 +889,15 @@ extern "C" int gsm_measure_alu_peak(gsm_ctx* c, double* lane_ops_per_s) {
   *lane_ops_per_s = (double)grid * 256 * iters * 8 * 2 / (best * 1e-3);
   return GSM_OK;
 }
+
+#ifdef GSM_GF_PROFILE
+// dev builds only (make EXTRA=-DGSM_GF_PROFILE): read / reset the per-phase cycle counters of gf3_wta_kernel
+extern "C" int gsm_debug_gf_prof(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, gsm::g_gf_prof, sizeof(unsigned long long) * 16 * 9);
+  if (reset) {
+    unsigned long long z[16 * 9] = {0};
+    cudaMemcpyToSymbol(gsm::g_gf_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

@@ -114,6 +114,10 @@ __device__ __forceinline__ void gf3_init_sums(const u32 (&g)[WW], const u32 (&p)
   hip = (int)sip;
 }
 
+#ifdef GSM_GF_PROFILE
+__device__ unsigned long long g_gf_prof[16][9];  // [run][phase] cycles, summed over all CTAs of a launch
+#endif
+
 template <int R, int K, int RUNS, int LPR, bool EXPORT>
 __global__ void __launch_bounds__(RUNS * LPR, GSM_GF_MINB)
 gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float* __restrict__ stats,
@@ -232,12 +236,20 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   }
 
   // ================ part A of row `it` (input stage s): stage 1, (a, b), publish (V_A, V_B)
+#ifdef GSM_GF_PROFILE  // per-phase clock() shares of a march step (tools/phase_prof.py); not part of the product build
+  unsigned pacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned plast = (unsigned)clock();
+#define GSM_PH(i) { asm volatile("" ::: "memory"); const unsigned now_ = (unsigned)clock(); pacc[i] += now_ - plast; plast = now_; }
+#else
+#define GSM_PH(i)
+#endif
   auto part_a = [&](int it, int s, u32 sphase) {
     const int t = t_begin + it;
     mbar_wait(bar0 + 8 * s, sphase);
     const u8* stg = stage_base + (size_t)s * sg.bytes;
     const int t2 = t - 2 * R - 1;
 
+    GSM_PH(0)  // stage mbarrier wait
     if (need_ab) {
       // ---------------- stage 1: horizontal window sums of the three rows, folded into the vertical sums
       u32 pn[WW], pm[WW], po[WW];
@@ -276,6 +288,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
 #pragma unroll
         for (int i = 0; i < WW; ++i) po[i] = 0u;
       }
+      GSM_PH(1)  // AD windows + initial sums
       const int* hcn = reinterpret_cast<const int*>(stg + sg.off_HC) + run * K;
       const int* hcm = hcn + TWt;
       const int* hco = hcm + TWt;
@@ -310,6 +323,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
         }
       }
 
+      GSM_PH(2)  // horizontal slides
       // ---------------- (a, b) of the lead and trail rows folded into the stage-2 vertical sums
       {
         const float target = reinterpret_cast<const float*>(stg + sg.off_CEN)[run];
@@ -356,6 +370,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       }
     }
 
+    GSM_PH(3)  // (a, b)
     const int y = t - R;
     u32* xbuf = xb + (size_t)(it & 1) * 2 * planew;  // double-buffered (V_A, V_B) planes: one barrier per row
     float* ccbuf = ccs + (it & 1) * 48;
@@ -364,6 +379,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       exch_store<K, HL4>(xbuf + planew, reinterpret_cast<u32(&)[K]>(VB));
       if (lane == 0) ccbuf[run] = cc;
     }
+    GSM_PH(4)  // exchange stores
   };
 
   // ================ part B of row `it` (after the barrier that publishes it): stage 2 horizontal, q, WTA
@@ -382,6 +398,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       const float dr = run + 1 < runs ? cc - ccbuf[run + 1] : 0.f;
       slide_ab<R, K, HL4>(winA, winB, dl, dr, A, B);
     }
+    GSM_PH(6)  // exchange loads + stage-2 slide
     // The WTA compares N(x)*q_d(x): N > 0 does not depend on d, so the argmin is that of q (the packed-min plane
     // therefore carries the un-normalised cost); only the exported slices are divided by N.
     const float* icy = reinterpret_cast<const float*>(stg + sg.off_ICY) + run * K;
@@ -406,6 +423,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
         }
       }
     }
+    GSM_PH(7)  // q
     int key[K];
 #pragma unroll
     for (int c = 0; c < K; ++c) key[c] = sortable_i32(qn[c]);
@@ -443,6 +461,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
       const i64 k64 = (i64)(((unsigned long long)(u32)(mine & ~31) << 32) | (u32)(d0 + (mine & 31)));
       atomicMin(keys + ((size_t)frame * H + y) * W + x0 + lane, k64);
     }
+    GSM_PH(8)  // keys + WTA
   };
 
   const int T = t_end - t_begin;
@@ -453,9 +472,15 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
     __syncthreads();
     // every thread has now finished row it-1 completely: its stage is refilled for row it + GF3_NST - 1
     if (producer && it + GF3_NST - 1 < T) issue(t_begin + it + GF3_NST - 1, s == 0 ? GF3_NST - 1 : s - 1);
+    GSM_PH(5)  // row barrier (+ bulk-copy issue in the producer warp)
     part_b(it, s);
     if (++s == GF3_NST) { s = 0; sphase ^= 1u; }
   }
+#ifdef GSM_GF_PROFILE
+  if (lane == 0)
+    for (int i = 0; i < 9; ++i) atomicAdd(&g_gf_prof[run][i], (unsigned long long)pacc[i]);
+#endif
+#undef GSM_PH
 }
 
 }  // namespace gsm

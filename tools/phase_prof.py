@@ -1,4 +1,10 @@
-"""Per-phase cycle shares of gf3_wta_kernel from a -DPH instrumented build (dev tool, see git history of gsm_gf3.cuh)."""
+"""Per-phase cycle shares of gf3_wta_kernel (dev tool).
+
+Needs the instrumented build of the library:
+    make -C gpu_stereo_matching_b200/csrc OUT=../../tools/variants/libgsm_prof.so EXTRA=-DGSM_GF_PROFILE
+    python tools/phase_prof.py tools/variants/libgsm_prof.so
+GSM_GF_PROFILE adds clock() reads between the phases of a march step and a debug export; the product build has
+neither (identical SASS with the macro off)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
