@@ -4,6 +4,7 @@
                      `make -C oracle`)
   _ref/libref.so  -- the reference's own BlockMatching.cpp + ctmf.c compiled UNMODIFIED from
                      /root/reference (built in the dev container, travels as a prebuilt .so)
+  _ref/libstref.so -- likewise STMatching/StereoHelper.cpp (float WTA, right-view cost volume)
 
 Every wrapper cites the reference file:line its C counterpart follows (paths relative to
 /root/reference).
@@ -91,6 +92,46 @@ def ref() -> C.CDLL:
         R.ref_median.restype = None
         _ref = R
     return _ref
+
+
+_stref = None
+
+
+def have_stref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libstref.so"))
+
+
+def stref() -> C.CDLL:
+    """The reference's own STMatching/StereoHelper.cpp, compiled unmodified (oracle/Makefile target
+    _ref/libstref.so): ref_wta_float (StereoHelper.cpp:131-154), ref_right_from_left (:156-180)."""
+    global _stref
+    if _stref is None:
+        S = C.CDLL(os.path.join(_HERE, "_ref", "libstref.so"))
+        f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+        S.ref_wta_float.argtypes = [f32, C.c_int, C.c_int, C.c_int, _u8p]
+        S.ref_wta_float.restype = None
+        S.ref_right_from_left.argtypes = [f32, C.c_int, C.c_int, C.c_int, f32]
+        S.ref_right_from_left.restype = None
+        _stref = S
+    return _stref
+
+
+def ref_wta_float(vol) -> np.ndarray:
+    """GetDisparity_WTA of the compiled reference on a float32 volume [H][W][D]."""
+    vol = np.ascontiguousarray(vol, np.float32)
+    h, w, d = vol.shape
+    out = np.empty((h, w), np.uint8)
+    stref().ref_wta_float(vol, w, h, d, out)
+    return out
+
+
+def ref_right_from_left(vol) -> np.ndarray:
+    """GetRightMatchingCostFromLeft of the compiled reference on a float32 volume [H][W][D]."""
+    vol = np.ascontiguousarray(vol, np.float32)
+    h, w, d = vol.shape
+    out = np.empty_like(vol)
+    stref().ref_right_from_left(vol, w, h, d, out)
+    return out
 
 
 @contextlib.contextmanager

@@ -11,8 +11,12 @@
  *     Art pairs and on seeded random inputs, and against the committed digests in
  *     tests/golden/ (generated from oracle/_ref).
  *   - orc_median : PINNED against the reference's ctmf.c compiled unmodified.
- *   - orc_lr_check / right-view costs / float WTA : restatement of STMatching code that
- *     cannot be compiled here (needs OpenCV); pinned only by its 12-line source.
+ *   - right-view costs (orc_ad_slice view 1) and the float WTA rule of orc_gf_wta : PINNED against the
+ *     reference's STMatching/StereoHelper.cpp compiled unmodified (oracle/_ref/libstref.so, a small
+ *     cv::Mat stand-in under oracle/shim_st/).
+ *   - orc_lr_check : restatement of a loop inside stereo_disparity_iteration
+ *     (StereoDisparity.cpp:136-147), which cannot be called in isolation; pinned only by a
+ *     literal-loop test.
  *   - orc_gf_* (guided filter) : PARITY UNPINNED.  The reference contains no guided filter;
  *     this file is the de-facto definition ("GF-v1").
  *

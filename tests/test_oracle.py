@@ -199,3 +199,31 @@ def test_remap_and_cvtcolor_restatements(orc):
     s = (s + (f(.114) * rgb[..., 2].astype(f)).astype(f)).astype(f)
     assert np.array_equal(orc.cvtcolor(rgb, truncate=True), s.astype(np.uint8))
     assert np.array_equal(orc.cvtcolor(rgb, truncate=False), np.clip(np.rint(s), 0, 255).astype(np.uint8))
+
+
+def test_right_view_and_float_wta_against_compiled_stmatching(orc):
+    """SURVEY 8a rows a6 / a7 pinned on the reference's own code: STMatching/StereoHelper.cpp compiled unmodified
+    (oracle/_ref/libstref.so).  (i) GetRightMatchingCostFromLeft on the left AD volume == the oracle's right-view AD
+    slices; (ii) GetDisparity_WTA == "strict <, first minimum wins" on volumes with exact ties, which is the rule
+    orc_gf_wta applies to its own costs."""
+    if not orc.have_stref():
+        pytest.skip("oracle/_ref/libstref.so not built (reference tree absent)")
+    rng = np.random.default_rng(11)
+    # incl. D == w (every column is an edge column); the reference indexes out of bounds for D > w (x = w - D < 0)
+    for (h, w, D) in ((7, 19, 9), (5, 40, 33), (9, 12, 12), (4, 16, 15)):
+        L = rng.integers(0, 256, (h, w), dtype=np.uint8); R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        left = np.stack([orc.ad_slice(L, R, d, 0) for d in range(D)], axis=-1).astype(np.float32)   # [y][x][d]
+        right = orc.ref_right_from_left(left)
+        ours = np.stack([orc.ad_slice(L, R, d, 1) for d in range(D)], axis=-1).astype(np.float32)
+        assert np.array_equal(right, ours), (h, w, D)
+        vol = rng.integers(0, 4, (h, w, D)).astype(np.float32) * 0.25 - 0.25     # many exact ties, negative values
+        assert np.array_equal(orc.ref_wta_float(vol), np.argmin(vol, axis=-1).astype(np.uint8))
+    # the same rule on real guided-filter costs: the oracle's WTA picks what the reference's WTA picks
+    Lr = rng.integers(0, 256, (24, 40), dtype=np.uint8); Rr = np.roll(Lr, -3, axis=1)
+    q = orc.gf_cost_slices(Lr, Rr, 3, 0, 12)                      # float64 [D][H][W]
+    d_or = orc.gf_wta(Lr, Rr, 3, 12)
+    d_ref = orc.ref_wta_float(np.ascontiguousarray(np.moveaxis(q, 0, -1)).astype(np.float32))
+    diff = d_or != d_ref                                           # may differ only where the float32 cast creates a tie
+    q32 = np.moveaxis(q, 0, -1).astype(np.float32)
+    ys, xs = np.nonzero(diff)
+    assert all(q32[y, x, d_or[y, x]] == q32[y, x, d_ref[y, x]] for y, x in zip(ys, xs))
