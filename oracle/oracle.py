@@ -5,6 +5,7 @@
   _ref/libref.so  -- the reference's own BlockMatching.cpp + ctmf.c compiled UNMODIFIED from
                      /root/reference (built in the dev container, travels as a prebuilt .so)
   _ref/libstref.so -- likewise STMatching/StereoHelper.cpp (float WTA, right-view cost volume)
+  _ref/libutilref.so -- likewise BlockMatching/Utility.cpp (CPU_Remap, cvtColor_cpu)
 
 Every wrapper cites the reference file:line its C counterpart follows (paths relative to
 /root/reference).
@@ -114,6 +115,45 @@ def stref() -> C.CDLL:
         S.ref_right_from_left.restype = None
         _stref = S
     return _stref
+
+
+_utilref = None
+
+
+def have_utilref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libutilref.so"))
+
+
+def utilref() -> C.CDLL:
+    """The reference's own BlockMatching/Utility.cpp, compiled unmodified (oracle/Makefile target
+    _ref/libutilref.so): ref_cpu_remap (Utility.cpp:236-264), ref_cvtcolor_cpu (:289-298)."""
+    global _utilref
+    if _utilref is None:
+        U = C.CDLL(os.path.join(_HERE, "_ref", "libutilref.so"))
+        f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+        U.ref_cpu_remap.argtypes = [_u8p, C.c_int, C.c_int, f32, f32, _u8p]
+        U.ref_cpu_remap.restype = None
+        U.ref_cvtcolor_cpu.argtypes = [_u8p, _u8p, C.c_int, C.c_int]
+        U.ref_cvtcolor_cpu.restype = None
+        _utilref = U
+    return _utilref
+
+
+def ref_cpu_remap(src, mapx, mapy) -> np.ndarray:
+    """CPU_Remap of the compiled reference (Utility.cpp:236-246)."""
+    src = _u8(src)
+    out = np.empty_like(src)
+    utilref().ref_cpu_remap(src, src.shape[0], src.shape[1], np.ascontiguousarray(mapx, np.float32),
+                            np.ascontiguousarray(mapy, np.float32), out)
+    return out
+
+
+def ref_cvtcolor_cpu(src3) -> np.ndarray:
+    """cvtColor_cpu of the compiled reference (Utility.cpp:289-298)."""
+    src3 = np.ascontiguousarray(src3, np.uint8)
+    out = np.empty(src3.shape[:2], np.uint8)
+    utilref().ref_cvtcolor_cpu(src3.reshape(-1), out, src3.shape[0], src3.shape[1])
+    return out
 
 
 def ref_wta_float(vol) -> np.ndarray:

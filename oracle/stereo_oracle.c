@@ -17,6 +17,8 @@
  *   - orc_lr_check : restatement of a loop inside stereo_disparity_iteration
  *     (StereoDisparity.cpp:136-147), which cannot be called in isolation; pinned only by a
  *     literal-loop test.
+ *   - orc_remap / orc_cvtcolor(truncate) : PINNED against the reference's BlockMatching/Utility.cpp compiled
+ *     unmodified (oracle/_ref/libutilref.so, stand-in under oracle/shim_util/).
  *   - orc_gf_* (guided filter) : PARITY UNPINNED.  The reference contains no guided filter;
  *     this file is the de-facto definition ("GF-v1").
  *

@@ -227,3 +227,26 @@ def test_right_view_and_float_wta_against_compiled_stmatching(orc):
     q32 = np.moveaxis(q, 0, -1).astype(np.float32)
     ys, xs = np.nonzero(diff)
     assert all(q32[y, x, d_or[y, x]] == q32[y, x, d_ref[y, x]] for y, x in zip(ys, xs))
+
+
+def test_remap_and_cvtcolor_against_compiled_utility(orc):
+    """SURVEY 8f rows 1 / 2 pinned on the reference's own code: BlockMatching/Utility.cpp compiled unmodified
+    (oracle/_ref/libutilref.so).  CPU_Remap (incl. its (ycoo, xcoo) argument order, the out-of-image rule and the
+    rounding of saturate_cast) and cvtColor_cpu (truncation) == the oracle's restatements, bit for bit."""
+    if not orc.have_utilref():
+        pytest.skip("oracle/_ref/libutilref.so not built (reference tree absent)")
+    rng = np.random.default_rng(17)
+    for (h, w) in ((37, 53), (200, 320), (5, 4)):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        mx = (rng.random((h, w), dtype=np.float32) * (w + 6) - 3).astype(np.float32)
+        my = (rng.random((h, w), dtype=np.float32) * (h + 6) - 3).astype(np.float32)
+        # exact integers and .5 offsets exercise the borders (x2 >= rows -> 0) and the ties of the rounding
+        mx.flat[::7] = np.round(mx.flat[::7]); my.flat[::5] = np.round(my.flat[::5]) + 0.5
+        assert np.array_equal(orc.ref_cpu_remap(img, mx, my), orc.remap(img, mx, my)), (h, w)
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(orc.ref_cvtcolor_cpu(rgb), orc.cvtcolor(rgb, truncate=True)), (h, w)
+    # identity maps reproduce the image except the last row / column (x2 >= rows, y2 >= cols -> 0): a reference quirk
+    img = rng.integers(0, 256, (9, 11), dtype=np.uint8)
+    yy, xx = np.mgrid[0:9, 0:11].astype(np.float32)
+    out = orc.ref_cpu_remap(img, xx, yy)
+    assert np.array_equal(out[:-1, :-1], img[:-1, :-1]) and not out[-1].any() and not out[:, -1].any()
