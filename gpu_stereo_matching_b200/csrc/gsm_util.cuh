@@ -213,13 +213,21 @@ __global__ void remap_kernel(const u8* __restrict__ src, const float* __restrict
   dst[i] = remap_sample(src, rows, cols, mapx[i], mapy[i]);
 }
 
-// kernalCvtColor (Device.cu:136-143) / cvtColor_cpu (Utility.cpp:289-298)
+// kernalCvtColor (Device.cu:136-143) / cvtColor_cpu (Utility.cpp:289-298).  The two reference functions do not
+// round alike: the host function is compiled without contraction (three products, two sums, truncation), while nvcc
+// contracts the kernel's expression into FMUL(.587 c1), FFMA(.299 c0), FFMA(.114 c2) before cvt.rni.sat -- checked
+// on the reference's own kernel compiled for sm_100a (profiles/r01_reference_gpu_on_b200.txt).
 __global__ void cvtcolor_kernel(const u8* __restrict__ src3, u8* __restrict__ dst, size_t n, int truncate) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float c0 = src3[3 * i], c1 = src3[3 * i + 1], c2 = src3[3 * i + 2];
-  const float sum = __fadd_rn(__fadd_rn(__fmul_rn(.299f, c0), __fmul_rn(.587f, c1)), __fmul_rn(.114f, c2));
-  dst[i] = truncate ? (u8)sum : float2uchar_rni_sat(sum);
+  if (truncate) {
+    const float sum = __fadd_rn(__fadd_rn(__fmul_rn(.299f, c0), __fmul_rn(.587f, c1)), __fmul_rn(.114f, c2));
+    dst[i] = (u8)sum;
+  } else {
+    const float sum = __fmaf_rn(.114f, c2, __fmaf_rn(.299f, c0, __fmul_rn(.587f, c1)));
+    dst[i] = float2uchar_rni_sat(sum);
+  }
 }
 
 // FFMA + IADD3 issue-peak probe (roofline denominator for the ALU-bound fused kernels)

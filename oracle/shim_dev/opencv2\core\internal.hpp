@@ -1,0 +1,1 @@
+#include "cvshim_dev.hpp"

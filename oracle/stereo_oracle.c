@@ -418,12 +418,20 @@ void orc_remap(const u8* src, const float* mapx, const float* mapy, int rows, in
 
 /* SURVEY 8(f)-2  3-channel -> gray, weights .299/.587/.114 applied to channels 0/1/2 as stored
  * (the reference feeds OpenCV BGR data, Caller.cpp:106).  truncate = 1: cvtColor_cpu, Utility.cpp:289-298
- * ((uchar)channelSum); truncate = 0: kernalCvtColor, Device.cu:136-143 (round-nearest-even, saturate). */
+ * ((uchar)channelSum), host code: no contraction; truncate = 0: kernalCvtColor, Device.cu:136-143
+ * (round-nearest-even, saturate) with the contraction nvcc applies to the kernel's expression:
+ * FMUL(.587 c1), FFMA(.299 c0), FFMA(.114 c2) -- read off the SASS of the reference kernel compiled unmodified
+ * and confirmed by running it (tools/ref_gpu_compare.py). */
 void orc_cvtcolor(const u8* src3, int rows, int cols, int truncate, u8* dst) {
   size_t n = (size_t)rows * cols;
   for (size_t i = 0; i < n; ++i) {
-    float sum = .299f * (float)src3[3 * i] + .587f * (float)src3[3 * i + 1] + .114f * (float)src3[3 * i + 2];
-    dst[i] = truncate ? (u8)sum : sat_rne_u8(sum);
+    const float c0 = (float)src3[3 * i], c1 = (float)src3[3 * i + 1], c2 = (float)src3[3 * i + 2];
+    if (truncate) {
+      float sum = .299f * c0 + .587f * c1 + .114f * c2;
+      dst[i] = (u8)sum;
+    } else {
+      dst[i] = sat_rne_u8(fmaf(.114f, c2, fmaf(.299f, c0, .587f * c1)));
+    }
   }
 }
 

@@ -198,7 +198,13 @@ def test_remap_and_cvtcolor_restatements(orc):
     s = ((f(.299) * rgb[..., 0].astype(f)).astype(f) + (f(.587) * rgb[..., 1].astype(f)).astype(f)).astype(f)
     s = (s + (f(.114) * rgb[..., 2].astype(f)).astype(f)).astype(f)
     assert np.array_equal(orc.cvtcolor(rgb, truncate=True), s.astype(np.uint8))
-    assert np.array_equal(orc.cvtcolor(rgb, truncate=False), np.clip(np.rint(s), 0, 255).astype(np.uint8))
+    # the GPU kernel's expression is contracted by nvcc: fma(.114, c2, fma(.299, c0, .587 * c1)); float64 holds the
+    # products and sums of these operands exactly, so one rounding to float32 emulates each fma
+    d = np.float64
+    t = (f(.587) * rgb[..., 1].astype(f)).astype(f)
+    t = (d(f(.299)) * rgb[..., 0].astype(d) + t.astype(d)).astype(f)
+    t = (d(f(.114)) * rgb[..., 2].astype(d) + t.astype(d)).astype(f)
+    assert np.array_equal(orc.cvtcolor(rgb, truncate=False), np.clip(np.rint(t), 0, 255).astype(np.uint8))
 
 
 def test_right_view_and_float_wta_against_compiled_stmatching(orc):
