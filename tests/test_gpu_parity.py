@@ -519,3 +519,41 @@ def test_peer_memory_combine_two_gpus(tmp_path):
     out = str(tmp_path / "p2p")
     mp.spawn(_p2p_worker, args=(2, 29733, out), nprocs=2, join=True)
     assert [open(out + f".{r}").read() for r in range(2)] == ["ok", "ok"]
+
+
+def test_reference_gpu_code_agrees(ctx, fx, orc):
+    """The reference's OWN CUDA code -- BlockMatching/Device.cu compiled unmodified for sm_100a into
+    oracle/_ref/libdevref.so (`make -C oracle devref`, test infrastructure) -- run on this GPU: blockMatching_gpu,
+    kernalRemap and kernalCvtColor give what libgsm.so gives, bit for bit, on the reference's demo input (Art 320x256,
+    the only size its launch geometry covers)."""
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libdevref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libdevref.so not built (make -C oracle devref needs the reference tree)")
+    u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+    f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    dev = C.CDLL(path)
+    dev.devref_block_matching.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+    dev.devref_remap.argtypes = [u8p, u8p, f32p, f32p, f32p, f32p, C.c_int, C.c_int, u8p]
+    dev.devref_cvtcolor.argtypes = [u8p, u8p, C.c_int, C.c_int]
+    L, R = np.ascontiguousarray(fx["ArtDemo_L"]), np.ascontiguousarray(fx["ArtDemo_R"])
+    h, w = L.shape
+    assert (h, w) == (256, 320)
+    ref = np.empty_like(L)
+    with orc.quiet_stdout():  # the reference prints its phase timings
+        assert dev.devref_block_matching(L, R, h, w, 5, 64, ref) == 0
+    assert np.array_equal(ctx.block_matching(L, R, 5, 64), ref)
+    rng = np.random.default_rng(3)
+    hh, ww = 200, 320
+    img = rng.integers(0, 256, (hh, ww), dtype=np.uint8)
+    mx = (rng.random((hh, ww), dtype=np.float32) * (ww + 6) - 3).astype(np.float32)
+    my = (rng.random((hh, ww), dtype=np.float32) * (hh + 6) - 3).astype(np.float32)
+    res = np.empty_like(img)
+    with orc.quiet_stdout():
+        assert dev.devref_remap(img, img, mx, my, mx, my, hh, ww, res) == 0
+    assert np.array_equal(ctx.remap(img, mx, my), res)
+    rgb = rng.integers(0, 256, (hh, ww, 3), dtype=np.uint8)
+    gray = np.empty((hh, ww), np.uint8)
+    with orc.quiet_stdout():
+        assert dev.devref_cvtcolor(rgb.reshape(-1), gray, hh, ww) == 0
+    assert np.array_equal(ctx.cvtcolor(rgb), gray)
