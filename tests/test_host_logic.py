@@ -149,3 +149,23 @@ def test_frame_sharding_world2_gloo(tmp_path):
     mp.spawn(_frames_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     own = np.load(out)
     assert own.tolist() == [1, 1, 1, 1, 2, 2, 2]  # every frame owned exactly once, contiguous blocks
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on host cores only (the reference's getDisp through oracle/_ref, or the port):
+    one JSON line with the contract's keys, the same metric / unit / config.workload as the B200 arm."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "MDE/s" and line["unit"] == "MDE/s" and line["value"] > 0
+    assert line["config"]["workload"].startswith("config3") and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
