@@ -152,7 +152,8 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
   cudaError_t st = cudaSuccess;
   auto A = [&](void** p, size_t bytes) {
     if (st == cudaSuccess) st = cudaMalloc(p, bytes);
-    if (st == cudaSuccess) st = cudaMemset(*p, 0, bytes);
+    // zero-fill on the context's own (non-blocking) stream: a legacy-stream cudaMemset would not be ordered with it
+    if (st == cudaSuccess) st = cudaMemsetAsync(*p, 0, bytes, c->stream);
   };
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) st = cudaErrorUnknown;
   if (cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess) st = cudaErrorUnknown;
@@ -181,6 +182,7 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
   A((void**)&c->maskD, slot_px);
   A((void**)&c->dispOut, slot_px);
   A((void**)&c->peak_buf, (size_t)prop.multiProcessorCount * 8 * 256 * sizeof(u32));
+  if (st == cudaSuccess) st = cudaStreamSynchronize(c->stream);  // every buffer is zero before the first call
   if (st != cudaSuccess) {
     int rc = fail(GSM_ERR_CUDA, "gsm_create: allocation failed: %s", cudaGetErrorString(st));
     gsm_destroy(c);
@@ -278,8 +280,13 @@ static Plan make_plan(const gsm_params* p, int n, int rows, int cols, int d_begi
     // GF: bands of at most 768 rows bound the fp32 drift of the stage-2 running sums (measured at 2160 rows in one
     // band: error grows from 2e-5 to 9e-5 top to bottom; with <= 768-row bands it stays below 3e-5)
     const int b_min = p->mode == GSM_MODE_GF ? (rows + 767) / 768 : 1;
+    // The choice depends on the FULL disparity count, not on the sub-range [d_begin, d_end) this call evaluates: the
+    // fp32 running sums restart at every band, so ranks of a disparity split must all use the band structure of the
+    // single-GPU pass for their packed minima to combine into a bit-identical map (dist.py passes an explicit
+    // row_bands tuned for the world size to every rank instead).
+    const int dchunks_full = (p->num_disp + lpr - 1) / lpr;
     for (int b = b_min; b <= 16 && (rows / b >= 32 || b == b_min); ++b) {
-      const long long ctas = (long long)strips * dchunks * n * b;
+      const long long ctas = (long long)strips * dchunks_full * n * b;
       const long long cost = ((ctas + 147) / 148) * ((rows + b - 1) / b + warm);
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; bands = b; }
     }
@@ -859,7 +866,9 @@ extern "C" int gsm_set_rectification(gsm_ctx* c, const float* mxl, const float* 
   const size_t n = (size_t)rows * cols;
   CK(cudaMalloc((void**)&c->rect_maps, 4 * n * sizeof(float)));
   const float* srcs[4] = {mxl, myl, mxr, myr};
-  for (int i = 0; i < 4; ++i) CK(cudaMemcpy(c->rect_maps + i * n, srcs[i], n * sizeof(float), cudaMemcpyHostToDevice));
+  for (int i = 0; i < 4; ++i)
+    CK(cudaMemcpyAsync(c->rect_maps + i * n, srcs[i], n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // the host maps may be freed by the caller; kernels run on other streams too
   c->rect_rows = rows;
   c->rect_cols = cols;
   return GSM_OK;

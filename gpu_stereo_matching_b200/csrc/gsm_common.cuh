@@ -30,9 +30,18 @@ struct PlaneGeom {
   size_t plane_stride; // bytes per frame
 };
 
+// Per-frame geometry of a mixed-size batch (gsm_stereo_batch_v): frame f is H x W pixels at pixel offset `off` of the
+// tight image / packed-min / disparity arrays, inside a padded plane slot laid out for the LARGEST frame of the batch.
+// A null table means every frame is pg.H x pg.W at offset f * H * W.
+struct FrameDesc {
+  int H, W;
+  long long off;
+};
+
 // One launch of a fused aggregation+WTA kernel.
 struct FusedGeom {
   PlaneGeom pg;
+  const FrameDesc* ft;  // per-frame sizes (device), or nullptr
   int D;          // total disparities (for validity)
   int d_begin;    // first disparity evaluated by blockIdx.y == 0
   int d_end;      // one past the last disparity evaluated

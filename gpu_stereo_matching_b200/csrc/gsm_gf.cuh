@@ -38,15 +38,19 @@ constexpr int PP_C = 4, PP_THREADS = 96, PP_COLS = PP_THREADS * PP_C, PP_HALO = 
 static_assert(PP_TX % 16 == 0 && PP_HALO % PP_C == 0, "tiles start on run boundaries");
 __global__ void __launch_bounds__(PP_THREADS)
 gf_prepass_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeom pg, int R, float eps, int TW, int hl,
-                  int runs, int strips, i64* __restrict__ keys, i64 key_init, int rows_per_block) {
+                  int runs, int strips, i64* __restrict__ keys, i64 key_init, int rows_per_block,
+                  const FrameDesc* __restrict__ ft) {
   __shared__ __align__(16) int PW1[2][PP_COLS], PW2[2][PP_COLS], PIX[2][PP_COLS];
   __shared__ __align__(16) float CM[2][PP_COLS];
   const int tid = threadIdx.x, lane = tid & 31;
   const int f = blockIdx.z;
   const int c0 = PP_C * tid;                                                   // first column of the thread in the tile
   const int x = -hl - PP_HALO + (int)blockIdx.x * PP_TX + c0 - PP_HALO;        // its image column
-  const int yb = blockIdx.y * rows_per_block, ye = min(pg.H, yb + rows_per_block);
-  const int H = pg.H, W = pg.W;
+  int H = pg.H, W = pg.W;
+  size_t koff = (size_t)f * H * W;
+  if (ft) { const FrameDesc fd = ft[f]; H = fd.H; W = fd.W; koff = (size_t)fd.off; }
+  const int yb = blockIdx.y * rows_per_block, ye = min(H, yb + rows_per_block);
+  if (yb >= H || x - c0 >= W + R + 1 + PP_HALO) return;  // (mixed-size batches) block outside this frame
   const size_t plane_elems = pg.plane_stride;
   const u8* col = Ip + (size_t)f * pg.plane_stride + (size_t)PADV * pg.pitch + pg.xoff + x;  // 4-byte aligned
   float* base = stats + (size_t)f * GF_STAT_PLANES * plane_elems;
@@ -139,7 +143,7 @@ gf_prepass_kernel(const u8* __restrict__ Ip, float* __restrict__ stats, PlaneGeo
         cmv[k] = in ? (float)(SI - (int)GF_CENTRE * N) / (float)N : 0.f;
         invn[k] = in ? 1.0f / (float)N : 0.f;
         ic[k] = in ? (float)((pc >> (8 * k)) & 0xff) - GF_CENTRE : 0.f;
-        if (in) keys[((size_t)f * H + y) * W + x + k] = key_init;  // packed-min plane: +inf cost, d = 0
+        if (in) keys[koff + (size_t)y * W + x + k] = key_init;  // packed-min plane: +inf cost, d = 0
       }
       const size_t o = (size_t)(PADV + y) * pg.pitch + pg.xoff + x;  // multiple of 4: 16-byte aligned stores
       *reinterpret_cast<int4*>(base + ST_COEF * plane_elems + o) = make_int4(coef[0], coef[1], coef[2], coef[3]);

@@ -47,10 +47,13 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
   const int d = g.d_begin + blockIdx.y * WARP + lane;
   const int frame = blockIdx.z / g.bands;
   const int band = blockIdx.z - frame * g.bands;
-  const int H = g.pg.H, W = g.pg.W, pitch = g.pg.pitch;
+  int H = g.pg.H, W = g.pg.W;
+  size_t koff = (size_t)frame * H * W;
+  if (g.ft) { const FrameDesc fd = g.ft[frame]; H = fd.H; W = fd.W; koff = (size_t)fd.off; }
+  const int pitch = g.pg.pitch;
   const int yb0 = band * g.band_rows;
   const int yb1 = min(H, yb0 + g.band_rows);
-  if (yb0 >= H) return;
+  if (yb0 >= H || strip * g.TW >= W) return;
 
   const int pitchw = exch_pitch_words(runs, K, HL4);
   const int TWt = runs * K;
@@ -231,7 +234,7 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
     for (int i = 0; i < 2; ++i) m[i] = (lane & 4) ? m[2 * i + 1] : m[2 * i];
     const u32 mine = (lane & 8) ? m[1] : m[0];
     if (lane < K && mine != 0xffffffffu)
-      atomicMin(keys + ((size_t)frame * H + y) * W + x0 + lane, (i64)mine);
+      atomicMin(keys + koff + (size_t)y * W + x0 + lane, (i64)mine);
   }
 }
 

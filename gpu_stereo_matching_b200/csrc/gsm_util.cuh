@@ -36,24 +36,28 @@ __device__ __forceinline__ u8 remap_sample(const u8* __restrict__ src, int rows,
 // mapx/mapy (optional, tight float [H][W]): rectification fused into the packer -- the plane receives
 // remap(src) (raw frames in, disparity out) instead of a copy of src.
 __global__ void pack_plane_kernel(const u8* __restrict__ src, u8* __restrict__ dst, PlaneGeom pg, int fill,
-                                  const float* __restrict__ mapx, const float* __restrict__ mapy) {
+                                  const float* __restrict__ mapx, const float* __restrict__ mapy,
+                                  const FrameDesc* __restrict__ ft) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;  // 4-byte group within a padded row
   const int prow = blockIdx.y;
   const int frame = blockIdx.z;
   if (q * 4 >= pg.pitch) return;
   const int y = prow - PADV;
+  int H = pg.H, W = pg.W;
+  size_t off = (size_t)frame * H * W;
+  if (ft) { const FrameDesc fd = ft[frame]; H = fd.H; W = fd.W; off = (size_t)fd.off; }
   u32 v = 0;
-  if (y >= 0 && y < pg.H) {
-    const u8* s = src + ((size_t)frame * pg.H + y) * pg.W;
+  if (y >= 0 && y < H) {
+    const u8* s = src + off + (size_t)y * W;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       int x = q * 4 + b - pg.xoff;
       u32 px = 0;
-      if (fill == 1 && x >= pg.W) x = pg.W - 1;
-      if (x >= 0 && x < pg.W) {
+      if (fill == 1 && x >= W) x = W - 1;
+      if (x >= 0 && x < W) {
         if (mapx) {
-          const size_t mi = (size_t)y * pg.W + x;
-          px = remap_sample(s - (size_t)y * pg.W, pg.H, pg.W, mapx[mi], mapy[mi]);
+          const size_t mi = (size_t)y * W + x;
+          px = remap_sample(s - (size_t)y * W, H, W, mapx[mi], mapy[mi]);
         } else {
           px = s[x];
         }
@@ -124,12 +128,15 @@ reduce_keys_p2p_kernel(PeerPlanes pp, int world, int rank, size_t begin, size_t 
 
 // STMatching/StereoDisparity.cpp:136-147.  out_disp (optional) = DL with occluded pixels zeroed.
 __global__ void lr_check_kernel(const u8* __restrict__ DL, const u8* __restrict__ DR, u8* __restrict__ occ,
-                                u8* __restrict__ mask, u8* __restrict__ out_disp, int H, int W, int n) {
+                                u8* __restrict__ mask, u8* __restrict__ out_disp, int H, int W, int n,
+                                const FrameDesc* __restrict__ ft) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int f = blockIdx.z;
-  if (x >= W) return;
-  const size_t i = ((size_t)f * H + y) * W + x;
+  size_t off = (size_t)f * H * W;
+  if (ft) { const FrameDesc fd = ft[f]; H = fd.H; W = fd.W; off = (size_t)fd.off; }
+  if (x >= W || y >= H) return;
+  const size_t i = off + (size_t)y * W + x;
   const int d = DL[i];
   u8 o;
   if (x - d >= 0) {
@@ -148,12 +155,15 @@ __global__ void lr_check_kernel(const u8* __restrict__ DL, const u8* __restrict_
 // neighbourhood served from a shared-memory tile.
 constexpr int MED_TX = 32, MED_TY = 16, MED_MAXR = 7;
 __global__ void __launch_bounds__(MED_TX* MED_TY)
-median_kernel(const u8* __restrict__ src, u8* __restrict__ dst, int H, int W, int m) {
+median_kernel(const u8* __restrict__ src, u8* __restrict__ dst, int H, int W, int m, const FrameDesc* __restrict__ ft) {
   __shared__ u8 tile[(MED_TY + 2 * MED_MAXR) * (MED_TX + 2 * MED_MAXR)];
   const int f = blockIdx.z;
+  size_t off = (size_t)f * H * W;
+  if (ft) { const FrameDesc fd = ft[f]; H = fd.H; W = fd.W; off = (size_t)fd.off; }
   const int bx = blockIdx.x * MED_TX, by = blockIdx.y * MED_TY;
+  if (bx >= W || by >= H) return;  // (mixed-size batches) tile outside this frame
   const int tw = MED_TX + 2 * m, th = MED_TY + 2 * m;
-  const u8* s = src + (size_t)f * H * W;
+  const u8* s = src + off;
   for (int i = threadIdx.y * MED_TX + threadIdx.x; i < tw * th; i += MED_TX * MED_TY) {
     const int ty = i / tw, tx = i - ty * tw;
     const int yy = min(H - 1, max(0, by + ty - m));
@@ -174,7 +184,7 @@ median_kernel(const u8* __restrict__ src, u8* __restrict__ dst, int H, int W, in
     }
     if (cnt > t) hi = mid; else lo = mid + 1;
   }
-  dst[((size_t)f * H + y) * W + x] = (u8)lo;
+  dst[off + (size_t)y * W + x] = (u8)lo;
 }
 
 // PreCal, BlockMatching/BlockMatching.cpp:89-109 (== kernalPreCal_V2, Device.cu:19-32): debug export only,

@@ -36,6 +36,30 @@ def shard_disparities(num_disp: int, world: int, rank: int, align: int = WARP) -
     return min(c0 * align, num_disp), min(c1 * align, num_disp)
 
 
+def dsplit_row_bands(rows: int, cols: int, num_disp: int, world: int, radius: int = 9, sms: int = 148,
+                     strip_out_cols: int = 160) -> int:
+    """Row bands for a disparity split over `world` ranks: the value of gsm_params.row_bands EVERY rank must pass.
+
+    The fp32 running sums of the guided-filter kernel restart at every band, so the packed minima of the ranks combine
+    into a map that is bit-identical to a single-GPU pass only if all of them (and that pass) use the same bands.  The
+    choice mirrors the library's own cost model (csrc/gsm_api.cu make_plan: waves of CTAs x rows marched per CTA incl.
+    4r warm-up rows, bands of at most 768 rows) for the number of 32-disparity chunks ONE rank evaluates, so that a
+    rank with 1/world of the disparities still fills its GPU.  Any value is correct; this one is fast."""
+    if world < 1 or rows < 1 or cols < 1 or num_disp < 1:
+        raise ValueError("bad request")
+    strips = -(-cols // strip_out_cols)
+    chunks_rank = -(-(-(-num_disp // WARP)) // world)
+    warm, b_min = 4 * radius, -(-rows // 768)
+    best, best_cost = b_min, None
+    b = b_min
+    while b <= 16 and (rows // b >= 32 or b == b_min):
+        cost = -(-(strips * chunks_rank * b) // sms) * (-(-rows // b) + warm)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = b, cost
+        b += 1
+    return max(1, min(best, rows))
+
+
 def key_init(mode: int, radius: int) -> int:
     """Initial packed word of the min plane (must be identical on every rank)."""
     if mode == 0:  # SAD: acceptance threshold 50*(2r+1)^2, d = 0  (BlockMatching.cpp:157-158)

@@ -30,19 +30,37 @@ def _gf_err(q, qref):
     return np.abs(q.astype(np.float64) - qref) / np.maximum(np.abs(qref), 1.0)
 
 
-def _disp_bar(a, b, qref=None):
-    """(fraction identical, # pixels off by more than 1).  With qref (float64 oracle costs [D][H][W]) a pixel
-    off by more than 1 is not counted when it is a genuine near-tie: the oracle's own costs of the two
-    disparities differ by less than the stated cost tolerance, so both answers are correct to within it."""
+FORGIVEN_LOG = []  # (label, pixels, identical fraction, off-by->1 un-tied, forgiven near-ties): printed at session end
+
+
+def _disp_bar(a, b, qref=None, label=""):
+    """(fraction identical, # pixels off by more than 1 that are NOT near-ties).  With qref (float64 oracle costs
+    [D][H][W]) a pixel off by more than 1 is forgiven when it is a genuine near-tie: the oracle's own costs of the two
+    disparities differ by less than twice the stated cost tolerance, so both answers are correct to within it.  The
+    NUMBER of forgiven pixels is recorded, printed and bounded: at most 1e-5 of the map (and never more than 3 on maps
+    below 300k pixels)."""
     diff = np.abs(a.astype(int) - b.astype(int))
     far = diff > 1
+    same, off, forgiven = float((diff == 0).mean()), int(far.sum()), 0
     if qref is not None and far.any():
         ys, xs = np.nonzero(far)
         qa = qref[a[ys, xs].astype(int), ys, xs]
         qb = qref[b[ys, xs].astype(int), ys, xs]
         tie = np.abs(qa - qb) <= 2 * GF_RTOL * np.maximum(np.abs(qb), 1.0)
-        return float((diff == 0).mean()), int((~tie).sum())
-    return float((diff == 0).mean()), int(far.sum())
+        off, forgiven = int((~tie).sum()), int(tie.sum())
+    FORGIVEN_LOG.append((label, int(a.size), same, off, forgiven))
+    print(f"[disp-bar] {label or 'map'}: {a.size} px, identical {same:.6f}, off>1 un-tied {off}, forgiven near-ties {forgiven}")
+    assert forgiven <= max(3, int(1e-5 * a.size)), (label, forgiven, a.size)
+    return same, off
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _forgiven_summary():
+    yield
+    tot_px = sum(x[1] for x in FORGIVEN_LOG)
+    print(f"\n[disp-bar summary] {len(FORGIVEN_LOG)} maps, {tot_px} px, forgiven near-ties {sum(x[4] for x in FORGIVEN_LOG)}, "
+          f"un-tied off>1 {sum(x[3] for x in FORGIVEN_LOG)}, worst identical fraction "
+          f"{min([x[2] for x in FORGIVEN_LOG] or [1.0]):.6f}")
 
 
 # ------------------------------------------------------------------------------------------ SAD (pinned)
@@ -158,11 +176,11 @@ def test_gf_disparity_bar_config1_2(ctx, fx, orc, name):
     L, R = fx[name + "_L"], fx[name + "_R"]
     disp, _ = ctx.stereo_batch(L, R, g.make_params("gf", 9, 64))
     qref = orc.gf_cost_slices(L, R, 9, 0, 64)
-    same, off = _disp_bar(disp, orc.gf_wta(L, R, 9, 64), qref)
+    same, off = _disp_bar(disp, orc.gf_wta(L, R, 9, 64), qref, label=f"C1/C2 {name} WTA")
     assert same >= 0.999 and off == 0, (name, same, off)
     disp, mask = ctx.stereo_batch(L, R, g.make_params("gf", 9, 64, lr_check=True, median_radius=3))
     dref, mref = orc.stereo_pipeline(L, R, mode="gf", r=9, D=64, lr=True, median_r=3)
-    same, off = _disp_bar(disp, dref)
+    same, off = _disp_bar(disp, dref, label=f"C1/C2 {name} LR+median")
     # a flipped near-tie can flip the occlusion flag, which zeroes the pixel: count those separately
     flipped = (mask != mref)
     assert same >= 0.999, (name, same)
@@ -196,7 +214,7 @@ def test_full_size_720p_properties(ctx, orc):
     # (1) result does not depend on the row-band decomposition
     for bands in (1, 3, 7):
         alt, _ = ctx.stereo_batch(L, R, g.make_params("gf", 9, 128, row_bands=bands))
-        same, off = _disp_bar(alt, full)
+        same, off = _disp_bar(alt, full, label=f"C3 720p bands={bands} vs auto")
         assert same >= 0.9999 and off == 0, (bands, same, off)
     # (2) disparity split: partial packed minima of 4 ranges combined by min == the single pass, bit for bit
     Ld, Rd = _dev(L), _dev(R)
@@ -223,14 +241,36 @@ def test_full_size_720p_properties(ctx, orc):
     Lc = L[y0 - pad:y0 + hh + pad, x0 - pad - 128:x0 + ww + pad]
     Rc = R[y0 - pad:y0 + hh + pad, x0 - pad - 128:x0 + ww + pad]
     ref = orc.gf_wta(Lc, Rc, 9, 128)[pad:pad + hh, pad + 128:pad + 128 + ww]
-    same, off = _disp_bar(full[y0:y0 + hh, x0:x0 + ww], ref)
+    same, off = _disp_bar(full[y0:y0 + hh, x0:x0 + ww], ref, label="C3 720p crop vs oracle")
     assert same >= 0.999 and off == 0, (same, off)
     # (5) SAD mode at full size: bit-exact against the oracle
     assert np.array_equal(ctx.block_matching(L, R, 5, 128), orc.sad_wta(L, R, 5, 128))
 
 
+def _pipeline_crop_check(full_d, full_m, L, R, orc, r, D, y0, x0, hh, ww, label, median_r=3):
+    """Full pipeline (WTA both views -> median -> LR) of an interior window against the float64 oracle run on a padded
+    crop: 2r (two-stage window) + median radius rows/cols of context, D more columns on both sides (the left view
+    reads R at x-d, the LR check reads DR at x-d, the right view reads L at x+d)."""
+    pad = 2 * r + median_r + 3
+    H, W = L.shape
+    assert y0 - pad >= 0 and y0 + hh + pad <= H and x0 - pad - D >= 0 and x0 + ww + pad + D <= W
+    sl = (slice(y0 - pad, y0 + hh + pad), slice(x0 - pad - D, x0 + ww + pad + D))
+    dref, mref = orc.stereo_pipeline(L[sl], R[sl], mode="gf", r=r, D=D, lr=True, median_r=median_r)
+    win = (slice(pad, pad + hh), slice(pad + D, pad + D + ww))
+    dref, mref = dref[win], mref[win]
+    d, m = full_d[y0:y0 + hh, x0:x0 + ww], full_m[y0:y0 + hh, x0:x0 + ww]
+    flipped = m != mref  # a flipped near-tie can flip the occlusion flag, which zeroes the pixel
+    far = np.abs(d.astype(int) - dref.astype(int)) > 1
+    same = float((d == dref).mean())
+    print(f"[pipeline-crop] {label}: {d.size} px, identical {same:.6f}, occlusion flags flipped {int(flipped.sum())}, "
+          f"off>1 outside flipped {int(far[~flipped].sum())}")
+    return same, int(far[~flipped].sum()), float(flipped.mean())
+
+
 def test_full_size_1080p_lr_median(ctx, orc):
-    """BASELINE config 4 shape (1920x1080, D=192, GF r=9, LR + median): idempotence and crop check."""
+    """BASELINE config 4 shape (1920x1080, D=192, GF r=9, LR + 7x7 median): determinism, mask consistency and three
+    interior windows of the FULL pipeline against the oracle at the north_star bar (>= 99.9 % identical, none off by
+    more than 1 outside pixels whose occlusion flag flipped)."""
     L, R, _ = gdata.synthetic_pair(1080, 1920, 2000, dmax=180)
     p = g.make_params("gf", 9, 192, lr_check=True, median_radius=3)
     d1, m1 = ctx.stereo_batch(L, R, p)
@@ -238,12 +278,138 @@ def test_full_size_1080p_lr_median(ctx, orc):
     assert np.array_equal(d1, d2) and np.array_equal(m1, m2)  # deterministic (atomicMin on packed words)
     assert set(np.unique(m1)) <= {0, 1}
     assert np.all(d1[m1 == 0] == 0)  # occluded pixels are zeroed
-    y0, x0, hh, ww, pad = 500, 900, 48, 80, 24
-    sl = (slice(y0 - pad, y0 + hh + pad), slice(x0 - pad - 192, x0 + ww + pad + 192))
-    dref, mref = orc.stereo_pipeline(L[sl], R[sl], mode="gf", r=9, D=192, lr=True, median_r=3)
-    ref = dref[pad:pad + hh, pad + 192:pad + 192 + ww]
-    same, off = _disp_bar(d1[y0:y0 + hh, x0:x0 + ww], ref)
-    assert same >= 0.995, same
+    tot_same, tot_px = 0.0, 0
+    for (y0, x0, hh, ww) in [(500, 900, 64, 128), (40, 300, 64, 128), (960, 1500, 64, 128)]:
+        same, off, flipped = _pipeline_crop_check(d1, m1, L, R, orc, 9, 192, y0, x0, hh, ww, f"C4 1080p window ({y0},{x0})")
+        assert off == 0, (y0, x0, off)
+        assert flipped <= 1e-3, (y0, x0, flipped)
+        tot_same += same * hh * ww
+        tot_px += hh * ww
+    assert tot_same / tot_px >= 0.999, tot_same / tot_px
+    # the left-view WTA alone (no post-filters), with the oracle's costs to judge pixels off by more than 1
+    y0, x0, hh, ww, pad = 700, 1000, 64, 128, 18
+    sl = (slice(y0 - pad, y0 + hh + pad), slice(x0 - pad - 192, x0 + ww + pad))
+    dw, _ = ctx.stereo_batch(L, R, g.make_params("gf", 9, 192))
+    ref = orc.gf_wta(L[sl], R[sl], 9, 192)[pad:pad + hh, pad + 192:pad + 192 + ww]
+    qref = orc.gf_cost_slices(L[sl], R[sl], 9, 0, 192)[:, pad:pad + hh, pad + 192:pad + 192 + ww]
+    same, off = _disp_bar(dw[y0:y0 + hh, x0:x0 + ww], ref, qref, label="C4 1080p WTA window")
+    assert same >= 0.999 and off == 0, (same, off)
+
+
+# ------------------------------------------------------------------------------------------ config 5 (3840x2160x256)
+@pytest.fixture(scope="module")
+def ctx4k():
+    c = g.StereoContext(2160, 3840, 256, 1)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def pair4k():
+    L, R, _ = gdata.synthetic_pair(2160, 3840, 3000, dmax=250)
+    return L, R
+
+
+def _crop4k(L, R, y0, x0, hh, ww, D=256, pad=18):
+    """Window [y0, y0+hh) x [x0, x0+ww) with 2r rows/cols of context (clipped at the image border, where the oracle's
+    own border handling then applies) and D more columns on the left; returns the crops and the window inside them."""
+    H, W = L.shape
+    ya, yb = max(0, y0 - pad), min(H, y0 + hh + pad)
+    xa, xb = max(0, x0 - pad - D), min(W, x0 + ww + pad)
+    assert xa == 0 or x0 - xa == pad + D
+    sl = (slice(ya, yb), slice(xa, xb))
+    return np.ascontiguousarray(L[sl]), np.ascontiguousarray(R[sl]), (slice(y0 - ya, y0 - ya + hh), slice(x0 - xa, x0 - xa + ww))
+
+
+def test_config5_4k_windows_vs_oracle(ctx4k, pair4k, orc):
+    """BASELINE config 5 at full size (3840x2160, D=256, GF r=9, automatic row bands = 3 bands of 720 rows): windows at
+    the top border, across both band seams, in the middle, at the left / right image border and at the bottom border
+    against the float64 oracle (>= 99.9 % identical, no un-tied pixel off by more than 1); aggregated costs of the
+    last rows within 1e-4."""
+    L, R = pair4k
+    p = g.make_params("gf", 9, 256)
+    full, _ = ctx4k.stereo_batch(L, R, p)
+    wins = [(0, 1200, 40, 96, "top border"), (700, 2000, 40, 96, "band seam 720"), (1420, 2600, 40, 96, "band seam 1440"),
+            (1060, 1800, 40, 96, "middle"), (1500, 0, 40, 96, "left border"), (900, 3744, 40, 96, "right border"),
+            (2120, 3000, 40, 96, "bottom border")]
+    tot_same, tot_px = 0.0, 0
+    for (y0, x0, hh, ww, what) in wins:
+        Lc, Rc, win = _crop4k(L, R, y0, x0, hh, ww)
+        ref = orc.gf_wta(Lc, Rc, 9, 256)[win]
+        qref = orc.gf_cost_slices(Lc, Rc, 9, 0, 256)[(slice(None),) + win]
+        same, off = _disp_bar(full[y0:y0 + hh, x0:x0 + ww], ref, qref, label=f"C5 4K window {what}")
+        assert off == 0, (what, off)
+        tot_same += same * hh * ww
+        tot_px += hh * ww
+    assert tot_same / tot_px >= 0.999, tot_same / tot_px
+    # cost slices of the bottom rows (the end of the last 720-row band: largest accumulated fp32 drift) and of the rows
+    # just above the second band seam
+    for d0 in (0, 131, 252):
+        q = ctx4k.cost_slices(L, R, p, d0, 4)
+        for (y0, x0, hh, ww) in [(2100, 1000, 60, 128), (1400, 3000, 40, 128)]:
+            Lc, Rc, win = _crop4k(L, R, y0, x0, hh, ww)
+            qref = orc.gf_cost_slices(Lc, Rc, 9, d0, 4)[(slice(None),) + win]
+            err = _gf_err(q[:, y0:y0 + hh, x0:x0 + ww], qref)
+            assert err.max() <= GF_RTOL, (d0, y0, float(err.max()))
+        del q
+
+
+def _near_tie_by_gpu_costs(c, L, R, p, a, b):
+    """Pixels where maps a and b differ: (count, count whose two candidate costs -- exported by the same fused kernel --
+    differ by more than twice the cost tolerance)."""
+    ys, xs = np.nonzero(a != b)
+    bad = 0
+    cache = {}
+    for y, x in zip(ys, xs):
+        qs = []
+        for d in (int(a[y, x]), int(b[y, x])):
+            if d not in cache:
+                cache[d] = c.cost_slices(L, R, p, d, 1)[0]
+            qs.append(float(cache[d][y, x]))
+        bad += abs(qs[0] - qs[1]) > 2 * GF_RTOL * max(abs(qs[1]), 1.0)
+        if len(cache) > 24:
+            cache.clear()
+    return len(ys), int(bad)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_config5_4k_disparity_split_is_n_independent(ctx4k, pair4k, world):
+    """The disparity split at config 5 with 2 / 4 / 8 emulated ranks on one GPU: every rank evaluates its range with the
+    band structure of the single pass (automatic bands depend on the full D, or the explicit row_bands dist.py passes),
+    so the combined map -- through a min-reduce of the planes (what the NCCL all-reduce computes) and through
+    gsm_reduce_keys_p2p -- equals the single-GPU map BIT FOR BIT, independent of the number of ranks."""
+    import torch
+    from gpu_stereo_matching_b200.dist import dsplit_row_bands, shard_disparities
+    L, R = pair4k
+    h, w, D = 2160, 3840, 256
+    Ld, Rd = _dev(L), _dev(R)
+    npx = h * w
+    for bands in (0, dsplit_row_bands(h, w, D, world)):
+        single, _ = ctx4k.stereo_batch(L, R, g.make_params("gf", 9, D, row_bands=bands))
+        keys = []
+        for k in range(world):
+            d0, d1 = shard_disparities(D, world, k)
+            kt = torch.empty(npx, dtype=torch.int64, device="cuda")
+            ctx4k.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), kt.data_ptr(), h, w,
+                                      g.make_params("gf", 9, D, row_bands=bands, d_begin=d0, d_end=d1))
+            ctx4k.sync()
+            keys.append(kt)
+        red = (torch.stack(keys).min(dim=0).values & 0xFF).to(torch.uint8).cpu().numpy().reshape(h, w)
+        assert np.array_equal(red, single), (world, bands, int((red != single).sum()))
+        maps = [torch.full((npx,), 255, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        for k in range(world):
+            ctx4k.reduce_keys_p2p([t.data_ptr() for t in keys], [t.data_ptr() for t in maps], k, npx)
+        ctx4k.sync()
+        for k in range(world):
+            assert np.array_equal(maps[k].cpu().numpy().reshape(h, w), single), (world, bands, k)
+        del keys, maps
+    # different band structures (what a tuned N-GPU run uses vs the single-GPU default) may flip fp32 near-ties:
+    # count them and prove each one a near-tie with the costs the fused kernel itself exports
+    auto, _ = ctx4k.stereo_batch(L, R, g.make_params("gf", 9, D))
+    tuned, _ = ctx4k.stereo_batch(L, R, g.make_params("gf", 9, D, row_bands=dsplit_row_bands(h, w, D, world)))
+    n, bad = _near_tie_by_gpu_costs(ctx4k, L, R, g.make_params("gf", 9, D), auto, tuned)
+    print(f"[C5 bands] world={world}: auto vs tuned row bands differ in {n} of {npx} px, not near-ties: {bad}")
+    assert bad == 0 and n <= 1e-5 * npx, (n, bad)
 
 
 def test_errors_are_reported(ctx):
@@ -327,7 +493,8 @@ def test_disparity_subranges_and_odd_sizes(ctx, fx, orc):
     err = _gf_err(q, orc.gf_cost_slices(L, R, 6, 0, 50, eps=25.0))
     assert err.max() <= GF_RTOL_SMALL_R, float(err.max())
     d1, _ = ctx.stereo_batch(L, R, p)
-    same, off = _disp_bar(d1, orc.gf_wta(L, R, 6, 50, eps=25.0), orc.gf_cost_slices(L, R, 6, 0, 50, eps=25.0))
+    same, off = _disp_bar(d1, orc.gf_wta(L, R, 6, 50, eps=25.0), orc.gf_cost_slices(L, R, 6, 0, 50, eps=25.0),
+                          label="Laundry r=6 D=50 eps=25")
     assert same >= 0.999 and off == 0, (same, off)
     # 9 frames through a context whose batch capacity is 4 (same row-band decomposition, so bit-identical;
     # different band counts may flip fp32 near-ties, which test_full_size_720p_properties bounds)
@@ -336,7 +503,7 @@ def test_disparity_subranges_and_odd_sizes(ctx, fx, orc):
     Lb, Rb = np.stack([L] * 9), np.stack([R] * 9)
     db, _ = ctx.stereo_batch(Lb, Rb, p1)
     assert all(np.array_equal(db[i], d1b) for i in range(9))
-    same, off = _disp_bar(d1b, d1)
+    same, off = _disp_bar(d1b, d1, label="Laundry bands=1 vs auto")
     assert same >= 0.9999, same
 
 
@@ -443,6 +610,8 @@ def test_gf_degenerate_and_extreme_inputs(ctx, orc):
         ys, xs = np.nonzero(d != dref)
         qa, qb = qref[d[ys, xs].astype(int), ys, xs], qref[dref[ys, xs].astype(int), ys, xs]
         bad = np.abs(qa - qb) > 2 * GF_RTOL * np.maximum(np.abs(qb), 1.0)
+        print(f"[degenerate] {name}: {len(ys)} of {d.size} px differ from the oracle's argmin, all exact or near ties: "
+              f"{int(bad.sum()) == 0}")
         assert int(bad.sum()) == 0, (name, int(bad.sum()))
 
 
