@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 H, W, D, R_GF = 720, 1280, 128, 9
 WORKLOAD = "config3: rectified 1280x720 synthetic stereo stream, 128 disparities, guided filter r=9, no LR"
 GF_OPS_PER_DE = 28   # algorithmic lane-ops per pixel*disparity, guided-filter mode
+SAD_OPS_PER_DE = 7   # SAD mode (AD 1 + box sum 4 + WTA 2)
 HBM_BYTES_PER_PX = 3  # read L + R, write disparity
 
 
@@ -146,12 +147,22 @@ def _reference_arm(args, rank, world):
     v = de / dt / 1e6
     sample = (f"{len(bands)} bands of {band_rows}x{W} px x {D} d of a config-3 frame, one band per thread; "
               f"reference getDisp (SAD r={r_ref}, Caller.cpp:19 -- the reference has no guided filter)")
+    # the guided-filter aggregation itself has no reference implementation: our float64 oracle port (OpenMP, all cores)
+    # on a crop of the same frame, so the GF-vs-GF ratio can be read from the same line
+    gf_rows = 120
+    a, b = L[:gf_rows].copy(), R[:gf_rows].copy()
+    t0 = time.perf_counter()
+    O.gf_wta(a, b, R_GF, D)
+    gdt = time.perf_counter() - t0
+    gf_port = {"value": gf_rows * W * D / gdt / 1e6, "unit": "MDE/s", "cores": cores, "kind": "port",
+               "sample": f"oracle GF r={R_GF} float64 (OpenMP) on a {gf_rows}x{W} px x {D} d crop of a config-3 frame"}
     print(json.dumps({
         "impl": "reference", "metric": "MDE/s", "value": v, "unit": "MDE/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32", "data": "synthetic", "fps": v * 1e6 / (H * W * D),
         "config": {"workload": WORKLOAD, "reference_arm": sample},
-        "cpu_baseline": {"value": v, "unit": "MDE/s", "cores": len(bands), "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "MDE/s", "cores": len(bands), "kind": kind, "sample": sample,
+                         "gf_port": gf_port},
         "e2e": {"value": v, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -181,6 +192,195 @@ def _cpu_baseline(frames_L, frames_R):
     out["gf_port"] = {"value": rows * W * D / dt / 1e6, "unit": "MDE/s", "cores": os.cpu_count(), "kind": "port",
                       "sample": f"oracle GF r={R_GF} float64 (OpenMP) on a {rows}x{W} px x {D} d crop of frame 0"}
     return out
+
+
+def _stream_frames(gdata, n, seed0):
+    """n distinct config-3 frames (rectified_stream, seeds seed0 + i), cached in /tmp between runs."""
+    path = os.path.join("/tmp", f"gsm_bench_c3_{H}x{W}_{seed0}_{n}.npz")
+    try:
+        z = np.load(path)
+        if z["L"].shape == (n, H, W):
+            return z["L"], z["R"], bool(z["rectified"])
+    except Exception:
+        pass
+    L, R, rectified = gdata.rectified_stream(n, seed0=seed0)
+    try:
+        np.savez(path + f".{os.getpid()}.tmp.npz", L=L, R=R, rectified=np.array(rectified))
+        os.replace(path + f".{os.getpid()}.tmp.npz", path)
+    except Exception:
+        pass
+    return L, R, rectified
+
+
+def _time_device_steps(torch, stream, flush, fn, steps):
+    """Mean ms of `steps` runs of fn() on `stream`, CUDA events on that stream, L2 flushed between runs."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for a, b in evs:
+            flush.fill_(1)
+            a.record(stream)
+            fn()
+            b.record(stream)
+        stream.synchronize()
+    return float(sum(a.elapsed_time(b) for a, b in evs) / steps)
+
+
+def _sad_record(torch, ctx, g, stream, sh, flush, Ld, Rd, Dd, Lh, Rh, Dh, n, steps, alu_peak):
+    """Like-for-like with the reference arm (getDisp is SAD r=5): the bit-exact SAD kernel on the same frames --
+    device-resident value, end-to-end value through the host-buffer call, roofline at 7 lane-ops/DE."""
+    import time as _t
+    r = 5
+    p = g.make_params("sad", r, D)
+    fn = lambda: ctx.stereo_device(Ld.data_ptr(), Rd.data_ptr(), Dd.data_ptr(), 0, n, H, W, p, sh)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            fn()
+    stream.synchronize()
+    ctx.set_kernel_timing(True)
+    kms = []
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for a, b in evs:
+            flush.fill_(1)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            stream.synchronize()
+            kms.append(ctx.last_kernel_ms())
+    ctx.set_kernel_timing(False)
+    ms = float(sum(a.elapsed_time(b) for a, b in evs) / steps)
+    kernel_ms = float(np.mean(kms))
+    Ln, Rn, Dn = Lh.numpy(), Rh.numpy(), Dh.numpy()
+    for _ in range(2):
+        ctx.stereo_batch_async(Ln, Rn, p, out=Dn)
+    ctx.sync()
+    t0 = _t.perf_counter()
+    for _ in range(steps):
+        ctx.stereo_batch_async(Ln, Rn, p, out=Dn)
+    ctx.sync()
+    e2e_ms = (_t.perf_counter() - t0) / steps * 1e3
+    return {"ms": ms, "e2e_ms": e2e_ms, "kernel_ms": kernel_ms, "radius": r}
+
+
+def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
+    """BASELINE config 5 in front of the driver (N > 1): one 3840x2160 pair, 256 disparities, GF r=9, split by disparity
+    range over the ranks; packed (cost, d) planes combined over NVLink peer memory (gsm_reduce_keys_p2p), one cross-rank
+    barrier per frame in a stream of frames.  Speed-up is against the same process's single-GPU pass with ITS best
+    (automatic) row bands; the map is checked bit for bit against the single-GPU pass with the SAME row bands and
+    against the NCCL all-reduce combine."""
+    from gpu_stereo_matching_b200.dist import (PeerPlanes, dsplit_row_bands, dsplit_stereo, dsplit_stereo_p2p,
+                                              torch_stream_handle)
+    h, w, d = 2160, 3840, 256
+    path = "/tmp/gsm_bench_c5_pair.npz"
+    try:
+        z = np.load(path)
+        L, R = z["L"], z["R"]
+    except Exception:
+        L, R, _ = gdata.synthetic_pair(h, w, 3000, dmax=250)
+        if rank == 0:
+            try:
+                np.savez(path + ".tmp.npz", L=L, R=R)
+                os.replace(path + ".tmp.npz", path)
+            except Exception:
+                pass
+    Ld, Rd = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
+    ctx = g.StereoContext(h, w, d, 1, device=local_rank)
+    stream = torch.cuda.Stream()
+    sh = torch_stream_handle(stream)
+    bands = dsplit_row_bands(h, w, d, world)
+    p = g.make_params("gf", 9, d, row_bands=bands)
+    steps = max(args.steps, 10)
+
+    def partial(view, d0, d1, keys):
+        ctx.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w,
+                                g.make_params("gf", 9, d, row_bands=bands, d_begin=d0, d_end=d1), view, sh)
+
+    rec = {"workload": "config5: one synthetic 3840x2160 pair, 256 disparities, GF r=9, split by disparity range",
+           "row_bands": bands, "steps": steps}
+    planes, combine = None, "nccl all-reduce(MIN) of the int64 packed (cost,d) plane"
+    try:
+        planes = PeerPlanes(h * w, views=1, slots=2)
+        combine = ("peer memory over NVLink: reduce-scatter + finalize + all-gather of the u8 map in one kernel "
+                   "(gsm_reduce_keys_p2p), one cross-rank barrier per frame")
+    except Exception as e:  # noqa: BLE001
+        rec["peer_memory_unavailable"] = f"{type(e).__name__}: {e}"
+    kl = torch.empty(h * w, dtype=torch.int64, device="cuda")
+    Dn = torch.empty(h * w, dtype=torch.uint8, device="cuda")
+
+    def nccl_step():
+        dsplit_stereo(partial, lambda a, b: ctx.finalize_keys_device(a.data_ptr(), 0, Dn.data_ptr(), 0, h, w, p, sh),
+                      kl, None, p, world, rank)
+
+    def run(nsteps):
+        res = None
+        for i in range(nsteps):
+            if planes is not None:
+                res = dsplit_stereo_p2p(ctx, partial, planes, p, sh, final_barrier=(i == nsteps - 1))
+            else:
+                nccl_step()
+                res = Dn
+        return res
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        run(3)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        res = run(steps)
+        e1.record(stream)
+    sync_all()
+    ms_n = e0.elapsed_time(e1) / steps
+    map_n = res.clone()
+    # the same GPU alone: full disparity range, automatic bands (its best) and the split's bands (for bit-identity)
+    Dd1 = torch.empty(h * w, dtype=torch.uint8, device="cuda")
+    single = {}
+    for name, b in (("auto", 0), ("same_bands", bands)):
+        p1 = g.make_params("gf", 9, d, row_bands=b)
+        fn = lambda: ctx.stereo_device(Ld.data_ptr(), Rd.data_ptr(), Dd1.data_ptr(), 0, 1, h, w, p1, sh)
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                fn()
+            a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(5):
+                fn()
+            bb.record(stream)
+        stream.synchronize()
+        single[name] = a.elapsed_time(bb) / 5
+        if name == "auto":
+            diff_auto = int((Dd1 != map_n).sum().item())
+    identical = int(torch.equal(Dd1, map_n))
+    # the NCCL all-reduce combine must give the same map
+    with torch.cuda.stream(stream):
+        nccl_step()
+    stream.synchronize()
+    same_nccl = int(torch.equal(Dn, map_n))
+    t = torch.tensor([ms_n, single["auto"], single["same_bands"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    flags = torch.tensor([identical, same_nccl], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ms_n, ms1_auto, ms1_same = [float(x) for x in t.tolist()]
+    de = h * w * d
+    rec.update({
+        "n_gpus": world, "ms_per_step": ms_n, "value": de / (ms_n * 1e-3) / 1e6, "unit": "MDE/s", "scaling": "strong",
+        "single_gpu_ms_auto_bands": ms1_auto, "single_gpu_ms_same_bands": ms1_same,
+        "speedup_vs_single_gpu": ms1_auto / ms_n, "efficiency": ms1_auto / ms_n / world,
+        "combine": combine,
+        "map_identical_to_single_gpu_same_bands_on_all_ranks": bool(int(flags[0].item())),
+        "pixels_differing_from_single_gpu_auto_bands": diff_auto,
+        "combine_check": ("peer-memory map == all-reduce map on all ranks" if int(flags[1].item()) else
+                          "MISMATCH between the peer-memory and the all-reduce combine"),
+        "nvlink_bytes_per_rank_per_step": planes.nvlink_bytes_per_frame() if planes is not None else int(2 * h * w * 8 * (world - 1) / world),
+        "result_checksum": int(map_n.to(torch.int64).sum().item()),
+    })
+    ctx.close()
+    return rec
 
 
 def _extra_config(args, rank, world, local_rank):
@@ -239,7 +439,9 @@ def _extra_config(args, rank, world, local_rank):
         par = f"frame-batch x{world} (no collective)"
     else:
         h, w, d = 2160, 3840, 256
-        p = g.make_params("gf", 9, d, row_bands=0)
+        from gpu_stereo_matching_b200.dist import dsplit_row_bands
+        c5_bands = dsplit_row_bands(h, w, d, world)  # every rank uses the same bands: the map is N-independent
+        p = g.make_params("gf", 9, d, row_bands=c5_bands)
         L, R, _ = gdata.synthetic_pair(h, w, 3000, dmax=250)
         Ld, Rd = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
         Dd = torch.empty_like(Ld)
@@ -247,7 +449,7 @@ def _extra_config(args, rank, world, local_rank):
         ctx = g.StereoContext(h, w, d, 1, device=local_rank)
 
         def partial(view, d0, d1, keys):
-            pp = g.make_params("gf", 9, d, row_bands=0, d_begin=d0, d_end=d1)
+            pp = g.make_params("gf", 9, d, row_bands=c5_bands, d_begin=d0, d_end=d1)
             ctx.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w, pp, view, sh)
 
         def finalize(a, b):
@@ -262,7 +464,7 @@ def _extra_config(args, rank, world, local_rank):
             # cannot be set up on this box
             try:
                 from gpu_stereo_matching_b200.dist import PeerPlanes, dsplit_stereo_p2p
-                planes = PeerPlanes(h * w)
+                planes = PeerPlanes(h * w, views=1, slots=2)
                 step = lambda: dsplit_stereo_p2p(ctx, partial, planes, p, sh)
                 p2p_planes = planes
                 par = (f"disparity-split x{world}, packed (cost,d) planes combined over NVLink peer memory "
@@ -294,11 +496,12 @@ def _extra_config(args, rank, world, local_rank):
         with torch.cuda.stream(stream):
             dsplit_stereo(partial, finalize, kl, None, p, world, rank)
         stream.synchronize()
-        same = torch.tensor([int(torch.equal(p2p_planes.disp.view(-1), Dd.view(-1)))], device="cuda")
+        last = p2p_planes.disp_view((p2p_planes.frame - 1) % p2p_planes.slots, 0)
+        same = torch.tensor([int(torch.equal(last.view(-1), Dd.view(-1)))], device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         cfg_extra["combine_check"] = ("peer-memory map == all-reduce map on all ranks" if int(same.item()) == 1
                                       else "MISMATCH between the peer-memory and the all-reduce combine")
-        Dd.copy_(p2p_planes.disp.view_as(Dd))
+        Dd.copy_(last.view_as(Dd))
     if rank == 0:
         v = de_step / (ms * 1e-3) / 1e6
         print(json.dumps({"metric": "MDE/s", "value": v, "unit": "MDE/s", "n_gpus": world, "steps": args.steps,
@@ -319,6 +522,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dsplit", action="store_true", help="N > 1: skip the config-5 disparity-split record")
     ap.add_argument("--combine", default="p2p", choices=["p2p", "nccl"],
                     help="config c5, N > 1: combine the ranks' planes over peer memory (default) or with an NCCL all-reduce")
     ap.add_argument("--config", default="c3", choices=["c3", "c2", "c4", "c5"],
@@ -354,11 +558,11 @@ def main():
     n = args.frames
     # every rank owns its own block of the global stream (frame sharding, no collective on the data path)
     f0, f1 = shard_frames(n * world, world, rank)
-    uniq = 4  # distinct synthetic frames per rank, tiled to n (generation is host work outside the timed region)
-    Lu, Ru, rectified = gdata.rectified_stream(uniq, seed0=1234 + f0)
-    reps = (n + uniq - 1) // uniq
-    Lh = torch.from_numpy(np.tile(Lu, (reps, 1, 1))[:n]).pin_memory()
-    Rh = torch.from_numpy(np.tile(Ru, (reps, 1, 1))[:n]).pin_memory()
+    # n DISTINCT synthetic frames per rank (seeds 1234 + global frame index), generated once and cached under /tmp
+    # (host work outside the timed region)
+    Lu, Ru, rectified = _stream_frames(gdata, n, 1234 + f0)
+    Lh = torch.from_numpy(Lu).pin_memory()
+    Rh = torch.from_numpy(Ru).pin_memory()
     Dh = torch.empty_like(Lh).pin_memory()
     # capacity of two submissions: the host path double-buffers HALF the capacity per chunk, so a submission of n
     # frames is uploaded, computed (one launch of n frames, like the device-resident step) and downloaded as one chunk
@@ -421,12 +625,18 @@ def main():
     barrier()
     checksum = int(Dh.numpy().astype(np.uint64).sum())
     alu_peak = ctx.measure_alu_peak()
+    sad = _sad_record(torch, ctx, g, stream, sh, flush, Ld, Rd, Dd, Lh, Rh, Dh, n, args.steps, alu_peak)
+    barrier()
+    dsplit = None
+    if world > 1 and not args.no_dsplit:
+        del flush
+        dsplit = _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank)
 
     # ---- max over ranks ----------------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, kernel_ms, sad["ms"], sad["e2e_ms"], sad["kernel_ms"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = [float(x) for x in t.tolist()]
+    ms, e2e_ms, kernel_ms, sad_ms, sad_e2e_ms, sad_kernel_ms = [float(x) for x in t.tolist()]
     if rank == 0:
         peaks, peak_src = _peaks()
         value = de_step * world / (ms * 1e-3) / 1e6
@@ -448,7 +658,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32+fp32", "data": "synthetic",
             "fps": value * 1e6 / (H * W * D),
-            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": n, "rows": H, "cols": W, "num_disp": D,
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": n, "distinct_frames_per_gpu": n, "rows": H, "cols": W, "num_disp": D,
                        "mode": "gf", "radius": R_GF, "rectified_with_calib_maps": bool(rectified),
                        "parallelism": f"frame-batch x{world} (no collective)", "l2": "flushed between timed steps (256 MiB fill)",
                        "result_checksum": checksum},
@@ -471,6 +681,21 @@ def main():
                 "traffic_note": traffic_note,
             },
         }
+        sad_de_s_kernel = de_step / (sad_kernel_ms * 1e-3)
+        line["sad"] = {
+            "what": "the reference's own algorithm (getDisp: SAD r=5, bit-exact) on the same frames -- like-for-like "
+                    "with the reference arm / cpu_baseline",
+            "radius": 5, "value": de_step * world / (sad_ms * 1e-3) / 1e6, "unit": "MDE/s",
+            "fps": n * world / (sad_ms * 1e-3), "ms_per_step": sad_ms,
+            "e2e": {"value": de_step * world / (sad_e2e_ms * 1e-3) / 1e6, "unit": "MDE/s", "ms_per_step": sad_e2e_ms,
+                    "fps": n * world / (sad_e2e_ms * 1e-3)},
+            "roofline": {"bound": "alu", "kernel": "sad_wta_kernel<5,16>", "algorithmic_ops_per_de": SAD_OPS_PER_DE,
+                         "achieved": SAD_OPS_PER_DE * sad_de_s_kernel / 1e12, "peak": alu_peak / 1e12,
+                         "unit": "Tlane-op/s", "frac": SAD_OPS_PER_DE * sad_de_s_kernel / alu_peak,
+                         "kernel_ms_per_step": sad_kernel_ms},
+        }
+        if dsplit is not None:
+            line["dsplit"] = dsplit
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             with O.quiet_stdout():

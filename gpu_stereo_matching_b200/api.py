@@ -38,6 +38,26 @@ def _u8c(a, name):
     return np.ascontiguousarray(a)  # the reference requires continuous Mats (Device.cu:213-214)
 
 
+def _same_shape(ndim, **arrays):
+    """All arrays C-contiguous uint8 with `ndim` dimensions and ONE shape: the C ABI takes raw pointers plus a single
+    rows x cols, so a mismatch would read or write past the end of a host buffer instead of raising."""
+    shape = None
+    for name, a in arrays.items():
+        if a is None:
+            continue
+        if not isinstance(a, np.ndarray) or a.dtype != np.uint8:
+            raise TypeError(f"{name}: expected a uint8 numpy array (CV_8UC1)")
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"{name}: must be C-contiguous")
+        if a.ndim != ndim:
+            raise ValueError(f"{name}: expected {ndim} dimensions, got shape {a.shape}")
+        if shape is None:
+            shape = a.shape
+        elif a.shape != shape:
+            raise ValueError(f"{name}: shape {a.shape} differs from {shape}")
+    return shape
+
+
 def _ptr(a) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
 
@@ -87,10 +107,15 @@ class StereoContext:
         if L.ndim != 3 or L.shape != R.shape:
             raise ValueError("left/right must be [n, rows, cols] and the same size")
         n, rows, cols = L.shape
+        if single and out is not None and out.ndim == 2:
+            out = out[None]
+        if single and mask_out is not None and mask_out.ndim == 2:
+            mask_out = mask_out[None]
         disp = out if out is not None else np.empty_like(L)
         mask = None
         if params.lr_check:
             mask = mask_out if mask_out is not None else np.empty_like(L)
+        _same_shape(3, left=L, right=R, out=disp, mask_out=mask)
         _l.check(self._lib.gsm_stereo_batch(self._h, C.byref(params), n, _ptr(L), _ptr(R), _ptr(disp), _ptr(mask),
                                             rows, cols))
         if single and out is None:
@@ -102,15 +127,43 @@ class StereoContext:
         left/right/out(/mask_out) must be C-contiguous uint8 [n, rows, cols], page-locked for real asynchrony, and
         must stay alive until sync()."""
         L, R = left, right
-        for name, a in (("left", L), ("right", R), ("out", out)):
-            if a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"] or a.ndim != 3:
-                raise TypeError(f"{name}: C-contiguous uint8 [n, rows, cols] expected")
-        n, rows, cols = L.shape
+        n, rows, cols = _same_shape(3, left=L, right=R, out=out, mask_out=mask_out)
         _l.check(self._lib.gsm_stereo_batch_async(self._h, C.byref(params), n, _ptr(L), _ptr(R), _ptr(out),
                                                   _ptr(mask_out), rows, cols))
 
     def stereo(self, left, right, **kw):
         return self.stereo_batch(left, right, make_params(**kw))
+
+    def stereo_batch_v(self, lefts, rights, params: GsmParams):
+        """Mixed-size batch (gsm_stereo_batch_v): lists of [rows_i, cols_i] uint8 pairs -> (list of disparities, list of
+        masks | None), the whole batch as ONE launch per stage.  BASELINE config 2 (nine Middlebury sets, three sizes);
+        the separate Mats of Caller.cpp:12-19."""
+        Ls = [_u8c(a, f"lefts[{i}]") for i, a in enumerate(lefts)]
+        Rs = [_u8c(a, f"rights[{i}]") for i, a in enumerate(rights)]
+        if len(Ls) != len(Rs) or not Ls:
+            raise ValueError("lefts / rights must be non-empty lists of the same length")
+        for i, (a, b) in enumerate(zip(Ls, Rs)):
+            _same_shape(2, **{f"lefts[{i}]": a, f"rights[{i}]": b})
+        n = len(Ls)
+        disps = [np.empty_like(a) for a in Ls]
+        masks = [np.empty_like(a) for a in Ls] if params.lr_check else None
+        arr = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+        rows = (C.c_int * n)(*[a.shape[0] for a in Ls])
+        cols = (C.c_int * n)(*[a.shape[1] for a in Ls])
+        _l.check(self._lib.gsm_stereo_batch_v(self._h, C.byref(params), n, arr(Ls), arr(Rs), arr(disps),
+                                              arr(masks) if masks is not None else None, rows, cols))
+        return disps, masks
+
+    def stereo_device_v(self, left_ptr: int, right_ptr: int, disp_ptr: int, mask_ptr: int, shapes, params: GsmParams,
+                        stream: int = 0) -> None:
+        """Mixed-size batch on device buffers (gsm_stereo_device_v): shapes = [(rows_i, cols_i), ...], frames tight and
+        concatenated in every buffer."""
+        n = len(shapes)
+        rows = (C.c_int * n)(*[int(s[0]) for s in shapes])
+        cols = (C.c_int * n)(*[int(s[1]) for s in shapes])
+        _l.check(self._lib.gsm_stereo_device_v(self._h, C.byref(params), n, C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                               C.c_void_p(disp_ptr), C.c_void_p(mask_ptr or None), rows, cols,
+                                               C.c_void_p(stream or None)))
 
     def stereo_device(self, left_ptr: int, right_ptr: int, disp_ptr: int, mask_ptr: int, n: int, rows: int,
                       cols: int, params: GsmParams, stream: int = 0) -> None:
@@ -135,7 +188,13 @@ class StereoContext:
                                                     C.c_void_p(mask_ptr or None), rows, cols,
                                                     C.c_void_p(stream or None)))
 
-    # ---- cost-stage exports ------------------------------------------------------------------
+    def postfilter_device(self, disp_left_ptr, disp_right_ptr, disp_ptr, mask_ptr, rows, cols, params: GsmParams,
+                          stream=0):
+        """median on both views + LR check on device u8 maps (gsm_postfilter_device)."""
+        _l.check(self._lib.gsm_postfilter_device(self._h, C.byref(params), C.c_void_p(disp_left_ptr),
+                                                 C.c_void_p(disp_right_ptr or None), C.c_void_p(disp_ptr),
+                                                 C.c_void_p(mask_ptr or None), rows, cols, C.c_void_p(stream or None)))
+
     def reduce_keys_p2p(self, key_ptrs, disp_ptrs, rank: int, npx: int, stream=0):
         """Peer-memory combine of a disparity split (gsm_reduce_keys_p2p): key_ptrs / disp_ptrs are the device
         pointers of every rank's packed-min plane / disparity map as mapped into this process."""
@@ -147,6 +206,7 @@ class StereoContext:
     def ad_volume(self, left, right, num_disp: int) -> np.ndarray:
         """== PreCal (BlockMatching.cpp:89-109): u8 [D][rows][cols]."""
         L, R = _u8c(left, "left"), _u8c(right, "right")
+        _same_shape(2, left=L, right=R)
         out = np.empty((num_disp,) + L.shape, np.uint8)
         _l.check(self._lib.gsm_ad_volume(self._h, _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1], num_disp))
         return out
@@ -154,6 +214,7 @@ class StereoContext:
     def cost_slices(self, left, right, params: GsmParams, d0: int, nd: int, view: int = 0) -> np.ndarray:
         """Aggregated cost for d in [d0, d0+nd): int32 SAD (mode sad) or float32 q (mode gf), [nd][rows][cols]."""
         L, R = _u8c(left, "left"), _u8c(right, "right")
+        _same_shape(2, left=L, right=R)
         dt = np.int32 if params.mode == GSM_MODE_SAD else np.float32
         out = np.empty((nd,) + L.shape, dt)
         _l.check(self._lib.gsm_cost_slices(self._h, C.byref(params), view, _ptr(L), _ptr(R), d0, nd, _ptr(out),
@@ -163,6 +224,7 @@ class StereoContext:
     def all_sad(self, left, right, radius: int, num_disp: int) -> np.ndarray:
         """== getAllSAD (BlockMatching.cpp:191-261): u8 [rows*cols][D]."""
         L, R = _u8c(left, "left"), _u8c(right, "right")
+        _same_shape(2, left=L, right=R)
         out = np.empty((L.size, num_disp), np.uint8)
         _l.check(self._lib.gsm_all_sad(self._h, _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1], radius,
                                        num_disp))
@@ -176,6 +238,7 @@ class StereoContext:
 
     def lr_check(self, disp_left, disp_right):
         a, b = _u8c(disp_left, "disp_left"), _u8c(disp_right, "disp_right")
+        _same_shape(2, disp_left=a, disp_right=b)
         occ, mask = np.empty_like(a), np.empty_like(a)
         _l.check(self._lib.gsm_lr_check(self._h, _ptr(a), _ptr(b), _ptr(occ), _ptr(mask), a.shape[0], a.shape[1]))
         return occ, mask

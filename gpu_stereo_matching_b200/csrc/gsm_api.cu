@@ -49,7 +49,9 @@ struct gsm_ctx {
   i64 *keysL = nullptr, *keysR = nullptr;                         // packed-min planes
   u8 *dispA = nullptr, *dispB = nullptr, *dispC = nullptr, *dispD = nullptr, *maskD = nullptr;
   u8* dispOut = nullptr;                                          // final map of the host path before D2H
-  long long stat_key[2] = {-1, -1};                               // geometry the statistic planes were zeroed for
+  struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
+  FrameDesc* ft_dev = nullptr;                                    // per-frame sizes of a mixed-size batch (max_batch entries)
+  unsigned attr_sad[2] = {0, 0}, attr_gf[2] = {0, 0};             // radii whose kernels already carry the smem attribute
   void* export_buf = nullptr;
   size_t export_bytes = 0;
   u32* peak_buf = nullptr;
@@ -106,7 +108,8 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   void* bufs[] = {c->tightL, c->tightR, c->planeL, c->planeR, c->planeLrep, c->stats[0], c->stats[1], c->keysL,
-                  c->keysR,  c->dispA,  c->dispB,  c->dispC,  c->dispD,     c->maskD,    c->export_buf, c->peak_buf, c->dispOut, c->rect_maps};
+                  c->keysR,  c->dispA,  c->dispB,  c->dispC,  c->dispD,     c->maskD,    c->export_buf, c->peak_buf, c->dispOut, c->rect_maps,
+                  c->ft_dev};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -182,6 +185,7 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
   A((void**)&c->maskD, slot_px);
   A((void**)&c->dispOut, slot_px);
   A((void**)&c->peak_buf, (size_t)prop.multiProcessorCount * 8 * 256 * sizeof(u32));
+  A((void**)&c->ft_dev, (size_t)max_batch * sizeof(FrameDesc));
   if (st == cudaSuccess) st = cudaStreamSynchronize(c->stream);  // every buffer is zero before the first call
   if (st != cudaSuccess) {
     int rc = fail(GSM_ERR_CUDA, "gsm_create: allocation failed: %s", cudaGetErrorString(st));
@@ -293,6 +297,8 @@ static Plan make_plan(const gsm_params* p, int n, int rows, int cols, int d_begi
     if (bands <= 0) bands = 1;
   }
   bands = std::max(1, std::min(bands, rows));
+  bands = std::max(1, std::min(bands, 65535 / std::max(1, n)));  // grid.z = n * bands
+  pl.g.ft = nullptr;
   pl.g.bands = bands;
   pl.g.band_rows = (rows + bands - 1) / bands;
   pl.g.view = view;
@@ -334,13 +340,15 @@ static i64 key_init(const gsm_params* p) {
 
 template <bool EXPORT>
 static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, int view,
-                      const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0, int end_) {
+                      const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0, int end_,
+                      const FrameDesc* ft) {
   constexpr int K = 16;
   const int runs = GSM_SAD_RUNS;
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, R, 2, HL4);
   pl.smem = sad_smem_bytes(runs, K, HL4);
+  pl.g.ft = ft;
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
   pl.g.export_nd = end_;
@@ -348,7 +356,10 @@ static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols
 #define X(r)                                                                                                \
   case r: {                                                                                                 \
     auto kfn = sad_wta_kernel<r, K, EXPORT>;                                                                \
-    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));               \
+    if (!(c->attr_sad[EXPORT] >> r & 1u)) { /* once per context and kernel, not per launch */               \
+      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));             \
+      c->attr_sad[EXPORT] |= 1u << r;                                                                       \
+    }                                                                                                       \
     kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, keys, pl.g);                                               \
     break;                                                                                                  \
   }
@@ -368,7 +379,7 @@ static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols
 template <bool EXPORT>
 static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, float eps,
                      int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
-                     int end_) {
+                     int end_, const FrameDesc* ft) {
   constexpr int K = GSM_GF_K;
   // 12 runs of 16 columns x 32 disparities per CTA: a 192-column strip, 160 of them output columns (v3 needs a halo
   // of only r columns).  Measured alternatives at 720p x 128d: 24 runs x 16 disparities 1654 fps, this 1713 fps.
@@ -377,16 +388,21 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, stage_halo_of(GSM_MODE_GF, R), 6, HL4, lpr);
   pl.smem = gf3_smem_bytes(runs, K, HL4, lpr);
+  pl.g.ft = ft;
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
   pl.g.export_nd = end_;
   const PlaneGeom& pg = pl.g.pg;
   float* stats = c->stats[view];
-  // the statistic planes must be zero outside the image: re-zero when the padded geometry changes
-  const long long key = ((long long)rows << 40) ^ ((long long)cols << 20) ^ ((long long)pg.xoff << 8) ^ n;
-  if (c->stat_key[view] != key) {
+  // the statistic planes must be zero outside the image: re-zero when the padded geometry changes (a mixed-size
+  // batch always does: its frames occupy slots that may have held larger images)
+  gsm_ctx::StatGeom& sg = c->stat_geom[view];
+  if (ft || sg.rows != rows || sg.cols != cols || sg.xoff != pg.xoff || sg.n < n) {
     CK(cudaMemsetAsync(stats, 0, (size_t)n * GF_STAT_PLANES * pg.plane_stride * sizeof(float), s));
-    c->stat_key[view] = key;
+    sg.rows = ft ? -1 : rows;
+    sg.cols = cols;
+    sg.xoff = pg.xoff;
+    sg.n = n;
   }
   {
     static_assert(K == 16, "gf_prepass_kernel assumes one global grid of 16-column runs");
@@ -396,7 +412,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     int rpb = PP_ROWS;
     while (rpb > 8 && (long long)nbx * ((rows + rpb - 1) / rpb) * n < 2 * 148) rpb /= 2;
     gf_prepass_kernel<<<dim3(nbx, (rows + rpb - 1) / rpb, n), PP_THREADS, 0, s>>>(
-        G, stats, pg, R, eps, pl.g.TW, pl.g.hl, runs, strips, keys, key_init(p), rpb);
+        G, stats, pg, R, eps, pl.g.TW, pl.g.hl, runs, strips, keys, key_init(p), rpb, ft);
     c->launches++;
     CK(cudaGetLastError());
   }
@@ -406,7 +422,10 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
 #define X(r)                                                                                  \
   case r: {                                                                                   \
     auto kfn = GF_KERNEL<r, K, runs, lpr, EXPORT>;                                            \
-    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    if (!(c->attr_gf[EXPORT] >> r & 1u)) {                                                    \
+      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+      c->attr_gf[EXPORT] |= 1u << r;                                                          \
+    }                                                                                         \
     kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                          \
     break;                                                                                    \
   }
@@ -422,10 +441,10 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
 }
 
 static int pack_planes(gsm_ctx* c, const PlaneGeom& pg, int n, const u8* src, u8* dst, int fill, cudaStream_t s,
-                       const float* mapx = nullptr, const float* mapy = nullptr) {
+                       const float* mapx, const float* mapy, const FrameDesc* ft) {
   dim3 block(128);
   dim3 grid((pg.pitch / 4 + 127) / 128, pg.plane_rows, n);
-  pack_plane_kernel<<<grid, block, 0, s>>>(src, dst, pg, fill, mapx, mapy);
+  pack_plane_kernel<<<grid, block, 0, s>>>(src, dst, pg, fill, mapx, mapy, ft);
   c->launches++;
   CK(cudaGetLastError());
   return GSM_OK;
@@ -439,9 +458,10 @@ static int fill_keys(gsm_ctx* c, i64* keys, size_t npx, i64 v, cudaStream_t s) {
 }
 
 
-static int median_launch(gsm_ctx* c, const u8* src, u8* dst, int n, int rows, int cols, int m, cudaStream_t s) {
+static int median_launch(gsm_ctx* c, const u8* src, u8* dst, int n, int rows, int cols, int m, cudaStream_t s,
+                         const FrameDesc* ft = nullptr) {
   dim3 grid((cols + MED_TX - 1) / MED_TX, (rows + MED_TY - 1) / MED_TY, n);
-  median_kernel<<<grid, dim3(MED_TX, MED_TY), 0, s>>>(src, dst, rows, cols, m);
+  median_kernel<<<grid, dim3(MED_TX, MED_TY), 0, s>>>(src, dst, rows, cols, m, ft);
   c->launches++;
   CK(cudaGetLastError());
   return GSM_OK;
@@ -450,8 +470,9 @@ static int median_launch(gsm_ctx* c, const u8* src, u8* dst, int n, int rows, in
 // Fused aggregation + WTA of one view for a sub-batch that fits the context: tight images -> packed keys.
 static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end,
                          float eps, int view, const u8* Ltight, const u8* Rtight, i64* keys, cudaStream_t s,
-                         void* export_ptr = nullptr, int ed0 = 0, int end_ = 0) {
-  const size_t npx = (size_t)n * rows * cols;
+                         void* export_ptr = nullptr, int ed0 = 0, int end_ = 0, const FrameDesc* ft = nullptr,
+                         size_t npx_total = 0) {
+  const size_t npx = ft ? npx_total : (size_t)n * rows * cols;
   const int stage_halo = stage_halo_of(p->mode, p->radius);
   const PlaneGeom pg = make_plane_geom(rows, cols, strip_left_halo(strip_columns(p->mode), stage_halo));
   int rc;
@@ -463,63 +484,76 @@ static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int c
   const float* mL = p->rectify ? c->rect_maps : nullptr;
   const float* mR = p->rectify ? c->rect_maps + 2 * mpx : nullptr;
   if (view == 0) {
-    if ((rc = pack_planes(c, pg, n, Ltight, Gp, 0, s, mL, mL ? mL + mpx : nullptr))) return rc;
-    if ((rc = pack_planes(c, pg, n, Rtight, Op, 0, s, mR, mR ? mR + mpx : nullptr))) return rc;
+    if ((rc = pack_planes(c, pg, n, Ltight, Gp, 0, s, mL, mL ? mL + mpx : nullptr, ft))) return rc;
+    if ((rc = pack_planes(c, pg, n, Rtight, Op, 0, s, mR, mR ? mR + mpx : nullptr, ft))) return rc;
   } else {
-    if ((rc = pack_planes(c, pg, n, Rtight, Gp, 0, s, mR, mR ? mR + mpx : nullptr))) return rc;
-    if ((rc = pack_planes(c, pg, n, Ltight, Op, 1, s, mL, mL ? mL + mpx : nullptr))) return rc;
+    if ((rc = pack_planes(c, pg, n, Rtight, Gp, 0, s, mR, mR ? mR + mpx : nullptr, ft))) return rc;
+    if ((rc = pack_planes(c, pg, n, Ltight, Op, 1, s, mL, mL ? mL + mpx : nullptr, ft))) return rc;
   }
   // GF: the guide pre-pass also initialises the packed-min plane (it visits every pixel anyway)
   if (p->mode == GSM_MODE_SAD && (rc = fill_keys(c, keys, npx, key_init(p), s))) return rc;
   if (p->mode == GSM_MODE_SAD) {
     if ((rc = timing_begin(c, s))) return rc;
     if (export_ptr)
-      rc = launch_sad<true>(c, p, n, rows, cols, d_begin, d_end, view, Gp, Op, keys, s, export_ptr, ed0, end_);
+      rc = launch_sad<true>(c, p, n, rows, cols, d_begin, d_end, view, Gp, Op, keys, s, export_ptr, ed0, end_, ft);
     else
-      rc = launch_sad<false>(c, p, n, rows, cols, d_begin, d_end, view, Gp, Op, keys, s, nullptr, 0, 0);
+      rc = launch_sad<false>(c, p, n, rows, cols, d_begin, d_end, view, Gp, Op, keys, s, nullptr, 0, 0, ft);
     if (rc) return rc;
     if ((rc = timing_end(c, s))) return rc;
   } else {
     if (export_ptr)
-      rc = launch_gf<true>(c, p, n, rows, cols, d_begin, d_end, eps, view, Gp, Op, keys, s, export_ptr, ed0, end_);
+      rc = launch_gf<true>(c, p, n, rows, cols, d_begin, d_end, eps, view, Gp, Op, keys, s, export_ptr, ed0, end_, ft);
     else
-      rc = launch_gf<false>(c, p, n, rows, cols, d_begin, d_end, eps, view, Gp, Op, keys, s, nullptr, 0, 0);
+      rc = launch_gf<false>(c, p, n, rows, cols, d_begin, d_end, eps, view, Gp, Op, keys, s, nullptr, 0, 0, ft);
     if (rc) return rc;
   }
+  return GSM_OK;
+}
+
+// u8 maps (left [, right]) -> final disparity [, mask]: median on both views, then the LR check
+// (STMatching/StereoDisparity.cpp:119,126,128-147).  dl / dr may be scratch maps of the context or caller maps.
+static int post_maps(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, const u8* dl, const u8* dr,
+                     u8* disp_out, u8* mask_out, cudaStream_t s, const FrameDesc* ft, size_t npx) {
+  int rc;
+  const bool lr = p->lr_check && dr;
+  const int m = p->median_radius;
+  if (m > 0) {
+    u8* dst = lr ? c->dispB : disp_out;
+    if ((rc = median_launch(c, dl, dst, n, rows, cols, m, s, ft))) return rc;
+    dl = dst;
+  }
+  if (lr) {
+    if (m > 0) {
+      if ((rc = median_launch(c, dr, c->dispD, n, rows, cols, m, s, ft))) return rc;
+      dr = c->dispD;
+    }
+    dim3 grid((cols + 255) / 256, rows, n);
+    lr_check_kernel<<<grid, 256, 0, s>>>(dl, dr, nullptr, mask_out, disp_out, rows, cols, n, ft);
+    c->launches++;
+  } else if (dl != disp_out) {
+    CK(cudaMemcpyAsync(disp_out, dl, npx, cudaMemcpyDeviceToDevice, s));
+  }
+  CK(cudaGetLastError());
   return GSM_OK;
 }
 
 // keys (left [, right]) -> disparity [, mask]; order follows STMatching/StereoDisparity.cpp:115-147:
 // WTA -> median on both views -> LR check.
 static int finalize_views(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, const i64* kL, const i64* kR,
-                          u8* disp_out, u8* mask_out, cudaStream_t s) {
-  const size_t npx = (size_t)n * rows * cols;
+                          u8* disp_out, u8* mask_out, cudaStream_t s, const FrameDesc* ft = nullptr,
+                          size_t npx_total = 0) {
+  const size_t npx = ft ? npx_total : (size_t)n * rows * cols;
   const unsigned gb = (unsigned)((npx + 255) / 256);
-  int rc;
   const bool lr = p->lr_check && kR;
-  const int m = p->median_radius;
-  u8* dl = (m > 0 || lr) ? c->dispA : disp_out;
+  u8* dl = (p->median_radius > 0 || lr) ? c->dispA : disp_out;
   finalize_keys_kernel<<<gb, 256, 0, s>>>(kL, dl, npx);
   c->launches++;
-  if (m > 0) {
-    u8* dst = lr ? c->dispB : disp_out;
-    if ((rc = median_launch(c, dl, dst, n, rows, cols, m, s))) return rc;
-    dl = dst;
-  }
   if (lr) {
-    u8* dr = c->dispC;
-    finalize_keys_kernel<<<gb, 256, 0, s>>>(kR, dr, npx);
-    c->launches++;
-    if (m > 0) {
-      if ((rc = median_launch(c, dr, c->dispD, n, rows, cols, m, s))) return rc;
-      dr = c->dispD;
-    }
-    dim3 grid((cols + 255) / 256, rows, n);
-    lr_check_kernel<<<grid, 256, 0, s>>>(dl, dr, nullptr, mask_out, disp_out, rows, cols, n);
+    finalize_keys_kernel<<<gb, 256, 0, s>>>(kR, c->dispC, npx);
     c->launches++;
   }
   CK(cudaGetLastError());
-  return GSM_OK;
+  return post_maps(c, p, n, rows, cols, dl, lr ? c->dispC : nullptr, disp_out, mask_out, s, ft, npx);
 }
 
 extern "C" int gsm_stereo_device(gsm_ctx* c, const gsm_params* p, int n, const void* left_dev, const void* right_dev,
@@ -602,6 +636,115 @@ extern "C" int gsm_stereo_batch(gsm_ctx* c, const gsm_params* p, int n, const ui
   return gsm_sync(c);
 }
 
+// Mixed-size batch (BASELINE config 2: the nine Middlebury sets come in three sizes): every frame has its own rows x
+// cols and its own host buffers, like the separate Mats of Caller.cpp:12-19; the whole batch runs as ONE launch per
+// stage over a per-frame geometry table (FrameDesc).  Blocking.
+extern "C" int gsm_stereo_batch_v(gsm_ctx* c, const gsm_params* p, int n, const uint8_t* const* left,
+                                  const uint8_t* const* right, uint8_t* const* disparity, uint8_t* const* mask,
+                                  const int* rows, const int* cols) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  if (!p || !left || !right || !disparity || !rows || !cols || n < 1)
+    return fail(GSM_ERR_INVALID, "gsm_stereo_batch_v: null argument or n=%d", n);
+  if (p->rectify) return fail(GSM_ERR_INVALID, "gsm_stereo_batch_v: rectify needs frames of the maps' size (gsm_stereo_batch)");
+  int max_r = 0, max_c = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!left[i] || !right[i] || !disparity[i]) return fail(GSM_ERR_INVALID, "gsm_stereo_batch_v: null image pointer (frame %d)", i);
+    if (rows[i] < 1 || cols[i] < 1) return fail(GSM_ERR_INVALID, "gsm_stereo_batch_v: frame %d is %dx%d", i, rows[i], cols[i]);
+    max_r = std::max(max_r, rows[i]);
+    max_c = std::max(max_c, cols[i]);
+  }
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, 1, max_r, max_c, &d_begin, &d_end, &eps))) return rc;
+  CK(cudaSetDevice(c->device));
+  if ((rc = gsm_sync(c))) return rc;  // drain any streaming batches still in flight
+  cudaStream_t s = c->stream;
+  const bool want_mask = mask && p->lr_check;
+  c->ev_used = 0;
+  std::vector<FrameDesc> ft;
+  for (int f0 = 0; f0 < n; f0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, n - f0);
+    // geometry of THIS sub-batch: plane slots are laid out for its largest frame
+    int br = 0, bc = 0;
+    ft.assign(nb, FrameDesc());
+    long long off = 0;
+    for (int i = 0; i < nb; ++i) {
+      ft[i].H = rows[f0 + i];
+      ft[i].W = cols[f0 + i];
+      ft[i].off = off;
+      off += (long long)ft[i].H * ft[i].W;
+      br = std::max(br, ft[i].H);
+      bc = std::max(bc, ft[i].W);
+    }
+    const size_t npx = (size_t)off;
+    CK(cudaMemcpyAsync(c->ft_dev, ft.data(), nb * sizeof(FrameDesc), cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < nb; ++i) {
+      const size_t bytes = (size_t)ft[i].H * ft[i].W;
+      CK(cudaMemcpyAsync(c->tightL + ft[i].off, left[f0 + i], bytes, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(c->tightR + ft[i].off, right[f0 + i], bytes, cudaMemcpyHostToDevice, s));
+    }
+    if ((rc = run_view_keys(c, p, nb, br, bc, d_begin, d_end, eps, 0, c->tightL, c->tightR, c->keysL, s, nullptr, 0, 0,
+                            c->ft_dev, npx)))
+      return rc;
+    if (p->lr_check)
+      if ((rc = run_view_keys(c, p, nb, br, bc, d_begin, d_end, eps, 1, c->tightL, c->tightR, c->keysR, s, nullptr, 0,
+                              0, c->ft_dev, npx)))
+        return rc;
+    if ((rc = finalize_views(c, p, nb, br, bc, c->keysL, p->lr_check ? c->keysR : nullptr, c->dispOut,
+                             want_mask ? c->maskD : nullptr, s, c->ft_dev, npx)))
+      return rc;
+    for (int i = 0; i < nb; ++i) {
+      const size_t bytes = (size_t)ft[i].H * ft[i].W;
+      CK(cudaMemcpyAsync(disparity[f0 + i], c->dispOut + ft[i].off, bytes, cudaMemcpyDeviceToHost, s));
+      if (want_mask && mask[f0 + i])
+        CK(cudaMemcpyAsync(mask[f0 + i], c->maskD + ft[i].off, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));  // the table and the slots are reused by the next sub-batch
+  }
+  return GSM_OK;
+}
+
+// Same on DEVICE buffers: frame i is rows[i] x cols[i] at pixel offset sum_{j<i} rows[j]*cols[j] of left_dev /
+// right_dev / disparity_dev / mask_dev (tight, concatenated).  n <= the context's batch capacity.  Asynchronous on
+// `stream`; rows / cols are host arrays and are consumed before the call returns.
+extern "C" int gsm_stereo_device_v(gsm_ctx* c, const gsm_params* p, int n, const void* left_dev, const void* right_dev,
+                                   void* disparity_dev, void* mask_dev, const int* rows, const int* cols, void* stream) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  if (!p || !left_dev || !right_dev || !disparity_dev || !rows || !cols || n < 1)
+    return fail(GSM_ERR_INVALID, "gsm_stereo_device_v: null argument or n=%d", n);
+  if (n > c->max_batch) return fail(GSM_ERR_CAPACITY, "gsm_stereo_device_v: %d frames exceed the batch capacity %d", n, c->max_batch);
+  if (p->rectify) return fail(GSM_ERR_INVALID, "gsm_stereo_device_v: rectify needs frames of the maps' size");
+  std::vector<FrameDesc> ft(n);
+  int br = 0, bc = 0;
+  long long off = 0;
+  for (int i = 0; i < n; ++i) {
+    if (rows[i] < 1 || cols[i] < 1) return fail(GSM_ERR_INVALID, "gsm_stereo_device_v: frame %d is %dx%d", i, rows[i], cols[i]);
+    ft[i].H = rows[i];
+    ft[i].W = cols[i];
+    ft[i].off = off;
+    off += (long long)rows[i] * cols[i];
+    br = std::max(br, rows[i]);
+    bc = std::max(bc, cols[i]);
+  }
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, 1, br, bc, &d_begin, &d_end, &eps))) return rc;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  c->ev_used = 0;
+  const size_t npx = (size_t)off;
+  CK(cudaMemcpyAsync(c->ft_dev, ft.data(), n * sizeof(FrameDesc), cudaMemcpyHostToDevice, s));  // pageable: staged now
+  if ((rc = run_view_keys(c, p, n, br, bc, d_begin, d_end, eps, 0, (const u8*)left_dev, (const u8*)right_dev, c->keysL, s,
+                          nullptr, 0, 0, c->ft_dev, npx)))
+    return rc;
+  if (p->lr_check)
+    if ((rc = run_view_keys(c, p, n, br, bc, d_begin, d_end, eps, 1, (const u8*)left_dev, (const u8*)right_dev, c->keysR,
+                            s, nullptr, 0, 0, c->ft_dev, npx)))
+      return rc;
+  return finalize_views(c, p, n, br, bc, c->keysL, p->lr_check ? c->keysR : nullptr, (u8*)disparity_dev, (u8*)mask_dev, s,
+                        c->ft_dev, npx);
+}
+
 extern "C" int gsm_block_matching(gsm_ctx* c, const uint8_t* left, const uint8_t* right, uint8_t* disparity, int rows,
                                   int cols, int radius, int num_disp) {
   gsm_params p;
@@ -639,6 +782,23 @@ extern "C" int gsm_finalize_keys_device(gsm_ctx* c, const gsm_params* p, const v
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
   return finalize_views(c, p, 1, rows, cols, (const i64*)keys_left_dev, (const i64*)keys_right_dev, (u8*)disparity_dev,
                         (u8*)mask_dev, s);
+}
+
+// Post-filters on DEVICE maps: median on both views, then the LR check (StereoDisparity.cpp:119,126,128-147) -- what
+// gsm_finalize_keys_device does after extracting the disparities, for callers that already hold u8 maps (the
+// peer-memory disparity split, whose combine kernel writes the raw WTA maps of both views into every rank).
+extern "C" int gsm_postfilter_device(gsm_ctx* c, const gsm_params* p, const void* disp_left_dev,
+                                     const void* disp_right_dev, void* disparity_dev, void* mask_dev, int rows, int cols,
+                                     void* stream) {
+  int d_begin, d_end, rc;
+  float eps;
+  if ((rc = check_params(c, p, 1, rows, cols, &d_begin, &d_end, &eps))) return rc;
+  if (!disp_left_dev || !disparity_dev) return fail(GSM_ERR_INVALID, "null pointer");
+  if (p->lr_check && !disp_right_dev) return fail(GSM_ERR_INVALID, "lr_check needs the right-view map");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+  return post_maps(c, p, 1, rows, cols, (const u8*)disp_left_dev, p->lr_check ? (const u8*)disp_right_dev : nullptr,
+                   (u8*)disparity_dev, (u8*)mask_dev, s, nullptr, (size_t)rows * cols);
 }
 
 extern "C" int gsm_reduce_keys_p2p(gsm_ctx* c, const void* const* key_ptrs, void* const* disp_ptrs, int world,
@@ -796,7 +956,7 @@ extern "C" int gsm_lr_check(gsm_ctx* c, const uint8_t* dl, const uint8_t* dr, ui
   CK(cudaMemcpyAsync(c->dispA, dl, fpx, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(c->dispB, dr, fpx, cudaMemcpyHostToDevice, s));
   lr_check_kernel<<<dim3((cols + 255) / 256, rows, 1), 256, 0, s>>>(c->dispA, c->dispB, c->dispC, c->maskD, nullptr, rows,
-                                                                      cols, 1);
+                                                                      cols, 1, nullptr);
   c->launches++;
   CK(cudaGetLastError());
   if (occ) CK(cudaMemcpyAsync(occ, c->dispC, fpx, cudaMemcpyDeviceToHost, s));

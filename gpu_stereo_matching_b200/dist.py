@@ -102,45 +102,106 @@ def dsplit_stereo(partial_keys: Callable, finalize: Callable, keys_left, keys_ri
 
 
 class PeerPlanes:
-    """Per-rank packed-min plane and disparity map in symmetric (peer-mapped) device memory, for dsplit_stereo_p2p.
+    """Per-rank packed-min planes and raw WTA maps in symmetric (peer-mapped) device memory, for dsplit_stereo_p2p.
 
     Allocated with torch.distributed._symmetric_memory (CUDA IPC over NVLink / NVSwitch): after the rendezvous every
-    rank holds device pointers to every other rank's planes.  Raises if peer memory is unavailable -- callers fall
-    back to dsplit_stereo (NCCL all-reduce).
+    rank holds device pointers to every other rank's planes.  `views` = 2 keeps a second plane / map for the right view
+    (LR check).  `slots` = 2 double-buffers planes and maps so that consecutive frames need ONE cross-rank barrier each
+    instead of two (see dsplit_stereo_p2p).  Raises if peer memory is unavailable -- callers fall back to
+    dsplit_stereo (NCCL all-reduce).
     """
 
-    def __init__(self, npx: int, group=None):
+    def __init__(self, npx: int, group=None, views: int = 1, slots: int = 2):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         grp = group if group is not None else dist.group.WORLD
         self.npx = int(npx)
-        self.keys = symm.empty(self.npx, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
-        self.disp = symm.empty(self.npx, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.views, self.slots = int(views), int(slots)
+        self.stride = (self.npx + 15) // 16 * 16  # pixels per (slot, view) plane: keeps every plane 16-byte aligned
+        dev = torch.device("cuda", torch.cuda.current_device())
+        total = self.slots * self.views * self.stride
+        self.keys = symm.empty(total, dtype=torch.int64, device=dev)
+        self.disp = symm.empty(total, dtype=torch.uint8, device=dev)
         self.keys_h = symm.rendezvous(self.keys, grp)
         self.disp_h = symm.rendezvous(self.disp, grp)
         self.world, self.rank = self.keys_h.world_size, self.keys_h.rank
-        self.key_ptrs = [int(p) for p in self.keys_h.buffer_ptrs]
-        self.disp_ptrs = [int(p) for p in self.disp_h.buffer_ptrs]
+        self._kbase = [int(p) for p in self.keys_h.buffer_ptrs]
+        self._dbase = [int(p) for p in self.disp_h.buffer_ptrs]
+        self.frame = 0  # frames submitted so far (slot = frame % slots)
+        # results of the optional post-filters (local, not peer-mapped)
+        self.out = torch.empty(self.npx, dtype=torch.uint8, device=dev)
+        self.mask = torch.empty(self.npx, dtype=torch.uint8, device=dev)
+
+    def _index(self, slot: int, view: int) -> int:
+        return (slot * self.views + view) * self.stride
+
+    def keys_view(self, slot: int, view: int):
+        o = self._index(slot, view)
+        return self.keys[o:o + self.npx]
+
+    def disp_view(self, slot: int, view: int):
+        o = self._index(slot, view)
+        return self.disp[o:o + self.npx]
+
+    def key_ptrs(self, slot: int, view: int):
+        return [b + 8 * self._index(slot, view) for b in self._kbase]
+
+    def disp_ptrs(self, slot: int, view: int):
+        return [b + self._index(slot, view) for b in self._dbase]
+
+    def nvlink_bytes_per_frame(self, views: int = 1) -> int:
+        """Bytes this rank moves over NVLink per frame: P2P loads of its 1/world slice of the other ranks' int64
+        planes + P2P stores of its u8 slice into the other ranks' maps."""
+        sl = self.npx / self.world
+        return int(views * (self.world - 1) * sl * (8 + 1))
 
 
-def dsplit_stereo_p2p(ctx, partial_keys: Callable, planes: PeerPlanes, params, stream_handle: int = 0):
-    """Disparity-split evaluation of ONE frame with the combine fused over peer memory (no LR check / median).
+def dsplit_stereo_p2p(ctx, partial_keys: Callable, planes: PeerPlanes, params, stream_handle: int = 0,
+                      rows: Optional[int] = None, cols: Optional[int] = None, final_barrier: bool = True):
+    """Disparity-split evaluation of ONE frame with the combine fused over peer memory.
 
-    partial_keys(view, d_begin, d_end, keys_tensor) as in dsplit_stereo.  Every rank ends with the full u8 map in
-    planes.disp.  Must run with torch's current stream == the stream behind stream_handle: the two cross-rank
-    barriers (symmetric-memory signal pads) are enqueued on the current stream.
-      barrier 1: every rank's plane is complete before anybody reads it over NVLink;
-      barrier 2: every slice has landed in every map, and nobody still reads a plane the next frame overwrites.
+    partial_keys(view, d_begin, d_end, keys_tensor) as in dsplit_stereo; every rank must evaluate its range with the
+    SAME gsm_params.row_bands (dsplit_row_bands) for the result to equal the single-GPU map bit for bit.  Every rank
+    ends with the full map: the raw left-view WTA map in planes.disp_view(slot, 0) or, with params.lr_check /
+    params.median_radius (needs rows, cols), the post-filtered map in planes.out (+ planes.mask), computed by every
+    rank on its own copy (gsm_postfilter_device; no further communication).  Returns the result tensor.
+
+    Must run with torch's current stream == the stream behind stream_handle: the cross-rank barriers (symmetric-memory
+    signal pads) are enqueued on the current stream.
+      barrier A (always): every rank's planes of this frame are complete before anybody reads them over NVLink.  Because
+                 each rank enqueues its combine kernel of frame k BEFORE its partial keys of frame k+1, this barrier
+                 also proves that every combine of the previous frame has finished: with two plane / map slots
+                 (PeerPlanes(slots=2)) nothing written for frame k+1 can race with frame k.
+      barrier B (final_barrier=True): every slice of THIS frame has landed in every rank's map.  A stream of frames sets
+                 final_barrier=False on all but the last frame and reads frame k's map after barrier A of frame k+1.
     """
-    if params.lr_check or params.median_radius:
-        raise ValueError("dsplit_stereo_p2p combines the left view only; use dsplit_stereo for LR check / median")
+    lr = bool(params.lr_check)
+    if lr and planes.views < 2:
+        raise ValueError("lr_check needs PeerPlanes(views=2)")
+    post = lr or params.median_radius > 0
+    if post and (rows is None or cols is None or rows * cols != planes.npx):
+        raise ValueError("post-filters need rows, cols with rows*cols == planes.npx")
+    if planes.slots < 2 and not final_barrier:
+        raise ValueError("final_barrier=False needs PeerPlanes(slots=2)")
+    slot = planes.frame % planes.slots
+    planes.frame += 1
     d0, d1 = shard_disparities(params.num_disp, planes.world, planes.rank)
-    if d1 > d0:
-        partial_keys(0, d0, d1, planes.keys)
-    else:
-        planes.keys.fill_(key_init(params.mode, params.radius))
+    views = (0, 1) if lr else (0,)
+    for view in views:
+        k = planes.keys_view(slot, view)
+        if d1 > d0:
+            partial_keys(view, d0, d1, k)
+        else:
+            k.fill_(key_init(params.mode, params.radius))
     planes.keys_h.barrier(channel=0)
-    ctx.reduce_keys_p2p(planes.key_ptrs, planes.disp_ptrs, planes.rank, planes.npx, stream_handle)
-    planes.keys_h.barrier(channel=1)
-    return planes.disp
+    for view in views:
+        ctx.reduce_keys_p2p(planes.key_ptrs(slot, view), planes.disp_ptrs(slot, view), planes.rank, planes.npx,
+                            stream_handle)
+    if final_barrier or post:
+        planes.keys_h.barrier(channel=1)
+    if not post:
+        return planes.disp_view(slot, 0)
+    ctx.postfilter_device(planes.disp_view(slot, 0).data_ptr(), planes.disp_view(slot, 1).data_ptr() if lr else 0,
+                          planes.out.data_ptr(), planes.mask.data_ptr() if lr else 0, rows, cols, params, stream_handle)
+    return planes.out

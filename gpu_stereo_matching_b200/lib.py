@@ -50,6 +50,10 @@ SYMBOLS = {
     "gsm_stereo_batch": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_stereo_batch_async": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_stereo_device": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "gsm_stereo_batch_v": (C.c_int, [_P, _PP, C.c_int, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gsm_stereo_device_v": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]),
+    "gsm_postfilter_device": (C.c_int, [_P, _PP, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gsm_sync": (C.c_int, [_P]),
     "gsm_partial_keys_device": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gsm_finalize_keys_device": (C.c_int, [_P, _PP, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -89,6 +89,15 @@ int gsm_block_matching(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, 
 int gsm_stereo_batch(gsm_ctx* ctx, const gsm_params* p, int n, const uint8_t* left, const uint8_t* right,
                      uint8_t* disparity, uint8_t* mask, int rows, int cols);
 
+/* Mixed-size batch: frame i is rows[i] x cols[i] with its own host buffers left[i] / right[i] / disparity[i]
+ * (/ mask[i]; mask or mask[i] may be NULL) -- the separate Mats of Caller.cpp:12-19, and BASELINE config 2 (the nine
+ * Middlebury sets come in three sizes).  The whole batch runs as ONE launch per stage over a per-frame geometry
+ * table; every frame must fit the context (rows[i] <= max_rows, cols[i] <= max_cols).  Blocking.  Results are
+ * bit-identical to calling gsm_stereo_batch once per frame with the same row_bands. */
+int gsm_stereo_batch_v(gsm_ctx* ctx, const gsm_params* p, int n, const uint8_t* const* left,
+                       const uint8_t* const* right, uint8_t* const* disparity, uint8_t* const* mask, const int* rows,
+                       const int* cols);
+
 /* Streaming variant: enqueues uploads, kernels and downloads and returns; the results are in `disparity` / `mask`
  * after gsm_sync().  Back-to-back submissions keep the two-slot pipeline full across calls (frame k+1 uploads while
  * frame k computes and frame k-1 downloads) -- what a capture loop (reference: Utility.cpp:198-226) would use.  The
@@ -101,6 +110,10 @@ int gsm_stereo_batch_async(gsm_ctx* ctx, const gsm_params* p, int n, const uint8
  * (a cudaStream_t; NULL = the context's own stream).  Asynchronous: returns after enqueueing. */
 int gsm_stereo_device(gsm_ctx* ctx, const gsm_params* p, int n, const void* left_dev, const void* right_dev,
                       void* disparity_dev, void* mask_dev, int rows, int cols, void* stream);
+/* Mixed-size batch on DEVICE pointers: frame i is rows[i] x cols[i] at pixel offset sum_{j<i} rows[j]*cols[j] of
+ * every buffer (tight, concatenated); n <= the context's batch capacity; rows / cols are HOST arrays. */
+int gsm_stereo_device_v(gsm_ctx* ctx, const gsm_params* p, int n, const void* left_dev, const void* right_dev,
+                        void* disparity_dev, void* mask_dev, const int* rows, const int* cols, void* stream);
 /* Waits for everything enqueued on the context's own streams (compute, upload, download). */
 int gsm_sync(gsm_ctx* ctx);
 
@@ -118,6 +131,12 @@ int gsm_partial_keys_device(gsm_ctx* ctx, const gsm_params* p, int view, const v
 int gsm_finalize_keys_device(gsm_ctx* ctx, const gsm_params* p, const void* keys_left_dev,
                              const void* keys_right_dev, void* disparity_dev, void* mask_dev, int rows,
                              int cols, void* stream);
+
+/* u8 maps -> final map: (2m+1)^2 median on both views, then the LR check against disp_right_dev (may be NULL without
+ * lr_check) -- the part of gsm_finalize_keys_device after the disparities are extracted
+ * (STMatching/StereoDisparity.cpp:119,126,128-147). */
+int gsm_postfilter_device(gsm_ctx* ctx, const gsm_params* p, const void* disp_left_dev, const void* disp_right_dev,
+                          void* disparity_dev, void* mask_dev, int rows, int cols, void* stream);
 
 /* Combine the ranks' packed-min planes over PEER MEMORY (NVLink P2P) instead of an all-reduce: rank `rank` of `world`
  * reduces its 1/world slice of the npx pixels over all planes (key_ptrs[w] = rank w's int64 plane, mapped into this

@@ -412,6 +412,57 @@ def test_config5_4k_disparity_split_is_n_independent(ctx4k, pair4k, world):
     assert bad == 0 and n <= 1e-5 * npx, (n, bad)
 
 
+def test_mixed_size_batch_config2(ctx, fx, orc):
+    """BASELINE config 2: the nine Middlebury sets (three sizes) in ONE gsm_stereo_batch_v call == one call per set, bit
+    for bit (same row bands), for GF + LR (+ median) and for SAD; device-pointer variant included."""
+    import torch
+    Ls = [fx[s + "_L"] for s in SETS]
+    Rs = [fx[s + "_R"] for s in SETS]
+    assert len({a.shape for a in Ls}) == 3
+    with g.StereoContext(370, 463, 64, 9) as c9:
+        for kw in (dict(mode="gf", radius=9, num_disp=64, lr_check=True, row_bands=1),
+                   dict(mode="gf", radius=9, num_disp=64, lr_check=True, median_radius=3, row_bands=2),
+                   dict(mode="sad", radius=5, num_disp=64)):
+            p = g.make_params(**kw)
+            l0 = c9.launch_count
+            disps, masks = c9.stereo_batch_v(Ls, Rs, p)
+            launches = c9.launch_count - l0
+            for i, s_ in enumerate(SETS):
+                d1, m1 = c9.stereo_batch(Ls[i], Rs[i], p)
+                assert np.array_equal(disps[i], d1), (kw["mode"], s_)
+                if masks is not None:
+                    assert np.array_equal(masks[i], m1), (kw["mode"], s_)
+            if kw["mode"] == "sad":
+                for i, s_ in enumerate(SETS):
+                    assert np.array_equal(disps[i], orc.sad_wta(Ls[i], Rs[i], 5, 64)), s_
+            else:
+                assert launches <= 16, launches  # one launch per stage for the whole batch, not per size group
+        # automatic row bands: the batch may pick other bands than a single frame does -> near-ties only
+        p = g.make_params("gf", 9, 64, lr_check=True)
+        disps, masks = c9.stereo_batch_v(Ls, Rs, p)
+        for i, s_ in enumerate(SETS):
+            d1, _ = c9.stereo_batch(Ls[i], Rs[i], p)
+            assert (disps[i] == d1).mean() >= 0.9995, s_
+        # device-resident variant
+        cat = lambda xs: torch.from_numpy(np.concatenate([x.reshape(-1) for x in xs])).cuda()
+        Ld, Rd = cat(Ls), cat(Rs)
+        Dd, Md = torch.empty_like(Ld), torch.empty_like(Ld)
+        p = g.make_params("gf", 9, 64, lr_check=True, row_bands=1)
+        c9.stereo_device_v(Ld.data_ptr(), Rd.data_ptr(), Dd.data_ptr(), Md.data_ptr(), [a.shape for a in Ls], p)
+        c9.sync()
+        ref, _ = c9.stereo_batch_v(Ls, Rs, p)
+        assert np.array_equal(Dd.cpu().numpy(), np.concatenate([x.reshape(-1) for x in ref]))
+        # a smaller image after a larger one in the same slot: stale statistic planes must not leak
+        small = (Ls[0][:200, :300].copy(), Rs[0][:200, :300].copy())
+        dv, _ = c9.stereo_batch_v([Ls[0], small[0]], [Rs[0], small[1]], p)
+        d1, _ = c9.stereo_batch(small[0], small[1], p)
+        assert np.array_equal(dv[1], d1)
+        with pytest.raises(g.GsmError):
+            c9.stereo_batch_v([np.zeros((400, 10), np.uint8)], [np.zeros((400, 10), np.uint8)], p)  # rows > capacity
+        with pytest.raises(ValueError):
+            c9.stereo_batch_v([Ls[0]], [Rs[1][:, :400]], p)
+
+
 def test_errors_are_reported(ctx):
     z = np.zeros((16, 16), np.uint8)
     with pytest.raises(g.GsmError):
@@ -658,21 +709,27 @@ def _p2p_worker(rank, world, port, out):
         L, R, _ = gdata.synthetic_pair(h, w, 4242)
         Ld, Rd = torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda()
         c = g.StereoContext(h, w, D, 1, device=rank)
-        planes = PeerPlanes(h * w)
-        p = g.make_params("gf", 9, D)
+        from gpu_stereo_matching_b200.dist import dsplit_row_bands
+        bands = dsplit_row_bands(h, w, D, world)
+        planes = PeerPlanes(h * w, views=2, slots=2)
         st = torch.cuda.Stream()
         sh = torch_stream_handle(st)
+        ok = True
+        for kw in (dict(), dict(lr_check=True, median_radius=3)):
+            p = g.make_params("gf", 9, D, row_bands=bands, **kw)
 
-        def partial(view, d0, d1, keys):
-            c.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w,
-                                  g.make_params("gf", 9, D, d_begin=d0, d_end=d1), view, sh)
+            def partial(view, d0, d1, keys):
+                c.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w,
+                                      g.make_params("gf", 9, D, row_bands=bands, d_begin=d0, d_end=d1), view, sh)
 
-        with torch.cuda.stream(st):
-            for _ in range(3):  # repeated frames exercise the barrier pair / plane reuse
-                disp = dsplit_stereo_p2p(c, partial, planes, p, sh)
-        st.synchronize()
-        one, _ = c.stereo_batch(L, R, p)
-        ok = bool(np.array_equal(disp.cpu().numpy().reshape(h, w), one))
+            with torch.cuda.stream(st):
+                for i in range(5):  # a stream of frames: one barrier per frame, a closing one on the last
+                    disp = dsplit_stereo_p2p(c, partial, planes, p, sh, rows=h, cols=w, final_barrier=(i == 4))
+            st.synchronize()
+            one, mask1 = c.stereo_batch(L, R, p)  # the single-GPU map with the same row bands: bit-identical
+            ok = ok and bool(np.array_equal(disp.cpu().numpy().reshape(h, w), one))
+            if kw:
+                ok = ok and bool(np.array_equal(planes.mask.cpu().numpy().reshape(h, w), mask1))
         with open(out + f".{rank}", "w") as f:
             f.write("ok" if ok else "mismatch")
     finally:
