@@ -156,7 +156,7 @@ def _reference_arm(args, rank, world):
     gdt = time.perf_counter() - t0
     gf_port = {"value": gf_rows * W * D / gdt / 1e6, "unit": "MDE/s", "cores": cores, "kind": "port",
                "sample": f"oracle GF r={R_GF} float64 (OpenMP) on a {gf_rows}x{W} px x {D} d crop of a config-3 frame"}
-    print(json.dumps({
+    _emit(({
         "impl": "reference", "metric": "MDE/s", "value": v, "unit": "MDE/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32", "data": "synthetic", "fps": v * 1e6 / (H * W * D),
@@ -504,7 +504,7 @@ def _extra_config(args, rank, world, local_rank):
         Dd.copy_(last.view_as(Dd))
     if rank == 0:
         v = de_step / (ms * 1e-3) / 1e6
-        print(json.dumps({"metric": "MDE/s", "value": v, "unit": "MDE/s", "n_gpus": world, "steps": args.steps,
+        _emit(({"metric": "MDE/s", "value": v, "unit": "MDE/s", "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
                           "vs_baseline": None, "dtype": "u8/int32+fp32", "data": "synthetic",
                           "fps": v * 1e6 / (h * w * d) * (1 if args.config == "c5" else 1),
@@ -512,6 +512,30 @@ def _extra_config(args, rank, world, local_rank):
                                      **cfg_extra},
                           "result_checksum": int(Dd.to(torch.int64).sum().item()), "clocks": clk.summary()}))
     ctx.close()
+
+
+_JSON_FD = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout: keep a private copy of fd 1 for it and point fd 1 at stderr, so that
+    library chatter (NCCL prints its version on stdout when NCCL_DEBUG is set; the reference prints phase timings)
+    cannot land in front of the line."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -534,6 +558,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _protect_stdout()
     if args.impl == "reference":
         _reference_arm(args, rank, world)
         return
@@ -701,7 +726,7 @@ def main():
             with O.quiet_stdout():
                 cb = _cpu_baseline(Lu, Ru)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -263,6 +263,15 @@ class StereoContext:
         _l.check(self._lib.gsm_cvtcolor(self._h, _ptr(a), _ptr(out), a.shape[0], a.shape[1], int(truncate)))
         return out
 
+    def disparity_to_depth(self, disp, fB: float) -> np.ndarray:
+        """depth = fB / d (float32, 0 where d == 0): the Q-matrix depth of the rectified rig (Utility.cpp:228-234)."""
+        a = _u8c(disp, "disp")
+        if a.ndim != 2:
+            raise ValueError("disp must be [rows, cols]")
+        out = np.empty(a.shape, np.float32)
+        _l.check(self._lib.gsm_disparity_to_depth(self._h, _ptr(a), _ptr(out), a.shape[0], a.shape[1], float(fB)))
+        return out
+
     def set_rectification(self, mapx_left, mapy_left, mapx_right, mapy_right):
         """Upload the four CV_32FC1 maps Rectify() builds (Utility.cpp:228-234); params.rectify=True then feeds RAW
         frames, rectified on the device inside the plane packer.  Pass None four times to drop the maps."""

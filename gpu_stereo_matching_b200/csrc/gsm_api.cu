@@ -1010,6 +1010,26 @@ extern "C" int gsm_cvtcolor(gsm_ctx* c, const uint8_t* src3, uint8_t* dst, int r
   return GSM_OK;
 }
 
+extern "C" int gsm_disparity_to_depth(gsm_ctx* c, const uint8_t* disparity, float* depth, int rows, int cols, float fB) {
+  if (!c || !disparity || !depth) return fail(GSM_ERR_INVALID, "null pointer");
+  if (rows < 1 || cols < 1) return fail(GSM_ERR_INVALID, "bad shape %dx%d", rows, cols);
+  CK(cudaSetDevice(c->device));
+  if (int rc_sync = gsm_sync(c)) return rc_sync;  // drain any streaming batches still in flight
+  const size_t n = (size_t)rows * cols;
+  int rc;
+  if ((rc = ensure_export(c, n * 5))) return rc;  // [depth f32][disp u8]
+  float* dd = (float*)c->export_buf;
+  u8* ds = (u8*)(dd + n);
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(ds, disparity, n, cudaMemcpyHostToDevice, s));
+  depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ds, dd, n, fB);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(depth, dd, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
 extern "C" int gsm_set_rectification(gsm_ctx* c, const float* mxl, const float* myl, const float* mxr, const float* myr,
                                      int rows, int cols) {
   if (!c) return fail(GSM_ERR_INVALID, "null ctx");

@@ -240,6 +240,14 @@ __global__ void cvtcolor_kernel(const u8* __restrict__ src3, u8* __restrict__ ds
   }
 }
 
+// depth = f*B / d for a rectified rig (Q matrix of stereoRectify, Utility.cpp:228-234); 0 where d == 0
+__global__ void depth_kernel(const u8* __restrict__ disp, float* __restrict__ depth, size_t n, float fB) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = disp[i];
+  depth[i] = d ? __fdiv_rn(fB, (float)d) : 0.f;
+}
+
 // FFMA + IADD3 issue-peak probe (roofline denominator for the ALU-bound fused kernels)
 __global__ void __launch_bounds__(256) alu_peak_kernel(u32* out, int iters) {
   float f[8];

@@ -65,6 +65,7 @@ SYMBOLS = {
     "gsm_lr_check": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_remap": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_cvtcolor": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "gsm_disparity_to_depth": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float]),
     "gsm_set_rectification": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_launch_count": (C.c_longlong, [_P]),
     "gsm_set_kernel_timing": (C.c_int, [_P, C.c_int]),

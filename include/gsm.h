@@ -175,6 +175,11 @@ int gsm_remap(gsm_ctx* ctx, const uint8_t* src, const float* mapx, const float* 
  * Utility.cpp:289-298). */
 int gsm_cvtcolor(gsm_ctx* ctx, const uint8_t* src3, uint8_t* dst, int rows, int cols, int truncate);
 
+/* depth(r,c) = fB / disparity(r,c), float32; 0 where the disparity is 0 (occluded / no match).  fB = focal length in
+ * pixels x baseline: the depth the Q matrix of stereoRectify gives for a rectified rig (Utility.cpp:228-234).  Host
+ * pointers.  SURVEY 8(f) row 3. */
+int gsm_disparity_to_depth(gsm_ctx* ctx, const uint8_t* disparity, float* depth, int rows, int cols, float fB);
+
 /* Rectification maps for gsm_params.rectify (float32 rows x cols each, host pointers; copied to the device).  They
  * are what Rectify() builds (initUndistortRectifyMap CV_32FC1, Utility.cpp:228-234); sampling follows gsm_remap.
  * Pass NULL maps to drop them. */

@@ -24,15 +24,37 @@ inline gsm_ctx*& shared_ctx() {
   static gsm_ctx* ctx = nullptr;
   return ctx;
 }
+struct Config {
+  int device = 0;                      // CUDA device of the shared context
+  int min_rows = 1080, min_cols = 1920;  // capacity the context is created with at least (it grows on demand)
+  int cap_rows = 0, cap_cols = 0;
+};
+inline Config& config() {
+  static Config cfg;
+  return cfg;
+}
+// Select the GPU (and the initial capacity) the wrappers run on; takes effect on the next call.  The reference always
+// runs on the current CUDA device (it never calls cudaSetDevice).
+inline void set_device(int device, int min_rows = 1080, int min_cols = 1920) {
+  Config& cfg = config();
+  if (device != cfg.device && shared_ctx()) {
+    gsm_destroy(shared_ctx());
+    shared_ctx() = nullptr;
+    cfg.cap_rows = cfg.cap_cols = 0;
+  }
+  cfg.device = device;
+  cfg.min_rows = min_rows;
+  cfg.min_cols = min_cols;
+}
 inline gsm_ctx* ctx_for(int rows, int cols) {
-  static int cap_rows = 0, cap_cols = 0;
+  Config& cfg = config();
   gsm_ctx*& ctx = shared_ctx();
-  if (!ctx || rows > cap_rows || cols > cap_cols) {
+  if (!ctx || rows > cfg.cap_rows || cols > cfg.cap_cols) {
     if (ctx) gsm_destroy(ctx);
     ctx = nullptr;
-    cap_rows = rows > 1080 ? rows : 1080;
-    cap_cols = cols > 1920 ? cols : 1920;
-    if (gsm_create(&ctx, 0, cap_rows, cap_cols, 256, 1) != GSM_OK) {
+    cfg.cap_rows = rows > cfg.min_rows ? rows : cfg.min_rows;
+    cfg.cap_cols = cols > cfg.min_cols ? cols : cfg.min_cols;
+    if (gsm_create(&ctx, cfg.device, cfg.cap_rows, cfg.cap_cols, 256, 1) != GSM_OK) {
       std::fprintf(stderr, "gsm_compat: %s\n", gsm_last_error());
       std::abort();  // the reference has no error path either; failing loudly beats silent garbage
     }
@@ -118,6 +140,19 @@ inline void remap_gpu(cv::Mat& left, cv::Mat& right, cv::Mat& mapX1, cv::Mat& ma
                       int rows, int cols, int total, unsigned char* result) {
   gsm_compat::remap_gpu<cv::Mat>(left, right, mapX1, mapY1, mapX2, mapY2, rows, cols, total, result);
 }
+// cvtColor_gpu(uchar3* src, uchar* dst, int rows, int cols), Device.cuh:52 -- Caller.cpp:106 links unchanged.  uchar3 is
+// CUDA's vector type (vector_types.h); translation units without the CUDA headers define GSM_COMPAT_DEFINE_UCHAR3.
+#if defined(GSM_COMPAT_DEFINE_UCHAR3) && !defined(__VECTOR_TYPES_H__)
+struct uchar3 {
+  unsigned char x, y, z;
+};
+#define GSM_COMPAT_HAVE_UCHAR3
+#endif
+#if defined(__VECTOR_TYPES_H__) || defined(GSM_COMPAT_HAVE_UCHAR3)
+inline void cvtColor_gpu(uchar3* src, unsigned char* dst, int rows, int cols) {
+  gsm_compat::cvtColor_gpu<uchar3>(src, dst, rows, cols);
+}
+#endif
 #endif
 
 #endif  // GSM_COMPAT_HPP

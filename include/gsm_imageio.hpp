@@ -146,8 +146,11 @@ inline bool read_image(const char* path, Image& img, std::string& err) {
   return decode_png(buf, img, err);
 }
 
-// 8-bit gray exactly as cv::cvtColor(..., CV_BGR2GRAY) computes it (Caller.cpp:15-16; OpenCV 2.4 .. 4.x fixed point:
-// (R*4899 + G*9617 + B*1868 + 8192) >> 14), alpha dropped like cv::imread's default flags do.
+// 8-bit gray as cv::cvtColor(..., CV_BGR2GRAY) computes it (Caller.cpp:15-16), alpha dropped like cv::imread's default
+// flags do.  OpenCV 3.x / 4.x fixed point: (R*9798 + G*19235 + B*3735 + 16384) >> 15 -- the version the fixtures of
+// this repository were made with (cv2 4.13, tests/golden/make_fixtures.py) and pinned against them byte for byte by
+// tests/test_abi.py.  (OpenCV 2.4, which the reference linked, used 14-bit coefficients 4899 / 9617 / 1868: the two
+// differ by one grey level on ~0.06 % of the pixels; nothing in the reference pins either.)
 inline std::vector<uint8_t> to_gray(const Image& img) {
   const size_t n = (size_t)img.rows * img.cols;
   std::vector<uint8_t> g(n);
@@ -156,7 +159,7 @@ inline std::vector<uint8_t> to_gray(const Image& img) {
   } else {
     for (size_t i = 0; i < n; ++i) {
       const uint8_t* p = &img.data[i * img.channels];
-      g[i] = (uint8_t)((p[0] * 4899 + p[1] * 9617 + p[2] * 1868 + 8192) >> 14);
+      g[i] = (uint8_t)((p[0] * 9798 + p[1] * 19235 + p[2] * 3735 + 16384) >> 15);
     }
   }
   return g;

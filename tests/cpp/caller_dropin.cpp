@@ -3,13 +3,16 @@
 // followed by the reference's own acceptance hook compareDisp (BlockMatching.cpp:278-293; commented out at
 // Device.cu:296-297) when the test links oracle/_ref/libref.so (-DWITH_REF).  compareDisp prints one block
 // per mismatching pixel and nothing when GPU == CPU.
-//   usage: caller_dropin left.gray right.gray rows cols [radius=5] [searchRange=64] [out.gray]
+// With an eighth argument it also calls ::cvtColor_gpu((uchar3*)..., gray, rows, cols) exactly like Caller.cpp:106 on a
+// 3-channel image built from the two inputs and writes the gray result there.
+//   usage: caller_dropin left.gray right.gray rows cols [radius=5] [searchRange=64] [out.gray] [cvt_out.gray]
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
 #include "cvshim.hpp"  // stands in for <opencv2/core/core.hpp> in this repository's tests
 #define GSM_COMPAT_REFERENCE_NAMES
+#define GSM_COMPAT_DEFINE_UCHAR3  // this translation unit has no CUDA headers: the wrapper brings its own uchar3
 #include "gsm_compat.hpp"
 
 using namespace cv;
@@ -33,6 +36,7 @@ int main(int argc, char** argv) {
   const int radius = argc > 5 ? std::atoi(argv[5]) : 5, range = argc > 6 ? std::atoi(argv[6]) : 64;
   std::vector<uchar> l = slurp(argv[1], (size_t)rows * cols), r = slurp(argv[2], (size_t)rows * cols);
   Mat g1(rows, cols, CV_8UC1, l.data()), g2(rows, cols, CV_8UC1, r.data()), disp;
+  gsm_compat::set_device(0);                       // the wrappers run on a selectable GPU (default 0)
   blockMatching_gpu(g1, g2, disp, radius, range);  // Caller.cpp:19
   std::printf("GPU_DONE %d %d\n", disp.rows, disp.cols);
   std::fflush(stdout);
@@ -43,6 +47,14 @@ int main(int argc, char** argv) {
   if (argc > 7) {
     FILE* f = std::fopen(argv[7], "wb");
     std::fwrite(disp.data, 1, (size_t)rows * cols, f);
+    std::fclose(f);
+  }
+  if (argc > 8) {
+    std::vector<uchar> bgr((size_t)3 * rows * cols), gray((size_t)rows * cols);
+    for (size_t i = 0; i < (size_t)rows * cols; ++i) { bgr[3 * i] = l[i]; bgr[3 * i + 1] = r[i]; bgr[3 * i + 2] = (uchar)(l[i] ^ r[i]); }
+    cvtColor_gpu((uchar3*)bgr.data(), gray.data(), rows, cols);  // Caller.cpp:106, reference name and signature
+    FILE* f = std::fopen(argv[8], "wb");
+    std::fwrite(gray.data(), 1, gray.size(), f);
     std::fclose(f);
   }
   return 0;

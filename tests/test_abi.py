@@ -95,3 +95,31 @@ def test_header_is_valid_c_and_runs(tmp_path):
     assert run.returncode == 0, run.stdout + run.stderr
     assert "sm_100a" in run.stdout
     assert ("no device" in run.stdout and "no CPU fallback" in run.stdout) or "ok " in run.stdout
+
+
+def _read_pgm(path):
+    raw = open(path, "rb").read()
+    assert raw[:2] == b"P5"
+    parts = raw.split(b"\n", 3)
+    w, h = [int(x) for x in parts[1].split()]
+    return np.frombuffer(parts[3], np.uint8, w * h).reshape(h, w)
+
+
+def test_caller_decodes_the_demo_pair_like_opencv(tmp_path):
+    """Host side of the GUI-free singleFrame (Caller.cpp:12-16: imread + cvtColor BGR2GRAY): the built-in PNG decoder
+    and the fixed-point gray conversion reproduce, byte for byte, the grays cv2 made from the same files
+    (tests/golden/make_fixtures.py -> middlebury_gray.npz ArtDemo_L / ArtDemo_R).  No GPU involved."""
+    exe = os.path.join(ROOT, "gpu_stereo_matching_b200", "gsm_caller")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "gpu_stereo_matching_b200", "csrc")], check=True, capture_output=True)
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "middlebury_gray.npz"))
+    for name, key in (("view1_.png", "ArtDemo_L"), ("view5_.png", "ArtDemo_R")):
+        out = tmp_path / (name + ".pgm")
+        subprocess.run([exe, "gray", os.path.join(ROOT, "tests", "golden", "art_demo", name), str(out)], check=True)
+        assert np.array_equal(_read_pgm(out), fx[key]), name
+    # PNG written by the front-end decodes back to the same bytes
+    png = tmp_path / "g.png"
+    subprocess.run([exe, "gray", os.path.join(ROOT, "tests", "golden", "art_demo", "view1_.png"), str(png)], check=True)
+    pgm = tmp_path / "g.pgm"
+    subprocess.run([exe, "gray", str(png), str(pgm)], check=True)
+    assert np.array_equal(_read_pgm(pgm), fx["ArtDemo_L"])

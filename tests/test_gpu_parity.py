@@ -126,13 +126,95 @@ def test_reference_caller_dropin(ctx, fx, tmp_path):
     L, R = fx["ArtDemo_L"], fx["ArtDemo_R"]  # the 320x256 pair Caller.cpp:12-13 loads
     L.tofile(tmp_path / "l.gray"); R.tofile(tmp_path / "r.gray")
     out = subprocess.run([str(exe), str(tmp_path / "l.gray"), str(tmp_path / "r.gray"), "256", "320", "5", "64",
-                          str(tmp_path / "d.gray")], capture_output=True, text=True, check=True)
+                          str(tmp_path / "d.gray"), str(tmp_path / "cvt.gray")], capture_output=True, text=True, check=True)
     assert "GPU_DONE 256 320" in out.stdout
     if with_ref:
         tail = out.stdout.split("GPU_DONE 256 320\n", 1)[1]
         assert "CPU =" not in tail and "[" not in tail, tail[:400]  # compareDisp printed no mismatch
     d = np.fromfile(tmp_path / "d.gray", np.uint8).reshape(256, 320)
     assert np.array_equal(d, ctx.block_matching(L, R, 5, 64))
+    # ::cvtColor_gpu(uchar3*, uchar*, int, int) under its reference name (Device.cuh:52, call site Caller.cpp:106)
+    from oracle import oracle as O
+    bgr = np.stack([L, R, L ^ R], -1)
+    assert np.array_equal(np.fromfile(tmp_path / "cvt.gray", np.uint8).reshape(256, 320), O.cvtcolor(bgr))
+
+
+def _read_pgm(path):
+    raw = open(path, "rb").read()
+    parts = raw.split(b"\n", 3)
+    w, h = [int(x) for x in parts[1].split()]
+    return np.frombuffer(parts[3], np.uint8, w * h).reshape(h, w)
+
+
+def _write_pnm(path, a):
+    with open(path, "wb") as f:
+        f.write((b"P5" if a.ndim == 2 else b"P6") + b"\n%d %d\n255\n" % (a.shape[1], a.shape[0]))
+        f.write(np.ascontiguousarray(a).tobytes())
+
+
+def test_caller_frontend_from_disk(ctx, fx, orc, tmp_path):
+    """SURVEY 8(f) row 3, the GUI-free replacement of Caller.cpp / Main.cpp: singleFrame on the reference's demo pair
+    read from disk (then the reference's own compareDisp prints nothing), remapTest, cvtColorTest, depth, and the batch
+    front-end on the nine Middlebury sets -- files in, files out, no imshow / waitKey."""
+    inc, shim = os.path.join(ROOT, "include"), os.path.join(ROOT, "oracle", "shim")
+    libdir = os.path.join(ROOT, "gpu_stereo_matching_b200")
+    exe = tmp_path / "caller_files"
+    cmd = ["g++", "-O1", "-std=c++14", "-I", inc, "-I", shim, os.path.join(ROOT, "tests", "cpp", "caller_files.cpp"),
+           "-o", str(exe), "-L", libdir, "-lgsm", "-lz", "-Wl,-rpath," + libdir]
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    with_ref = os.path.exists(os.path.join(ref, "libref.so"))
+    if with_ref:
+        cmd += ["-DWITH_REF", "-L", ref, "-lref", "-Wl,-rpath," + ref]
+    subprocess.run(cmd, check=True)
+    art = os.path.join(ROOT, "tests", "golden", "art_demo")
+    out = subprocess.run([str(exe), os.path.join(art, "view1_.png"), os.path.join(art, "view5_.png"),
+                          str(tmp_path / "disp.pgm")], capture_output=True, text=True, check=True)
+    assert "GPU_DONE 256 320" in out.stdout
+    if with_ref:
+        tail = out.stdout.split("GPU_DONE 256 320\n", 1)[1]
+        assert "COMPARE_DONE" in tail and "CPU =" not in tail and "[" not in tail, tail[:400]
+    d = _read_pgm(tmp_path / "disp.pgm")
+    assert np.array_equal(d, orc.sad_wta(fx["ArtDemo_L"], fx["ArtDemo_R"], 5, 64))
+    # the CLI: guided filter + LR + median on the same files, PNG out
+    cli = os.path.join(libdir, "gsm_caller")
+    subprocess.run([cli, "singleFrame", os.path.join(art, "view1_.png"), os.path.join(art, "view5_.png"),
+                    str(tmp_path / "gf.pgm"), "--gf", "9", "--disp", "64", "--lr", "--median", "3", "--mask",
+                    str(tmp_path / "mask.pgm")], check=True, capture_output=True)
+    dref, mref = ctx.stereo_batch(fx["ArtDemo_L"], fx["ArtDemo_R"], g.make_params("gf", 9, 64, lr_check=True, median_radius=3))
+    assert np.array_equal(_read_pgm(tmp_path / "gf.pgm"), dref) and np.array_equal(_read_pgm(tmp_path / "mask.pgm"), mref)
+    # remapTest (Caller.cpp:27-74) at its 320x200 size with the rig's maps, cvtColorTest (Caller.cpp:76-112)
+    rng = np.random.default_rng(5)
+    gl, gr = rng.integers(0, 256, (200, 320), dtype=np.uint8), rng.integers(0, 256, (200, 320), dtype=np.uint8)
+    maps = gdata.rectify_maps(320, 200)
+    _write_pnm(tmp_path / "l.pgm", gl); _write_pnm(tmp_path / "r.pgm", gr)
+    np.concatenate([m.astype(np.float32).reshape(-1) for m in maps]).tofile(tmp_path / "maps.f32")
+    subprocess.run([cli, "remapTest", str(tmp_path / "l.pgm"), str(tmp_path / "r.pgm"), str(tmp_path / "maps.f32"),
+                    str(tmp_path / "ol.pgm"), str(tmp_path / "or.pgm")], check=True)
+    assert np.array_equal(_read_pgm(tmp_path / "ol.pgm"), orc.remap(gl, maps[0], maps[1]))
+    assert np.array_equal(_read_pgm(tmp_path / "or.pgm"), orc.remap(gr, maps[2], maps[3]))
+    rgb = rng.integers(0, 256, (200, 320, 3), dtype=np.uint8)
+    _write_pnm(tmp_path / "c.ppm", rgb)
+    subprocess.run([cli, "cvtColorTest", str(tmp_path / "c.ppm"), str(tmp_path / "g.pgm")], check=True)
+    assert np.array_equal(_read_pgm(tmp_path / "g.pgm"), orc.cvtcolor(rgb))
+    subprocess.run([cli, "cvtColorTest", str(tmp_path / "c.ppm"), str(tmp_path / "gt.pgm"), "--truncate"], check=True)
+    assert np.array_equal(_read_pgm(tmp_path / "gt.pgm"), orc.cvtcolor(rgb, True))
+    # depth = f*B/d (Q of stereoRectify, Utility.cpp:228-234): IEEE float32 division, 0 where d == 0
+    fB = np.float32(52554.0)
+    subprocess.run([cli, "depth", str(tmp_path / "disp.pgm"), "52554", str(tmp_path / "depth.f32")], check=True)
+    depth = np.fromfile(tmp_path / "depth.f32", np.float32).reshape(d.shape)
+    with np.errstate(divide="ignore"):
+        want = np.where(d > 0, fB / d.astype(np.float32), np.float32(0)).astype(np.float32)
+    assert np.array_equal(depth, want)
+    assert np.array_equal(ctx.disparity_to_depth(d, 52554.0), want)
+    # batch front-end: the nine sets (three sizes) from a list file, one mixed-size batch
+    lines = []
+    for s_ in SETS:
+        _write_pnm(tmp_path / f"{s_}_l.pgm", fx[s_ + "_L"]); _write_pnm(tmp_path / f"{s_}_r.pgm", fx[s_ + "_R"])
+        lines.append(f"{tmp_path / (s_ + '_l.pgm')} {tmp_path / (s_ + '_r.pgm')} {tmp_path / (s_ + '_d.pgm')}")
+    (tmp_path / "list.txt").write_text("\n".join(lines) + "\n")
+    subprocess.run([cli, "batch", str(tmp_path / "list.txt"), "--radius", "5", "--disp", "64"], check=True, capture_output=True)
+    for s_ in SETS:
+        assert np.array_equal(_read_pgm(tmp_path / f"{s_}_d.pgm"), orc.sad_wta(fx[s_ + "_L"], fx[s_ + "_R"], 5, 64)), s_
 
 
 # ------------------------------------------------------------------------------------------ post filters
