@@ -268,7 +268,7 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
     barrier per frame in a stream of frames.  Speed-up is against the same process's single-GPU pass with ITS best
     (automatic) row bands; the map is checked bit for bit against the single-GPU pass with the SAME row bands and
     against the NCCL all-reduce combine."""
-    from gpu_stereo_matching_b200.dist import (PeerPlanes, dsplit_row_bands, dsplit_stereo, dsplit_stereo_p2p,
+    from gpu_stereo_matching_b200.dist import (DsplitStream, PeerPlanes, dsplit_row_bands, dsplit_stereo,
                                               torch_stream_handle)
     h, w, d = 2160, 3840, 256
     path = "/tmp/gsm_bench_c5_pair.npz"
@@ -297,11 +297,13 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
 
     rec = {"workload": "config5: one synthetic 3840x2160 pair, 256 disparities, GF r=9, split by disparity range",
            "row_bands": bands, "steps": steps}
-    planes, combine = None, "nccl all-reduce(MIN) of the int64 packed (cost,d) plane"
+    planes, pipe, combine = None, None, "nccl all-reduce(MIN) of the int64 packed (cost,d) plane"
     try:
-        planes = PeerPlanes(h * w, views=1, slots=2)
+        planes = PeerPlanes(h * w, views=1, slots=3)
+        pipe = DsplitStream(ctx, partial, planes, p, stream, torch.cuda.Stream())
         combine = ("peer memory over NVLink: reduce-scatter + finalize + all-gather of the u8 map in one kernel "
-                   "(gsm_reduce_keys_p2p), one cross-rank barrier per frame")
+                   "(gsm_reduce_keys_p2p) on a second stream, overlapping the next frame's kernels; one cross-rank "
+                   "barrier per frame (dist.DsplitStream)")
     except Exception as e:  # noqa: BLE001
         rec["peer_memory_unavailable"] = f"{type(e).__name__}: {e}"
     kl = torch.empty(h * w, dtype=torch.int64, device="cuda")
@@ -312,14 +314,16 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
                       kl, None, p, world, rank)
 
     def run(nsteps):
-        res = None
-        for i in range(nsteps):
-            if planes is not None:
-                res = dsplit_stereo_p2p(ctx, partial, planes, p, sh, final_barrier=(i == nsteps - 1))
-            else:
-                nccl_step()
-                res = Dn
-        return res
+        """a stream of nsteps frames; returns the last frame's map (complete on every rank when the stream ends)"""
+        if pipe is not None:
+            last = None
+            for _ in range(nsteps):
+                last = pipe.submit()
+            pipe.flush()
+            return pipe.result(last)
+        for _ in range(nsteps):
+            nccl_step()
+        return Dn
 
     def sync_all():
         torch.cuda.synchronize()

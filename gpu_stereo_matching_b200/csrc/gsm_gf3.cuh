@@ -139,6 +139,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   int H = g.pg.H, W = g.pg.W;
   size_t koff = (size_t)frame * H * W;
   if (g.ft) { const FrameDesc fd = g.ft[frame]; H = fd.H; W = fd.W; koff = (size_t)fd.off; }
+  keys += koff;  // this frame's packed-min plane
   const int pitch = g.pg.pitch;
   const int yb0 = band * g.band_rows;
   const int yb1 = min(H, yb0 + g.band_rows);
@@ -462,7 +463,7 @@ gf3_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
     }
     if (lane < K && mine != 0x7fffffff) {
       const i64 k64 = (i64)(((unsigned long long)(u32)(mine & ~31) << 32) | (u32)(d0 + (mine & 31)));
-      atomicMin(keys + koff + (size_t)y * W + x0 + lane, k64);
+      atomicMin(keys + (size_t)y * W + x0 + lane, k64);
     }
     GSM_PH(8)  // keys + WTA
   };

@@ -50,6 +50,7 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
   int H = g.pg.H, W = g.pg.W;
   size_t koff = (size_t)frame * H * W;
   if (g.ft) { const FrameDesc fd = g.ft[frame]; H = fd.H; W = fd.W; koff = (size_t)fd.off; }
+  keys += koff;  // this frame's packed-min plane
   const int pitch = g.pg.pitch;
   const int yb0 = band * g.band_rows;
   const int yb1 = min(H, yb0 + g.band_rows);
@@ -234,7 +235,7 @@ sad_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, i64* __rest
     for (int i = 0; i < 2; ++i) m[i] = (lane & 4) ? m[2 * i + 1] : m[2 * i];
     const u32 mine = (lane & 8) ? m[1] : m[0];
     if (lane < K && mine != 0xffffffffu)
-      atomicMin(keys + koff + (size_t)y * W + x0 + lane, (i64)mine);
+      atomicMin(keys + (size_t)y * W + x0 + lane, (i64)mine);
   }
 }
 

@@ -205,3 +205,70 @@ def dsplit_stereo_p2p(ctx, partial_keys: Callable, planes: PeerPlanes, params, s
     ctx.postfilter_device(planes.disp_view(slot, 0).data_ptr(), planes.disp_view(slot, 1).data_ptr() if lr else 0,
                           planes.out.data_ptr(), planes.mask.data_ptr() if lr else 0, rows, cols, params, stream_handle)
     return planes.out
+
+
+class DsplitStream:
+    """A STREAM of frames through the peer-memory disparity split with the combine off the critical path.
+
+    Two CUDA streams per rank: the compute stream runs gsm_partial_keys_device of frame k+1 while the combine stream
+    runs the cross-rank barrier and gsm_reduce_keys_p2p of frame k.  Planes and maps rotate through three slots
+    (PeerPlanes(slots=3)), so the only cross-stream waits are two frames old and never block in steady state:
+      * compute, before frame k:  "the combine stream of THIS rank has passed the barrier of frame k-2" -- every rank
+        enqueues its combine of frame k-3 before that barrier, so nobody still reads the slot frame k overwrites;
+      * combine, frame k: this rank's planes of frame k are complete -> barrier (everybody's are) -> reduce my 1/N
+        slice of all planes over NVLink, finalize, store it into every rank's map.
+    The map of frame k is complete on every rank once the barrier of frame k+1 (or flush()) has passed on the combine
+    stream.  Left view only, no post-filters (dsplit_stereo_p2p handles LR check / median per frame).
+    """
+
+    def __init__(self, ctx, partial_keys: Callable, planes: PeerPlanes, params, compute_stream, combine_stream):
+        import torch
+        if planes.slots < 3:
+            raise ValueError("DsplitStream needs PeerPlanes(slots=3)")
+        if params.lr_check or params.median_radius:
+            raise ValueError("DsplitStream combines the left view only")
+        self.ctx, self.partial, self.planes, self.params = ctx, partial_keys, planes, params
+        self.s_main, self.s_side = compute_stream, combine_stream
+        self.h_side = torch_stream_handle(combine_stream)
+        self.k = 0
+        self._torch = torch
+        self._passed = {}  # frame -> event recorded on the combine stream right after that frame's barrier
+
+    def submit(self):
+        """Enqueue one frame (partial_keys reads whatever input buffers it was bound to); returns the frame index."""
+        torch, pl, k = self._torch, self.planes, self.k
+        slot = k % pl.slots
+        d0, d1 = shard_disparities(self.params.num_disp, pl.world, pl.rank)
+        with torch.cuda.stream(self.s_main):
+            ev = self._passed.pop(k - 2, None)
+            if ev is not None:
+                self.s_main.wait_event(ev)
+            keys = pl.keys_view(slot, 0)
+            if d1 > d0:
+                self.partial(0, d0, d1, keys)
+            else:
+                keys.fill_(key_init(self.params.mode, self.params.radius))
+            done = torch.cuda.Event()
+            done.record(self.s_main)
+        with torch.cuda.stream(self.s_side):
+            self.s_side.wait_event(done)
+            pl.keys_h.barrier(channel=0)
+            passed = torch.cuda.Event()
+            passed.record(self.s_side)
+            self._passed[k] = passed
+            self.ctx.reduce_keys_p2p(pl.key_ptrs(slot, 0), pl.disp_ptrs(slot, 0), pl.rank, pl.npx, self.h_side)
+        self.k += 1
+        return k
+
+    def flush(self):
+        """Close the stream: after this (on the compute stream) every submitted frame's map is complete on every rank."""
+        torch, pl = self._torch, self.planes
+        with torch.cuda.stream(self.s_side):
+            pl.keys_h.barrier(channel=1)
+            ev = torch.cuda.Event()
+            ev.record(self.s_side)
+        self.s_main.wait_event(ev)
+
+    def result(self, k: int):
+        """u8 map of frame k (valid after the barrier of frame k+1 or flush(), until frame k+3 is submitted)."""
+        return self.planes.disp_view(k % self.planes.slots, 0)

@@ -812,6 +812,22 @@ def _p2p_worker(rank, world, port, out):
             ok = ok and bool(np.array_equal(disp.cpu().numpy().reshape(h, w), one))
             if kw:
                 ok = ok and bool(np.array_equal(planes.mask.cpu().numpy().reshape(h, w), mask1))
+        # the two-stream pipeline (combine of frame k overlaps the kernels of frame k+1; three plane slots)
+        from gpu_stereo_matching_b200.dist import DsplitStream
+        p = g.make_params("gf", 9, D, row_bands=bands)
+        planes3 = PeerPlanes(h * w, views=1, slots=3)
+
+        def partial3(view, d0, d1, keys):
+            c.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w,
+                                  g.make_params("gf", 9, D, row_bands=bands, d_begin=d0, d_end=d1), view, sh)
+
+        pipe = DsplitStream(c, partial3, planes3, p, st, torch.cuda.Stream())
+        frames = [pipe.submit() for _ in range(7)]
+        pipe.flush()
+        st.synchronize()
+        one, _ = c.stereo_batch(L, R, p)
+        for k in frames[-3:]:  # the three slots hold the last three frames
+            ok = ok and bool(np.array_equal(pipe.result(k).cpu().numpy().reshape(h, w), one))
         with open(out + f".{rank}", "w") as f:
             f.write("ok" if ok else "mismatch")
     finally:
