@@ -291,9 +291,9 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
     p = g.make_params("gf", 9, d, row_bands=bands)
     steps = max(args.steps, 10)
 
-    def partial(view, d0, d1, keys):
+    def partial(view, d0, d1, keys, wait_event=0):
         ctx.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w,
-                                g.make_params("gf", 9, d, row_bands=bands, d_begin=d0, d_end=d1), view, sh)
+                                g.make_params("gf", 9, d, row_bands=bands, d_begin=d0, d_end=d1), view, sh, wait_event)
 
     rec = {"workload": "config5: one synthetic 3840x2160 pair, 256 disparities, GF r=9, split by disparity range",
            "row_bands": bands, "steps": steps}

@@ -176,10 +176,14 @@ class StereoContext:
         _l.check(self._lib.gsm_sync(self._h))
 
     # ---- multi-GPU disparity split -----------------------------------------------------------
-    def partial_keys_device(self, left_ptr, right_ptr, keys_ptr, rows, cols, params: GsmParams, view=0, stream=0):
-        _l.check(self._lib.gsm_partial_keys_device(self._h, C.byref(params), view, C.c_void_p(left_ptr),
-                                                   C.c_void_p(right_ptr), C.c_void_p(keys_ptr), rows, cols,
-                                                   C.c_void_p(stream or None)))
+    def partial_keys_device(self, left_ptr, right_ptr, keys_ptr, rows, cols, params: GsmParams, view=0, stream=0,
+                            wait_event=0):
+        """gsm_partial_keys_device; with wait_event (a cudaEvent_t handle, e.g. torch.cuda.Event.cuda_event) the fused
+        kernel -- but not the disparity-independent passes in front of it -- waits for that event
+        (gsm_partial_keys_device_ex)."""
+        _l.check(self._lib.gsm_partial_keys_device_ex(self._h, C.byref(params), view, C.c_void_p(left_ptr),
+                                                      C.c_void_p(right_ptr), C.c_void_p(keys_ptr), rows, cols,
+                                                      C.c_void_p(stream or None), C.c_void_p(wait_event or None)))
 
     def finalize_keys_device(self, keys_left_ptr, keys_right_ptr, disp_ptr, mask_ptr, rows, cols, params: GsmParams,
                              stream=0):

@@ -50,6 +50,7 @@ struct gsm_ctx {
   u8 *dispA = nullptr, *dispB = nullptr, *dispC = nullptr, *dispD = nullptr, *maskD = nullptr;
   u8* dispOut = nullptr;                                          // final map of the host path before D2H
   struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
+  cudaEvent_t fused_wait = nullptr;                                // one-shot: the next fused kernel waits for it (gsm_partial_keys_device_ex)
   FrameDesc* ft_dev = nullptr;                                    // per-frame sizes of a mixed-size batch (max_batch entries)
   unsigned attr_sad[2] = {0, 0}, attr_gf[2] = {0, 0};             // radii whose kernels already carry the smem attribute
   void* export_buf = nullptr;
@@ -417,6 +418,10 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     CK(cudaGetLastError());
   }
   int rc;
+  if (c->fused_wait) {  // the disparity-independent passes above may overlap whatever records this event
+    CK(cudaStreamWaitEvent(s, c->fused_wait, 0));
+    c->fused_wait = nullptr;
+  }
   if ((rc = timing_begin(c, s))) return rc;
   switch (R) {
 #define X(r)                                                                                  \
@@ -493,6 +498,10 @@ static int run_view_keys(gsm_ctx* c, const gsm_params* p, int n, int rows, int c
   // GF: the guide pre-pass also initialises the packed-min plane (it visits every pixel anyway)
   if (p->mode == GSM_MODE_SAD && (rc = fill_keys(c, keys, npx, key_init(p), s))) return rc;
   if (p->mode == GSM_MODE_SAD) {
+    if (c->fused_wait) {
+      CK(cudaStreamWaitEvent(s, c->fused_wait, 0));
+      c->fused_wait = nullptr;
+    }
     if ((rc = timing_begin(c, s))) return rc;
     if (export_ptr)
       rc = launch_sad<true>(c, p, n, rows, cols, d_begin, d_end, view, Gp, Op, keys, s, export_ptr, ed0, end_, ft);
@@ -768,6 +777,21 @@ extern "C" int gsm_partial_keys_device(gsm_ctx* c, const gsm_params* p, int view
   c->ev_used = 0;
   return run_view_keys(c, p, 1, rows, cols, d_begin, d_end, eps, view, (const u8*)left_dev, (const u8*)right_dev,
                        (i64*)keys_dev, s);
+}
+
+// Like gsm_partial_keys_device, but the fused aggregation+WTA kernel additionally waits for `wait_event` (a
+// cudaEvent_t recorded on another stream; NULL = none).  The disparity-independent passes in front of it (plane
+// packing, guide statistics) do not wait: they overlap whatever the event marks the end of -- dist.DsplitStream uses it
+// to run them beside the previous frame's peer-memory combine, which cannot share SMs with the fused kernel (it
+// occupies every register of an SM).
+extern "C" int gsm_partial_keys_device_ex(gsm_ctx* c, const gsm_params* p, int view, const void* left_dev,
+                                          const void* right_dev, void* keys_dev, int rows, int cols, void* stream,
+                                          void* wait_event) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  c->fused_wait = (cudaEvent_t)wait_event;
+  const int rc = gsm_partial_keys_device(c, p, view, left_dev, right_dev, keys_dev, rows, cols, stream);
+  c->fused_wait = nullptr;
+  return rc;
 }
 
 extern "C" int gsm_finalize_keys_device(gsm_ctx* c, const gsm_params* p, const void* keys_left_dev,

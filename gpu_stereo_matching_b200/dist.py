@@ -215,6 +215,9 @@ class DsplitStream:
     (PeerPlanes(slots=3)), so the only cross-stream waits are two frames old and never block in steady state:
       * compute, before frame k:  "the combine stream of THIS rank has passed the barrier of frame k-2" -- every rank
         enqueues its combine of frame k-3 before that barrier, so nobody still reads the slot frame k overwrites;
+        the FUSED kernel of frame k also waits for this rank's combine of frame k-1 (partial_keys is called with that
+        event: partial_keys(view, d_begin, d_end, keys, wait_event)), because the fused kernel fills every SM's
+        register file and the two would serialise each other; plane packing and the guide statistics run beside it;
       * combine, frame k: this rank's planes of frame k are complete -> barrier (everybody's are) -> reduce my 1/N
         slice of all planes over NVLink, finalize, store it into every rank's map.
     The map of frame k is complete on every rank once the barrier of frame k+1 (or flush()) has passed on the combine
@@ -233,6 +236,7 @@ class DsplitStream:
         self.k = 0
         self._torch = torch
         self._passed = {}  # frame -> event recorded on the combine stream right after that frame's barrier
+        self._combined = None  # event recorded after the most recent combine kernel
 
     def submit(self):
         """Enqueue one frame (partial_keys reads whatever input buffers it was bound to); returns the frame index."""
@@ -245,7 +249,10 @@ class DsplitStream:
                 self.s_main.wait_event(ev)
             keys = pl.keys_view(slot, 0)
             if d1 > d0:
-                self.partial(0, d0, d1, keys)
+                # the fused kernel owns every register of the SMs it runs on, so it cannot share them with the
+                # previous frame's combine: it waits for that combine, the passes in front of it run beside it
+                prev = self._combined
+                self.partial(0, d0, d1, keys, prev.cuda_event if prev is not None else 0)
             else:
                 keys.fill_(key_init(self.params.mode, self.params.radius))
             done = torch.cuda.Event()
@@ -257,6 +264,8 @@ class DsplitStream:
             passed.record(self.s_side)
             self._passed[k] = passed
             self.ctx.reduce_keys_p2p(pl.key_ptrs(slot, 0), pl.disp_ptrs(slot, 0), pl.rank, pl.npx, self.h_side)
+            self._combined = torch.cuda.Event()
+            self._combined.record(self.s_side)
         self.k += 1
         return k
 

@@ -127,6 +127,13 @@ int gsm_sync(gsm_ctx* ctx);
  * view: 0 = left disparity, 1 = right-view disparity (for the LR check). */
 int gsm_partial_keys_device(gsm_ctx* ctx, const gsm_params* p, int view, const void* left_dev,
                             const void* right_dev, void* keys_dev, int rows, int cols, void* stream);
+/* Same, but the fused kernel also waits for wait_event (a cudaEvent_t recorded on another stream, NULL = none) while
+ * the disparity-independent passes in front of it (plane packing, guide statistics) do not: a caller overlaps them
+ * with work on another stream that must not share SMs with the fused kernel, e.g. the previous frame's
+ * gsm_reduce_keys_p2p (gpu_stereo_matching_b200/dist.py: DsplitStream). */
+int gsm_partial_keys_device_ex(gsm_ctx* ctx, const gsm_params* p, int view, const void* left_dev,
+                               const void* right_dev, void* keys_dev, int rows, int cols, void* stream,
+                               void* wait_event);
 /* keys -> u8 disparity (+ optional median / LR check against keys_right_dev, may be NULL). */
 int gsm_finalize_keys_device(gsm_ctx* ctx, const gsm_params* p, const void* keys_left_dev,
                              const void* keys_right_dev, void* disparity_dev, void* mask_dev, int rows,

@@ -817,9 +817,9 @@ def _p2p_worker(rank, world, port, out):
         p = g.make_params("gf", 9, D, row_bands=bands)
         planes3 = PeerPlanes(h * w, views=1, slots=3)
 
-        def partial3(view, d0, d1, keys):
+        def partial3(view, d0, d1, keys, wait_event=0):
             c.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w,
-                                  g.make_params("gf", 9, D, row_bands=bands, d_begin=d0, d_end=d1), view, sh)
+                                  g.make_params("gf", 9, D, row_bands=bands, d_begin=d0, d_end=d1), view, sh, wait_event)
 
         pipe = DsplitStream(c, partial3, planes3, p, st, torch.cuda.Stream())
         frames = [pipe.submit() for _ in range(7)]
