@@ -845,8 +845,8 @@ extern "C" int gsm_reduce_keys_p2p(gsm_ctx* c, const void* const* key_ptrs, void
   CK(cudaSetDevice(c->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
   if (end > begin) {
-    const size_t groups = (end - begin + 15) / 16;
-    const unsigned blocks = (unsigned)std::min<size_t>((groups + 255) / 256, 148 * 8);
+    const size_t chunks = (end - begin + 511) / 512;  // one warp per 512-pixel chunk, eight warps per block
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((chunks + 7) / 8, 148 * 8));
     reduce_keys_p2p_kernel<<<blocks, 256, 0, s>>>(pp, world, rank, begin, end);
     c->launches++;
     CK(cudaGetLastError());

@@ -84,41 +84,60 @@ __global__ void finalize_keys_kernel(const i64* __restrict__ keys, u8* __restric
 // planes with a signed 64-bit min (order of (cost, d), ties to the lowest d), turns the winners into disparities
 // and stores the slice into every rank's map: reduce-scatter, finalize and all-gather of the u8 result in one
 // pass that moves 8 B/pixel/rank in and 1 B/pixel/rank out instead of an all-reduce of the 8-byte planes.
-// 16 pixels per thread and iteration: one 128-byte run of keys per peer (8 x LDG.128), one 16-byte store per peer.
 constexpr int P2P_MAX_RANKS = 16;
 struct PeerPlanes {
   const i64* keys[P2P_MAX_RANKS];
   u8* disp[P2P_MAX_RANKS];
 };
+// A warp reduces chunks of 512 pixels: every load instruction of the warp covers 512 contiguous bytes of ONE plane
+// (whole 128-byte lines over NVLink instead of 32 scattered 16-byte pieces), the next peer's eight vectors are in
+// flight while the current peer's are reduced, the 512 winners are transposed through 512 bytes of shared memory so
+// that every lane stores 16 contiguous bytes per map.
 __global__ void __launch_bounds__(256)
 reduce_keys_p2p_kernel(PeerPlanes pp, int world, int rank, size_t begin, size_t end) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x * 16;
-  size_t i = begin + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  for (; i + 16 <= end; i += stride) {
-    longlong2 m[8];
+  __shared__ __align__(16) u8 tr[8][512];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const size_t nwarps = (size_t)gridDim.x * 8;
+  const size_t nchunks = (end - begin) / 512;
+  for (size_t ch = (size_t)blockIdx.x * 8 + wib; ch < nchunks; ch += nwarps) {
+    const size_t base = begin + ch * 512;
+    longlong2 m[8], nx[8];
+    const longlong2* own = reinterpret_cast<const longlong2*>(pp.keys[rank] + base) + lane;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = reinterpret_cast<const longlong2*>(pp.keys[rank] + i)[j];
-    for (int w = 1; w < world; ++w) {
-      const i64* src = pp.keys[(rank + w) % world] + i;  // every rank starts on a different peer
+    for (int j = 0; j < 8; ++j) m[j] = own[32 * j];
+    if (world > 1) {
+      const longlong2* src = reinterpret_cast<const longlong2*>(pp.keys[(rank + 1) % world] + base) + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nx[j] = src[32 * j];
+    }
+    for (int w = 1; w < world; ++w) {  // every rank starts on a different peer
+      longlong2 cur[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nx[j];
+      if (w + 1 < world) {
+        const longlong2* src = reinterpret_cast<const longlong2*>(pp.keys[(rank + w + 1) % world] + base) + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nx[j] = src[32 * j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const longlong2 v = reinterpret_cast<const longlong2*>(src)[j];
-        m[j].x = min(m[j].x, v.x);
-        m[j].y = min(m[j].y, v.y);
+        m[j].x = min(m[j].x, cur[j].x);
+        m[j].y = min(m[j].y, cur[j].y);
       }
     }
-    u32 o[4];
+    // lane l holds pixels 64 j + 2 l, + 1: transpose to 16 contiguous pixels per lane
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      o[q] = (u32)(m[2 * q].x & 0xff) | ((u32)(m[2 * q].y & 0xff) << 8) | ((u32)(m[2 * q + 1].x & 0xff) << 16) |
-             ((u32)(m[2 * q + 1].y & 0xff) << 24);
-    const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
-    for (int w = 0; w < world; ++w) *reinterpret_cast<uint4*>(pp.disp[(rank + w) % world] + i) = ov;
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<unsigned short*>(&tr[wib][64 * j + 2 * lane]) =
+          (unsigned short)((u32)(m[j].x & 0xff) | ((u32)(m[j].y & 0xff) << 8));
+    __syncwarp();
+    const uint4 ov = *reinterpret_cast<const uint4*>(&tr[wib][16 * lane]);
+    __syncwarp();
+    for (int w = 0; w < world; ++w) *reinterpret_cast<uint4*>(pp.disp[(rank + w) % world] + base + 16 * lane) = ov;
   }
-  // tail of a slice whose length is not a multiple of 16 (only the last rank's can be)
+  // tail of a slice whose length is not a multiple of 512
   if (blockIdx.x == 0) {
-    const size_t t0 = begin + (end - begin) / 16 * 16;
-    for (size_t k = t0 + threadIdx.x; k < end; k += blockDim.x) {
+    for (size_t k = begin + nchunks * 512 + threadIdx.x; k < end; k += blockDim.x) {
       i64 mk = pp.keys[rank][k];
       for (int w = 1; w < world; ++w) mk = min(mk, pp.keys[(rank + w) % world][k]);
       for (int w = 0; w < world; ++w) pp.disp[w][k] = (u8)(mk & 0xff);
