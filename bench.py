@@ -300,7 +300,7 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
     planes, pipe, combine = None, None, "nccl all-reduce(MIN) of the int64 packed (cost,d) plane"
     try:
         planes = PeerPlanes(h * w, views=1, slots=3)
-        pipe = DsplitStream(ctx, partial, planes, p, stream, torch.cuda.Stream())
+        pipe = DsplitStream(ctx, partial, planes, p, stream, torch.cuda.Stream(), timing=True)
         combine = ("peer memory over NVLink: reduce-scatter + finalize + all-gather of the u8 map in one kernel "
                    "(gsm_reduce_keys_p2p) on a second stream, overlapping the next frame's kernels; one cross-rank "
                    "barrier per frame (dist.DsplitStream)")
@@ -341,6 +341,7 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
     sync_all()
     ms_n = e0.elapsed_time(e1) / steps
     map_n = res.clone()
+    bar_ms, red_ms = pipe.stats(skip=6) if pipe is not None else (None, None)  # the timed frames only
     # the same GPU alone: full disparity range, automatic bands (its best) and the split's bands (for bit-identity)
     Dd1 = torch.empty(h * w, dtype=torch.uint8, device="cuda")
     single = {}
@@ -365,8 +366,14 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
         nccl_step()
     stream.synchronize()
     same_nccl = int(torch.equal(Dn, map_n))
-    t = torch.tensor([ms_n, single["auto"], single["same_bands"]], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_n, single["auto"], single["same_bands"], bar_ms or 0.0, red_ms or 0.0], dtype=torch.float64,
+                     device="cuda")
+    tmin = t.clone()
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    bar_max, red_max = float(t[3].item()), float(t[4].item())
+    bar_min, red_min = float(tmin[3].item()), float(tmin[4].item())
+    t = t[:3]
     flags = torch.tensor([identical, same_nccl], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     ms_n, ms1_auto, ms1_same = [float(x) for x in t.tolist()]
@@ -376,6 +383,11 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
         "single_gpu_ms_auto_bands": ms1_auto, "single_gpu_ms_same_bands": ms1_same,
         "speedup_vs_single_gpu": ms1_auto / ms_n, "efficiency": ms1_auto / ms_n / world,
         "combine": combine,
+        "combine_stream_ms": {"barrier_wait_min_max_over_ranks": [bar_min, bar_max],
+                              "reduce_kernel_min_max_over_ranks": [red_min, red_max],
+                              "note": "CUDA events on the combine stream: time between this rank's planes being complete and "
+                                      "the cross-rank barrier releasing (= waiting for the slowest rank), and the "
+                                      "gsm_reduce_keys_p2p kernel (NVLink P2P loads of 7/8 of the slice, 16-byte P2P stores)"},
         "map_identical_to_single_gpu_same_bands_on_all_ranks": bool(int(flags[0].item())),
         "pixels_differing_from_single_gpu_auto_bands": diff_auto,
         "combine_check": ("peer-memory map == all-reduce map on all ranks" if int(flags[1].item()) else

@@ -224,8 +224,10 @@ class DsplitStream:
     stream.  Left view only, no post-filters (dsplit_stereo_p2p handles LR check / median per frame).
     """
 
-    def __init__(self, ctx, partial_keys: Callable, planes: PeerPlanes, params, compute_stream, combine_stream):
+    def __init__(self, ctx, partial_keys: Callable, planes: PeerPlanes, params, compute_stream, combine_stream,
+                 timing: bool = False):
         import torch
+        self.timing, self._marks = bool(timing), []
         if planes.slots < 3:
             raise ValueError("DsplitStream needs PeerPlanes(slots=3)")
         if params.lr_check or params.median_radius:
@@ -255,17 +257,19 @@ class DsplitStream:
                 self.partial(0, d0, d1, keys, prev.cuda_event if prev is not None else 0)
             else:
                 keys.fill_(key_init(self.params.mode, self.params.radius))
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=self.timing)
             done.record(self.s_main)
         with torch.cuda.stream(self.s_side):
             self.s_side.wait_event(done)
             pl.keys_h.barrier(channel=0)
-            passed = torch.cuda.Event()
+            passed = torch.cuda.Event(enable_timing=self.timing)
             passed.record(self.s_side)
             self._passed[k] = passed
             self.ctx.reduce_keys_p2p(pl.key_ptrs(slot, 0), pl.disp_ptrs(slot, 0), pl.rank, pl.npx, self.h_side)
-            self._combined = torch.cuda.Event()
+            self._combined = torch.cuda.Event(enable_timing=self.timing)
             self._combined.record(self.s_side)
+        if self.timing:
+            self._marks.append((done, passed, self._combined))
         self.k += 1
         return k
 
@@ -277,6 +281,16 @@ class DsplitStream:
             ev = torch.cuda.Event()
             ev.record(self.s_side)
         self.s_main.wait_event(ev)
+
+    def stats(self, skip: int = 3):
+        """(mean ms this rank's combine stream waited in the cross-rank barrier, mean ms of the combine kernel) over the
+        frames submitted with timing=True, the first `skip` excluded; call after the streams are synchronised."""
+        m = self._marks[skip:]
+        if not m:
+            return None, None
+        wait = sum(a.elapsed_time(b) for a, b, _ in m) / len(m)
+        red = sum(b.elapsed_time(c) for _, b, c in m) / len(m)
+        return wait, red
 
     def result(self, k: int):
         """u8 map of frame k (valid after the barrier of frame k+1 or flush(), until frame k+3 is submitted)."""
