@@ -50,6 +50,9 @@ struct gsm_ctx {
   u8 *dispA = nullptr, *dispB = nullptr, *dispC = nullptr, *dispD = nullptr, *maskD = nullptr;
   u8* dispOut = nullptr;                                          // final map of the host path before D2H
   struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
+  float* ring = nullptr;                                          // gf5_wta_kernel: per-SM rings of (a, b) rows (gsm_gf5.cuh)
+  int ring_slots = 0;                                             // == %nsmid of the device
+  size_t ring_bytes = 0;
   cudaEvent_t fused_wait = nullptr;                                // one-shot: the next fused kernel waits for it (gsm_partial_keys_device_ex)
   FrameDesc* ft_dev = nullptr;                                    // per-frame sizes of a mixed-size batch (max_batch entries)
   unsigned attr_sad[2] = {0, 0}, attr_gf[2] = {0, 0};             // radii whose kernels already carry the smem attribute
@@ -78,6 +81,14 @@ static int stage_halo_of(int /*mode*/, int radius) { return radius; }  // GF: st
 #endif
 #ifndef GSM_GF_LPR
 #define GSM_GF_LPR 32
+#endif
+#ifndef GSM_GF_RING
+#define GSM_GF_RING 0  // 0 (product): gf3_wta_kernel recomputes the leaving (a, b) row; 1 (experiment, make EXTRA=-DGSM_GF_RING=1):
+                       // gf5_wta_kernel reads it back from a per-SM ring in global memory -- parity-green but HBM-bound (the
+                       // 138 MB of rings do not stay in the 126 MB L2): profiles/experiments_r02/ab_results.txt
+#endif
+#if GSM_GF_RING
+#include "gsm_gf5.cuh"
 #endif
 static int strip_columns(int mode) { return mode == GSM_MODE_SAD ? GSM_SAD_RUNS * 16 : GSM_GF_RUNS * GSM_GF_K; }
 // left halo of a strip: a multiple of 4 >= the stage halo; a whole 16-column run when that costs no output column
@@ -110,7 +121,7 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   void* bufs[] = {c->tightL, c->tightR, c->planeL, c->planeR, c->planeLrep, c->stats[0], c->stats[1], c->keysL,
                   c->keysR,  c->dispA,  c->dispB,  c->dispC,  c->dispD,     c->maskD,    c->export_buf, c->peak_buf, c->dispOut, c->rect_maps,
-                  c->ft_dev};
+                  c->ft_dev, c->ring};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -187,6 +198,21 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
   A((void**)&c->dispOut, slot_px);
   A((void**)&c->peak_buf, (size_t)prop.multiProcessorCount * 8 * 256 * sizeof(u32));
   A((void**)&c->ft_dev, (size_t)max_batch * sizeof(FrameDesc));
+#if GSM_GF_RING
+  {
+    // one ring of (a, b) rows per SM id (gsm_gf5.cuh): ask the device how many SM ids it hands out
+    u32 nsm = 0;
+    if (st == cudaSuccess) {
+      nsmid_kernel<<<1, 1, 0, c->stream>>>(c->peak_buf);
+      st = cudaMemcpyAsync(&nsm, c->peak_buf, sizeof(u32), cudaMemcpyDeviceToHost, c->stream);
+      if (st == cudaSuccess) st = cudaStreamSynchronize(c->stream);
+      if (st == cudaSuccess) st = cudaMemsetAsync(c->peak_buf, 0, sizeof(u32), c->stream);
+    }
+    c->ring_slots = (int)std::max<u32>(nsm, (u32)prop.multiProcessorCount);
+    c->ring_bytes = (size_t)c->ring_slots * 19 * gf5_ring_row_floats(GSM_GF_RUNS, GSM_GF_K, GSM_GF_LPR) * sizeof(float);
+    A((void**)&c->ring, c->ring_bytes);
+  }
+#endif
   if (st == cudaSuccess) st = cudaStreamSynchronize(c->stream);  // every buffer is zero before the first call
   if (st != cudaSuccess) {
     int rc = fail(GSM_ERR_CUDA, "gsm_create: allocation failed: %s", cudaGetErrorString(st));
@@ -388,7 +414,11 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, stage_halo_of(GSM_MODE_GF, R), 6, HL4, lpr);
+#if GSM_GF_RING
+  pl.smem = gf5_smem_bytes(runs, K, HL4, lpr);
+#else
   pl.smem = gf3_smem_bytes(runs, K, HL4, lpr);
+#endif
   pl.g.ft = ft;
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
@@ -424,16 +454,29 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   }
   if ((rc = timing_begin(c, s))) return rc;
   switch (R) {
-#define X(r)                                                                                  \
-  case r: {                                                                                   \
-    auto kfn = GF_KERNEL<r, K, runs, lpr, EXPORT>;                                            \
-    if (!(c->attr_gf[EXPORT] >> r & 1u)) {                                                    \
-      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-      c->attr_gf[EXPORT] |= 1u << r;                                                          \
-    }                                                                                         \
-    kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                          \
-    break;                                                                                    \
+#if GSM_GF_RING
+#define X(r)                                                                                       \
+  case r: {                                                                                        \
+    auto kfn = gf5_wta_kernel<r, K, runs, lpr, EXPORT>;                                            \
+    if (!(c->attr_gf[EXPORT] >> r & 1u)) {                                                         \
+      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));    \
+      c->attr_gf[EXPORT] |= 1u << r;                                                               \
+    }                                                                                              \
+    kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, c->ring, pl.g);                      \
+    break;                                                                                         \
   }
+#else
+#define X(r)                                                                                       \
+  case r: {                                                                                        \
+    auto kfn = gf3_wta_kernel<r, K, runs, lpr, EXPORT>;                                            \
+    if (!(c->attr_gf[EXPORT] >> r & 1u)) { /* once per context and kernel, not per launch */       \
+      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));    \
+      c->attr_gf[EXPORT] |= 1u << r;                                                               \
+    }                                                                                              \
+    kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                               \
+    break;                                                                                         \
+  }
+#endif
     GF_CASES(X)
 #undef X
     default:

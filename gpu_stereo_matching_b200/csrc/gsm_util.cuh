@@ -267,6 +267,13 @@ __global__ void depth_kernel(const u8* __restrict__ disp, float* __restrict__ de
   depth[i] = d ? __fdiv_rn(fB, (float)d) : 0.f;
 }
 
+// number of SM ids the device hands out (%nsmid): sizes the per-SM rings of gsm_gf5.cuh
+__global__ void nsmid_kernel(u32* out) {
+  u32 n;
+  asm("mov.u32 %0, %%nsmid;" : "=r"(n));
+  *out = n;
+}
+
 // FFMA + IADD3 issue-peak probe (roofline denominator for the ALU-bound fused kernels)
 __global__ void __launch_bounds__(256) alu_peak_kernel(u32* out, int iters) {
   float f[8];
