@@ -130,7 +130,9 @@ gf5_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.75;" : "=l"(pol));
 #endif
   constexpr size_t ROW4 = (size_t)(TWt / 4) * LPR * 2;  // float4 per ring row
-  float4* rbase = reinterpret_cast<float4*>(ring) + (size_t)smid * RD * ROW4 + ((size_t)(run * (K / 4)) * LPR + lane) * 2;
+  // [row slot][a | b][4-column group][disparity lane]: every load / store instruction of the warp covers 512 contiguous bytes
+  float4* rbase = reinterpret_cast<float4*>(ring) + (size_t)smid * RD * ROW4 + (size_t)(run * (K / 4)) * LPR + lane;
+  constexpr size_t RB = ROW4 / 2;  // offset of the b half of a ring row
 
   const int xs = strip * g.TW - g.hl;
   const int x0 = xs + run * K;
@@ -215,8 +217,8 @@ gf5_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
     if (need_ab && has_trail) {  // issued first: an L2 round trip hides behind stage 1
 #pragma unroll
       for (int q = 0; q < K / 4; ++q) {
-        ra[q] = ld_hint(rrow + (size_t)q * LPR * 2, pol);
-        rb[q] = ld_hint(rrow + (size_t)q * LPR * 2 + 1, pol);
+        ra[q] = ld_hint(rrow + (size_t)q * LPR, pol);
+        rb[q] = ld_hint(rrow + RB + (size_t)q * LPR, pol);
       }
     }
     mbar_wait(bar0 + 8 * s, sphase);
@@ -306,8 +308,8 @@ gf5_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
             a4[j] = (float)num * idn[j];
             b4[j] = fmaf(-a4[j], cmv[j] - cc, (float)Sp[c] * inn[j]);
           }
-          st_hint(rrow + (size_t)(g4 / 4) * LPR * 2, make_float4(a4[0], a4[1], a4[2], a4[3]), pol);
-          st_hint(rrow + (size_t)(g4 / 4) * LPR * 2 + 1, make_float4(b4[0], b4[1], b4[2], b4[3]), pol);
+          st_hint(rrow + (size_t)(g4 / 4) * LPR, make_float4(a4[0], a4[1], a4[2], a4[3]), pol);
+          st_hint(rrow + RB + (size_t)(g4 / 4) * LPR, make_float4(b4[0], b4[1], b4[2], b4[3]), pol);
         }
         if (has_trail) {
           const float ta[4] = {ra[g4 / 4].x, ra[g4 / 4].y, ra[g4 / 4].z, ra[g4 / 4].w};
