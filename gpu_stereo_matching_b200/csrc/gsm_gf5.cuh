@@ -47,6 +47,9 @@ __host__ __device__ inline size_t gf5_smem_bytes(int runs, int K, int HL4, int L
 // floats of one ring row of a CTA: (a, b) x strip columns x disparities
 __host__ __device__ constexpr size_t gf5_ring_row_floats(int runs, int K, int LPR) { return (size_t)runs * K * LPR * 2; }
 
+#ifndef GSM_GF_RING_STREAM_ROWS
+#define GSM_GF_RING_STREAM_ROWS 0
+#endif
 #ifndef GSM_GF_RING_HINT
 #define GSM_GF_RING_HINT 1  // 1: per-instruction fractional evict_last policy; 0: plain accesses
 #endif
@@ -125,9 +128,12 @@ gf5_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
   // this CTA's ring: one per SM; this thread's entries: [row slot][4-column group][disparity lane][a4 | b4]
   u32 smid;
   asm("mov.u32 %0, %%smid;" : "=r"(smid));
-  unsigned long long pol = 0;
+  unsigned long long pol_keep = 0, pol_stream = 0;
 #if GSM_GF_RING_HINT
-  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, 0.75;" : "=l"(pol));
+  // GSM_GF_RING_STREAM_ROWS of the 2R+1 row slots bypass the L2 working set (evict_first), the others are kept
+  // (evict_last): the cached part of the 148 rings is sized to fit the L2, the rest streams through HBM
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 #endif
   constexpr size_t ROW4 = (size_t)(TWt / 4) * LPR * 2;  // float4 per ring row
   // [row slot][a | b][4-column group][disparity lane]: every load / store instruction of the warp covers 512 contiguous bytes
@@ -213,6 +219,7 @@ gf5_wta_kernel(const u8* __restrict__ Gp, const u8* __restrict__ Op, const float
     const int t2 = t - RD;  // the row that leaves the vertical window: its (a, b) are in ring slot rs
     const bool has_lead = t >= a0, has_trail = t2 >= a0;
     float4* rrow = rbase + (size_t)rs * ROW4;
+    const unsigned long long pol = rs < GSM_GF_RING_STREAM_ROWS ? pol_stream : pol_keep;
     float4 ra[K / 4], rb[K / 4];
     if (need_ab && has_trail) {  // issued first: an L2 round trip hides behind stage 1
 #pragma unroll
