@@ -19,7 +19,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import lib as _l
-from .lib import GSM_MODE_GF, GSM_MODE_SAD, GsmError, GsmParams  # noqa: F401
+from .lib import GSM_MODE_GF, GSM_MODE_SAD, GsmError, GsmParams, GsmStParams  # noqa: F401
 
 GF_EPS_DEFAULT = 6.5025  # 1e-4 * 255^2
 
@@ -289,6 +289,49 @@ class StereoContext:
         _l.check(self._lib.gsm_set_rectification(self._h, _ptr(maps[0]), _ptr(maps[1]), _ptr(maps[2]), _ptr(maps[3]),
                                                  rows, cols))
 
+    # ---- segment-tree stereo (STMatching) -------------------------------------
+    @staticmethod
+    def _bgr(a, name):
+        a = _u8c(a, name)
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise ValueError(f"{name}: expected [rows, cols, 3] uint8 (BGR as cv::imread gives it)")
+        return a
+
+    def segment_tree_stereo(self, left_bgr, right_bgr, num_disp: int, sigma: float = 0.1, tau: float = 1200.0,
+                            median_radius: int = 3, scale: int = 1) -> np.ndarray:
+        """== stereo_disparity_normal (STMatching/StereoDisparity.cpp:58-90): colour+gradient cost -> segment-tree
+        aggregation -> WTA -> median -> * scale; u8 [rows, cols]."""
+        L, R = self._bgr(left_bgr, "left_bgr"), self._bgr(right_bgr, "right_bgr")
+        if L.shape != R.shape:
+            raise ValueError("left / right differ in shape")
+        out = np.empty(L.shape[:2], np.uint8)
+        p = GsmStParams(int(num_disp), float(sigma), float(tau), int(median_radius), int(scale))
+        _l.check(self._lib.gsm_segment_tree_stereo(self._h, C.byref(p), _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1]))
+        return out
+
+    def st_matching_cost(self, left_bgr, right_bgr, num_disp: int) -> np.ndarray:
+        """== GetMatchingCost (StereoHelper.cpp:75-129): float32 [rows, cols, num_disp]."""
+        L, R = self._bgr(left_bgr, "left_bgr"), self._bgr(right_bgr, "right_bgr")
+        if L.shape != R.shape:
+            raise ValueError("left / right differ in shape")
+        out = np.empty(L.shape[:2] + (num_disp,), np.float32)
+        _l.check(self._lib.gsm_st_matching_cost(self._h, _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1], num_disp))
+        return out
+
+    def st_filter(self, image_bgr, cost, sigma: float = 0.1, tau: float = 1200.0):
+        """== CColorWeight + BuildSegmentTree + Filter (SegmentTree.cpp:38-195) on a float32 [rows, cols, D] volume:
+        returns (aggregated volume, order, father_id, father_dist) -- the ordered tree in breadth-first order."""
+        img = self._bgr(image_bgr, "image_bgr")
+        vol = np.ascontiguousarray(cost, np.float32).copy()
+        if vol.ndim != 3 or vol.shape[:2] != img.shape[:2]:
+            raise ValueError("cost must be [rows, cols, D] for the image's rows, cols")
+        n = img.shape[0] * img.shape[1]
+        order, father = np.empty(n, np.int32), np.empty(n, np.int32)
+        fdist = np.empty(n, np.uint8)
+        _l.check(self._lib.gsm_st_filter(self._h, _ptr(img), _ptr(vol), img.shape[0], img.shape[1], vol.shape[2],
+                                         float(sigma), float(tau), _ptr(order), _ptr(father), _ptr(fdist)))
+        return vol, order, father, fdist
+
     # ---- introspection -----------------------------------------------------------------------
     @property
     def launch_count(self) -> int:
@@ -318,6 +361,20 @@ def _ctx_for(rows: int, cols: int, num_disp: int) -> StereoContext:
             c.close()
         _default_ctx = c = StereoContext(max(rows, 1080), max(cols, 1920), 256, 1)
     return c
+
+
+def st_build_tree_host(wr, wu, tau: float = 1200.0):
+    """Host stage of the segment-tree stereo (gsm_st_build_tree_host; no GPU): u8 edge weights [rows, cols] ->
+    (order, father_id, father_dist, levels), the reference's ordered tree (CSegmentTree::m_tree)."""
+    a, b = _u8c(wr, "wr"), _u8c(wu, "wu")
+    _same_shape(2, wr=a, wu=b)
+    n = a.size
+    order, father = np.empty(n, np.int32), np.empty(n, np.int32)
+    fdist = np.empty(n, np.uint8)
+    levels = C.c_int(0)
+    _l.check(_l.load().gsm_st_build_tree_host(_ptr(a), _ptr(b), a.shape[0], a.shape[1], float(tau), _ptr(order),
+                                              _ptr(father), _ptr(fdist), C.byref(levels)))
+    return order, father, fdist, levels.value
 
 
 def blockMatching_gpu(h_left, h_right, SADWindowSize: int, searchRange: int) -> np.ndarray:

@@ -12,6 +12,8 @@
 #include "gsm_gf.cuh"
 #include "gsm_gf3.cuh"
 #include "gsm_sad.cuh"
+#include "gsm_st.cuh"
+#include "gsm_st_host.hpp"
 #include "gsm_util.cuh"
 
 using namespace gsm;
@@ -50,6 +52,9 @@ struct gsm_ctx {
   u8 *dispA = nullptr, *dispB = nullptr, *dispC = nullptr, *dispD = nullptr, *maskD = nullptr;
   u8* dispOut = nullptr;                                          // final map of the host path before D2H
   struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
+  // segment-tree stereo (gsm_st.cuh): one device arena, grown on demand
+  void* st_buf = nullptr;
+  size_t st_bytes = 0;
   float* ring = nullptr;                                          // gf5_wta_kernel: per-SM rings of (a, b) rows (gsm_gf5.cuh)
   int ring_slots = 0;                                             // == %nsmid of the device
   size_t ring_bytes = 0;
@@ -121,7 +126,7 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   void* bufs[] = {c->tightL, c->tightR, c->planeL, c->planeR, c->planeLrep, c->stats[0], c->stats[1], c->keysL,
                   c->keysR,  c->dispA,  c->dispB,  c->dispC,  c->dispD,     c->maskD,    c->export_buf, c->peak_buf, c->dispOut, c->rect_maps,
-                  c->ft_dev, c->ring};
+                  c->ft_dev, c->ring, c->st_buf};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -1118,6 +1123,194 @@ extern "C" int gsm_set_rectification(gsm_ctx* c, const float* mxl, const float* 
   CK(cudaStreamSynchronize(c->stream));  // the host maps may be freed by the caller; kernels run on other streams too
   c->rect_rows = rows;
   c->rect_cols = cols;
+  return GSM_OK;
+}
+
+
+// ---- segment-tree stereo (kernels in gsm_st.cuh, tree in gsm_st_host.hpp) --------------------------
+namespace {
+struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
+  u8 *L3, *R3, *med, *wr, *wu, *nchild, *disp, *disp2;
+  float *gL, *gR, *fw, *buf, *fin, *vol;
+  int *order, *father, *child0, *level_off, *pos;
+  size_t bytes;
+  StArena(void* base, size_t n, int D, bool with_vol) {
+    size_t o = 0;
+    auto take = [&](size_t b) { void* p = base ? (char*)base + o : nullptr; o += (b + 255) / 256 * 256; return p; };
+    L3 = (u8*)take(3 * n); R3 = (u8*)take(3 * n); med = (u8*)take(3 * n);
+    wr = (u8*)take(n); wu = (u8*)take(n); nchild = (u8*)take(n); disp = (u8*)take(n); disp2 = (u8*)take(n);
+    gL = (float*)take(4 * n); gR = (float*)take(4 * n); fw = (float*)take(4 * n);
+    order = (int*)take(4 * n); father = (int*)take(4 * n); child0 = (int*)take(4 * n); pos = (int*)take(4 * n);
+    level_off = (int*)take(4 * (n + 2));
+    buf = (float*)take(4 * n * D); fin = (float*)take(4 * n * D);
+    vol = with_vol ? (float*)take(4 * n * D) : nullptr;
+    bytes = o;
+  }
+};
+int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol) {
+  const size_t need = StArena(nullptr, n, D, with_vol).bytes;
+  if (c->st_bytes >= need) return GSM_OK;
+  if (c->st_buf) cudaFree(c->st_buf);
+  c->st_buf = nullptr;
+  c->st_bytes = 0;
+  CK(cudaMalloc(&c->st_buf, need));
+  c->st_bytes = need;
+  return GSM_OK;
+}
+int st_check(const gsm_ctx* c, int rows, int cols, int D) {
+  if (!c) return fail(GSM_ERR_INVALID, "null ctx");
+  // the reference's 3x3 median (ctmf.c:211-212) asserts on images below 3x3
+  if (rows < 3 || cols < 3) return fail(GSM_ERR_INVALID, "segment-tree stereo needs at least 3x3 pixels (got %dx%d)", rows, cols);
+  if (D < 1 || D > MAX_DISP) return fail(GSM_ERR_INVALID, "num_disp %d not in 1..256", D);
+  return GSM_OK;
+}
+// images (device, interleaved 3-channel) -> the ordered tree on the device; fills t (host) as well
+int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, float sigma, float tau, gsm_st::Tree& t,
+            StTree* dt, cudaStream_t s) {
+  const size_t n = (size_t)rows * cols;
+  const dim3 blk(128), grd((cols + 127) / 128, rows);
+  st_median3_kernel<<<grd, blk, 0, s>>>(img3, a.med, rows, cols);
+  st_edge_weight_kernel<<<grd, blk, 0, s>>>(a.med, a.wr, a.wu, rows, cols);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  std::vector<u8> wr(n), wu(n);
+  CK(cudaMemcpyAsync(wr.data(), a.wr, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(wu.data(), a.wu, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  gsm_st::build_tree(wr.data(), wu.data(), rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t);
+  float table[256];
+  gsm_st::weight_table(sigma, table);
+  std::vector<float> fw(n);
+  std::vector<int> pos(n);
+  for (size_t i = 0; i < n; ++i) { fw[i] = table[t.fdist[i]]; pos[t.order[i]] = (int)i; }
+  CK(cudaMemcpyAsync(a.order, t.order.data(), 4 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.father, t.father.data(), 4 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.child0, t.child0.data(), 4 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.nchild, t.nchild.data(), n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.fw, fw.data(), 4 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.pos, pos.data(), 4 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.level_off, t.level_off.data(), 4 * t.level_off.size(), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // the host vectors go out of scope
+  dt->father = a.father; dt->fw = a.fw; dt->child0 = a.child0; dt->nchild = a.nchild; dt->level_off = a.level_off;
+  dt->levels = (int)t.level_off.size() - 1;
+  dt->n = (int)n;
+  return GSM_OK;
+}
+}  // namespace
+
+// The host stage on its own (no GPU involved): edge weights in, ordered tree out -- what gsm_st_filter runs between its
+// two GPU stages.  wr[p] = weight of edge (p, p+1), wu[p] = weight of edge (p, p-cols) (entries of edges that do not
+// exist are ignored).
+extern "C" int gsm_st_build_tree_host(const uint8_t* wr, const uint8_t* wu, int rows, int cols, float tau, int* order,
+                                      int* father_id, uint8_t* father_dist, int* levels) {
+  if (!wr || !wu || rows < 1 || cols < 1) return fail(GSM_ERR_INVALID, "gsm_st_build_tree_host: bad arguments");
+  gsm_st::Tree t;
+  gsm_st::build_tree(wr, wu, rows, cols, tau > 0.f ? tau : 1200.f, 1.0f, t);
+  const size_t n = (size_t)rows * cols;
+  if (order) memcpy(order, t.order.data(), 4 * n);
+  if (father_id) memcpy(father_id, t.father_id.data(), 4 * n);
+  if (father_dist) memcpy(father_dist, t.fdist.data(), n);
+  if (levels) *levels = (int)t.level_off.size() - 1;
+  return GSM_OK;
+}
+
+extern "C" int gsm_st_matching_cost(gsm_ctx* c, const uint8_t* left3, const uint8_t* right3, float* cost, int rows,
+                                    int cols, int num_disp) {
+  int rc;
+  if ((rc = st_check(c, rows, cols, num_disp))) return rc;
+  if (!left3 || !right3 || !cost) return fail(GSM_ERR_INVALID, "null pointer");
+  CK(cudaSetDevice(c->device));
+  if ((rc = gsm_sync(c))) return rc;
+  const size_t n = (size_t)rows * cols;
+  if ((rc = st_reserve(c, n, num_disp, true))) return rc;
+  const StArena a(c->st_buf, n, num_disp, true);
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(a.L3, left3, 3 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.R3, right3, 3 * n, cudaMemcpyHostToDevice, s));
+  const dim3 blk(128), grd((cols + 127) / 128, rows);
+  st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
+  st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.R3, a.gR, rows, cols);
+  st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.vol, nullptr, 0, rows, cols, num_disp);
+  c->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(cost, a.vol, 4 * n * num_disp, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+extern "C" int gsm_st_filter(gsm_ctx* c, const uint8_t* image3, float* cost, int rows, int cols, int num_disp,
+                             float sigma, float tau, int* order, int* father_id, uint8_t* father_dist) {
+  int rc;
+  if ((rc = st_check(c, rows, cols, num_disp))) return rc;
+  if (!image3) return fail(GSM_ERR_INVALID, "null pointer");
+  CK(cudaSetDevice(c->device));
+  if ((rc = gsm_sync(c))) return rc;
+  const size_t n = (size_t)rows * cols;
+  if ((rc = st_reserve(c, n, num_disp, true))) return rc;
+  const StArena a(c->st_buf, n, num_disp, true);
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(a.L3, image3, 3 * n, cudaMemcpyHostToDevice, s));
+  gsm_st::Tree t;
+  StTree dt;
+  if ((rc = st_tree(c, a, a.L3, rows, cols, sigma, tau, t, &dt, s))) return rc;
+  if (order) memcpy(order, t.order.data(), 4 * n);
+  if (father_id) memcpy(father_id, t.father_id.data(), 4 * n);
+  if (father_dist) memcpy(father_dist, t.fdist.data(), n);
+  if (cost) {
+    CK(cudaMemcpyAsync(a.vol, cost, 4 * n * num_disp, cudaMemcpyHostToDevice, s));
+    const dim3 g2((unsigned)((n + 255) / 256), num_disp);
+    st_permute_kernel<<<g2, 256, 0, s>>>(a.vol, a.order, a.buf, (int)n, num_disp);
+    st_filter_kernel<<<num_disp, 256, 0, s>>>(a.buf, a.fin, dt);
+    st_unpermute_kernel<<<g2, 256, 0, s>>>(a.fin, a.order, a.vol, (int)n, num_disp);
+    c->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cost, a.vol, 4 * n * num_disp, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return GSM_OK;
+}
+
+extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const uint8_t* left3, const uint8_t* right3,
+                                       uint8_t* disparity, int rows, int cols) {
+  if (!p) return fail(GSM_ERR_INVALID, "null params");
+  int rc;
+  if ((rc = st_check(c, rows, cols, p->num_disp))) return rc;
+  if (!left3 || !right3 || !disparity) return fail(GSM_ERR_INVALID, "null pointer");
+  if (p->median_radius < 0 || p->median_radius > MED_MAXR) return fail(GSM_ERR_INVALID, "median_radius %d", p->median_radius);
+  if (p->scale < 1) return fail(GSM_ERR_INVALID, "scale %d", p->scale);
+  CK(cudaSetDevice(c->device));
+  if ((rc = gsm_sync(c))) return rc;
+  const size_t n = (size_t)rows * cols;
+  const int D = p->num_disp;
+  if ((rc = st_reserve(c, n, D, false))) return rc;
+  const StArena a(c->st_buf, n, D, false);
+  cudaStream_t s = c->stream;
+  CK(cudaMemcpyAsync(a.L3, left3, 3 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.R3, right3, 3 * n, cudaMemcpyHostToDevice, s));
+  const dim3 blk(128), grd((cols + 127) / 128, rows);
+  st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
+  st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.R3, a.gR, rows, cols);
+  c->launches += 2;
+  gsm_st::Tree t;
+  StTree dt;
+  if ((rc = st_tree(c, a, a.L3, rows, cols, p->sigma, p->tau > 0.f ? p->tau : 1200.f, t, &dt, s))) return rc;
+  // the cost kernel writes straight into the [D][BFS position] layout the filter works on
+  st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
+  st_filter_kernel<<<D, 256, 0, s>>>(a.buf, a.fin, dt);
+  st_wta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.fin, a.order, a.disp, (int)n, D);
+  c->launches += 3;
+  u8* out = a.disp;
+  if (p->median_radius > 0) {
+    if ((rc = median_launch(c, a.disp, a.disp2, 1, rows, cols, p->median_radius, s))) return rc;
+    out = a.disp2;
+  }
+  if (p->scale != 1) {
+    st_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, n, p->scale);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(disparity, out, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return GSM_OK;
 }
 

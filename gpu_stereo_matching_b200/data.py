@@ -44,6 +44,27 @@ def synthetic_pair(h: int, w: int, seed: int, dmin: int = 4, dmax: int = 120, no
     return to_u8(left), to_u8(right), disp
 
 
+def synthetic_color_pair(h: int, w: int, seed: int, dmax: int = 40):
+    """3-channel (B, G, R) version of synthetic_pair: three textures sharing ONE disparity field -> (left, right) u8
+    [h, w, 3].  Input of the segment-tree stereo."""
+    rng = np.random.default_rng(seed)
+    L0, R0, disp = synthetic_pair(h, w, seed, dmax=dmax)
+    left = np.empty((h, w, 3), np.uint8)
+    right = np.empty((h, w, 3), np.uint8)
+    left[:, :, 0], right[:, :, 0] = L0, R0
+    xr = np.arange(w, dtype=np.float32)[None, :] + disp
+    x0 = np.clip(np.floor(xr).astype(np.int32), 0, w - 1)
+    x1 = np.clip(x0 + 1, 0, w - 1)
+    f = xr - np.floor(xr)
+    rows = np.arange(h)[:, None]
+    for c in (1, 2):
+        tex = _smooth_texture(rng, h, w)
+        left[:, :, c] = np.clip(np.rint(tex), 0, 255).astype(np.uint8)
+        r = (1 - f) * tex[rows, x0] + f * tex[rows, x1] + rng.normal(0.0, 2.0, (h, w)).astype(np.float32)
+        right[:, :, c] = np.clip(np.rint(r), 0, 255).astype(np.uint8)
+    return left, right
+
+
 def synthetic_batch(n: int, h: int, w: int, seed0: int, **kw):
     L = np.empty((n, h, w), np.uint8); R = np.empty((n, h, w), np.uint8)
     for i in range(n):

@@ -32,6 +32,12 @@ class GsmParams(C.Structure):
     ]
 
 
+class GsmStParams(C.Structure):
+    """struct gsm_st_params (include/gsm.h)."""
+    _fields_ = [("num_disp", C.c_int), ("sigma", C.c_float), ("tau", C.c_float), ("median_radius", C.c_int),
+                ("scale", C.c_int)]
+
+
 class GsmError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"gsm error {code}: {msg}")
@@ -68,6 +74,10 @@ SYMBOLS = {
     "gsm_cvtcolor": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "gsm_disparity_to_depth": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float]),
     "gsm_set_rectification": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "gsm_segment_tree_stereo": (C.c_int, [_P, C.POINTER(GsmStParams), _P, _P, _P, C.c_int, C.c_int]),
+    "gsm_st_matching_cost": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "gsm_st_filter": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, _P, _P]),
+    "gsm_st_build_tree_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, C.POINTER(C.c_int)]),
     "gsm_launch_count": (C.c_longlong, [_P]),
     "gsm_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "gsm_last_kernel_ms": (C.c_float, [_P]),

@@ -193,6 +193,37 @@ int gsm_disparity_to_depth(gsm_ctx* ctx, const uint8_t* disparity, float* depth,
 int gsm_set_rectification(gsm_ctx* ctx, const float* mapx_left, const float* mapy_left, const float* mapx_right,
                           const float* mapy_right, int rows, int cols);
 
+/* ---- the segment-tree stereo of the reference's STMatching project ------------------------ */
+/* stereo_disparity_normal (STMatching/StereoDisparity.cpp:58-90): colour + gradient matching cost
+ * (StereoHelper.cpp:75-129) -> segment-tree aggregation (CColorWeight + BuildSegmentTree + Filter,
+ * SegmentTree.cpp:38-195) -> winner-take-all (StereoHelper.cpp:131-154) -> (2m+1)^2 median (Toolkit.cpp:33-48) ->
+ * disparity * scale.  Images: interleaved 3-channel u8, rows x cols, channel order as cv::imread gives it (B, G, R);
+ * at least 3 x 3 pixels (the reference's median asserts below that).  Host pointers, blocking.  Every stage is bit-exact to the reference compiled without FP contraction.
+ * The tree itself (Kruskal with an adaptive threshold: defined by its sequential edge order) is built on the host,
+ * in O(pixels); cost, tree filter, WTA and median run on the GPU. */
+typedef struct gsm_st_params {
+  int num_disp;      /* max_dis_level, 1..256 */
+  float sigma;       /* range parameter of the edge-weight table exp(-dist / (255 sigma)) (SegmentTree.cpp:141-146) */
+  float tau;         /* constant of the merge threshold tau / size (TAU = 1200, Toolkit.h:33); <= 0 selects 1200 */
+  int median_radius; /* 3 in the reference (StereoDisparity.cpp:85); 0 = none */
+  int scale;         /* final map = disparity * scale, saturated to 255 (StereoDisparity.cpp:87); >= 1 */
+} gsm_st_params;
+int gsm_segment_tree_stereo(gsm_ctx* ctx, const gsm_st_params* p, const uint8_t* left3, const uint8_t* right3,
+                            uint8_t* disparity, int rows, int cols);
+/* Stage exports (parity with the reference stage by stage).  GetMatchingCost: float [rows][cols][num_disp]. */
+int gsm_st_matching_cost(gsm_ctx* ctx, const uint8_t* left3, const uint8_t* right3, float* cost, int rows, int cols,
+                         int num_disp);
+/* CColorWeight + BuildSegmentTree (+ Filter when cost != NULL: float [rows][cols][num_disp], aggregated in place).
+ * order / father_id / father_dist (each optional, rows*cols entries): the ordered tree in breadth-first order --
+ * pixel id, father's pixel id (0 for the root) and quantised weight of the edge to the father (CSegmentTree::m_tree). */
+int gsm_st_filter(gsm_ctx* ctx, const uint8_t* image3, float* cost, int rows, int cols, int num_disp, float sigma,
+                  float tau, int* order, int* father_id, uint8_t* father_dist);
+
+/* The host stage of the segment tree on its own (no GPU): edge weights in (wr[p]: edge (p, p+1); wu[p]: edge
+ * (p, p-cols); u8 as CColorWeight produces them), ordered tree out (as gsm_st_filter); *levels = depth of the tree. */
+int gsm_st_build_tree_host(const uint8_t* wr, const uint8_t* wu, int rows, int cols, float tau, int* order,
+                           int* father_id, uint8_t* father_dist, int* levels);
+
 /* ---- introspection for benches -------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 long long gsm_launch_count(const gsm_ctx* ctx);

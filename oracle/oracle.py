@@ -139,6 +139,83 @@ def utilref() -> C.CDLL:
     return _utilref
 
 
+_segref = None
+
+
+def have_segref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libsegref.so"))
+
+
+def segref() -> C.CDLL:
+    """The reference's own segment-tree stereo -- STMatching/SegmentTree.cpp, segment-graph.h, disjoint-set.h,
+    StereoHelper.cpp, StereoDisparity.cpp, Toolkit.cpp, ctmf.c compiled unmodified (oracle/Makefile target
+    _ref/libsegref.so, driver oracle/seg_driver.cpp)."""
+    global _segref
+    if _segref is None:
+        S = C.CDLL(os.path.join(_HERE, "_ref", "libsegref.so"))
+        f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+        S.ref_st_matching_cost.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, f32]
+        S.ref_st_matching_cost.restype = None
+        S.ref_st_filter.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+        S.ref_st_filter.restype = None
+        for f in ("ref_st_routine", "ref_st_iteration"):
+            getattr(S, f).argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _u8p]
+            getattr(S, f).restype = None
+        _segref = S
+    return _segref
+
+
+def _bgr(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    return a
+
+
+def ref_st_matching_cost(left_bgr, right_bgr, D: int) -> np.ndarray:
+    """GetMatchingCost of the compiled reference (StereoHelper.cpp:75-129): float32 [H][W][D]."""
+    L, R = _bgr(left_bgr), _bgr(right_bgr)
+    out = np.empty(L.shape[:2] + (D,), np.float32)
+    segref().ref_st_matching_cost(L.reshape(-1), R.reshape(-1), L.shape[1], L.shape[0], D, out)
+    return out
+
+
+def ref_st_filter(image_bgr, cost=None, sigma: float = 0.1, tau: float = 1200.0):
+    """CColorWeight + BuildSegmentTree (+ Filter on a copy of cost, float32 [H][W][D]) of the compiled reference
+    (SegmentTree.cpp:38-195): (aggregated volume | None, order, father_id, father_dist)."""
+    img = _bgr(image_bgr)
+    h, w = img.shape[:2]
+    n = h * w
+    order, father, fdist = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.uint8)
+    vol = None if cost is None else np.ascontiguousarray(cost, np.float32).copy()
+    D = 1 if vol is None else vol.shape[2]
+    segref().ref_st_filter(img.reshape(-1), w, h, D, sigma, tau, None if vol is None else vol.ctypes.data,
+                           order.ctypes.data, father.ctypes.data, fdist.ctypes.data)
+    return vol, order, father, fdist
+
+
+def ref_st_routine(left_bgr, right_bgr, D: int, scale: int = 1, sigma: float = 0.1, refined: bool = False) -> np.ndarray:
+    """stereo_disparity_normal (StereoDisparity.cpp:58-90) or, refined=True, stereo_disparity_iteration (:92-160) of the
+    compiled reference: u8 [H][W]."""
+    L, R = _bgr(left_bgr), _bgr(right_bgr)
+    out = np.empty(L.shape[:2], np.uint8)
+    fn = segref().ref_st_iteration if refined else segref().ref_st_routine
+    fn(L.reshape(-1), R.reshape(-1), L.shape[1], L.shape[0], D, scale, sigma, out)
+    return out
+
+
+def st_edge_weights(image_bgr):
+    """CColorWeight (SegmentTree.cpp:183-195) restated: 3x3 median per channel (ctmf r=1 == replicate-border median), then
+    max over the channels of |a - b| between 4-neighbours: (wr, wu) u8 [H][W], 255 where the edge does not exist."""
+    img = _bgr(image_bgr)
+    med = np.stack([median(np.ascontiguousarray(img[:, :, c]), 1) for c in range(3)], -1).astype(np.int32)
+    wr = np.full(img.shape[:2], 255, np.uint8)
+    wu = np.full(img.shape[:2], 255, np.uint8)
+    wr[:, :-1] = np.abs(med[:, :-1] - med[:, 1:]).max(-1)
+    wu[1:, :] = np.abs(med[1:, :] - med[:-1, :]).max(-1)
+    return wr, wu
+
+
 def ref_cpu_remap(src, mapx, mapy) -> np.ndarray:
     """CPU_Remap of the compiled reference (Utility.cpp:236-246)."""
     src = _u8(src)

@@ -545,6 +545,47 @@ def test_mixed_size_batch_config2(ctx, fx, orc):
             c9.stereo_batch_v([Ls[0]], [Rs[1][:, :400]], p)
 
 
+# ------------------------------------------------------------------------------------------ SURVEY 8(f) row 4
+def _art_demo_bgr():
+    import cv2
+    d = os.path.join(ROOT, "tests", "golden", "art_demo")
+    return cv2.imread(os.path.join(d, "view1_.png")), cv2.imread(os.path.join(d, "view5_.png"))
+
+
+def test_segment_tree_stereo_bit_exact(ctx, orc):
+    """The segment-tree stereo of the reference's STMatching project, stage by stage and end to end, against the
+    reference's own code compiled unmodified (oracle/_ref/libsegref.so): matching cost (StereoHelper.cpp:75-129), ordered
+    tree (SegmentTree.cpp:38-139), tree filter (:148-181), and stereo_disparity_normal (StereoDisparity.cpp:58-90) --
+    all bit for bit (float volumes compared with array_equal)."""
+    if not orc.have_segref():
+        pytest.skip("oracle/_ref/libsegref.so not built (needs the reference tree)")
+    L, R = _art_demo_bgr()  # the reference's demo pair, 320x256, colour
+    Ls, Rs = gdata.synthetic_color_pair(150, 260, 11, dmax=40)
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    for name, (a, b), D in (("art_demo", (L, R), 64), ("synthetic", (Ls, Rs), 48), ("noise_odd", (noise, np.roll(noise, -3, 1)), 20),
+                            ("tiny", (L[:7, :11].copy(), R[:7, :11].copy()), 7)):  # the reference needs D <= cols and, for its 7x7 median, >= 7x7
+        cost = ctx.st_matching_cost(a, b, D)
+        cref = orc.ref_st_matching_cost(a, b, D)
+        assert np.array_equal(cost, cref), (name, "cost", float(np.abs(cost - cref).max()))
+        for sigma, tau in ((0.1, 1200.0), (0.03, 300.0)):
+            vol, order, father, fdist = ctx.st_filter(a, cref, sigma, tau)
+            vref, oref, fref, dref = orc.ref_st_filter(a, cref, sigma, tau)
+            assert np.array_equal(order, oref) and np.array_equal(father, fref) and np.array_equal(fdist, dref), (name, "tree")
+            assert np.array_equal(vol, vref), (name, "filter", sigma, float(np.abs(vol - vref).max()))
+        for scale, sigma in ((1, 0.1), (4, 0.1), (3, 0.05)):
+            d = ctx.segment_tree_stereo(a, b, D, sigma=sigma, scale=scale)
+            assert np.array_equal(d, orc.ref_st_routine(a, b, D, scale, sigma)), (name, "pipeline", scale, sigma)
+    # deterministic, and independent of what the arena held before
+    d1 = ctx.segment_tree_stereo(L, R, 64, scale=4)
+    ctx.segment_tree_stereo(Ls, Rs, 32)
+    assert np.array_equal(ctx.segment_tree_stereo(L, R, 64, scale=4), d1)
+    with pytest.raises(g.GsmError):
+        ctx.segment_tree_stereo(L[:2], R[:2], 16)  # the reference's 3x3 median asserts below 3x3
+    with pytest.raises(ValueError):
+        ctx.segment_tree_stereo(L[:, :, 0], R[:, :, 0], 16)
+
+
 def test_errors_are_reported(ctx):
     z = np.zeros((16, 16), np.uint8)
     with pytest.raises(g.GsmError):

@@ -1,8 +1,10 @@
 """CPU tests: the oracle against the reference's golden outputs and against itself (no GPU)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import SETS
+from conftest import ROOT, SETS
 
 
 def test_getdisp_digests_all_sets(fx, digests, orc):
@@ -256,3 +258,33 @@ def test_remap_and_cvtcolor_against_compiled_utility(orc):
     yy, xx = np.mgrid[0:9, 0:11].astype(np.float32)
     out = orc.ref_cpu_remap(img, xx, yy)
     assert np.array_equal(out[:-1, :-1], img[:-1, :-1]) and not out[-1].any() and not out[:, -1].any()
+
+
+def _art_demo_bgr():
+    import cv2
+    d = os.path.join(ROOT, "tests", "golden", "art_demo")
+    return cv2.imread(os.path.join(d, "view1_.png")), cv2.imread(os.path.join(d, "view5_.png"))
+
+
+def test_segment_tree_host_builder_equals_reference_tree():
+    """SURVEY 8f row 4, host stage: the product's O(N) tree builder (gsm_st_build_tree_host: counting sort + Kruskal with
+    the adaptive threshold + breadth-first ordering) reproduces the ordered tree of the reference's BuildSegmentTree
+    (SegmentTree.cpp:38-139, compiled unmodified into oracle/_ref/libsegref.so) node for node -- same order, same
+    fathers, same quantised edge weights -- on the reference's demo image, on synthetic colour images, on odd shapes,
+    on a constant image (all weights tie) and for several tau.  No GPU involved."""
+    from oracle import oracle as O
+    if not O.have_segref():
+        pytest.skip("oracle/_ref/libsegref.so not built (needs the reference tree)")
+    import gpu_stereo_matching_b200 as g
+    from gpu_stereo_matching_b200 import data as gdata
+    L, _ = _art_demo_bgr()
+    cases = [(L, 1200.0), (L, 300.0), (L[:57, :83].copy(), 1200.0), (gdata.synthetic_color_pair(120, 200, 5)[0], 1200.0),
+             (np.full((40, 30, 3), 77, np.uint8), 1200.0), (L[:3, :50].copy(), 1200.0), (L[:50, :3].copy(), 50.0)]  # the reference's ctmf needs >= 3x3
+    rng = np.random.default_rng(0)
+    cases.append((rng.integers(0, 256, (64, 96, 3), dtype=np.uint8), 1200.0))  # noise: heavy use of the second pass
+    for img, tau in cases:
+        _, order, father, fdist = O.ref_st_filter(img, None, 0.1, tau)
+        wr, wu = O.st_edge_weights(img)
+        o2, f2, d2, levels = g.st_build_tree_host(wr, wu, tau)
+        assert np.array_equal(order, o2) and np.array_equal(father, f2) and np.array_equal(fdist, d2), (img.shape, tau)
+        assert levels >= 1
