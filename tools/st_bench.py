@@ -1,0 +1,33 @@
+"""Segment-tree stereo (gsm_segment_tree_stereo) timing on one GPU: whole call from host buffers, and the host tree
+builder alone (dev tool).  usage: python tools/st_bench.py"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from scipy.ndimage import median_filter
+import gpu_stereo_matching_b200 as g
+from gpu_stereo_matching_b200 import data
+
+
+def weights(img):
+    med = np.stack([median_filter(img[:, :, c], size=3, mode="nearest") for c in range(3)], -1).astype(np.int32)
+    wr = np.full(img.shape[:2], 255, np.uint8); wu = np.full(img.shape[:2], 255, np.uint8)
+    wr[:, :-1] = np.abs(med[:, :-1] - med[:, 1:]).max(-1); wu[1:, :] = np.abs(med[1:, :] - med[:-1, :]).max(-1)
+    return wr, wu
+
+
+for (h, w, D) in ((256, 320, 64), (370, 463, 64), (720, 1280, 128)):
+    L, R = data.synthetic_color_pair(h, w, 7, dmax=min(D - 8, 120))
+    with g.StereoContext(h, w, D, 1) as ctx:
+        for _ in range(2):
+            d = ctx.segment_tree_stereo(L, R, D, scale=1)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.segment_tree_stereo(L, R, D, scale=1)
+        ms = (time.perf_counter() - t0) / 5 * 1e3
+    wr, wu = weights(L)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        _, _, _, levels = g.st_build_tree_host(wr, wu)
+    tms = (time.perf_counter() - t0) / 5 * 1e3
+    print(f"{w}x{h} x{D}: whole call {ms:8.2f} ms ({h * w * D / ms / 1e3:8.1f} MDE/s), host tree builder {tms:7.2f} ms, "
+          f"tree depth {levels} levels", flush=True)
