@@ -298,14 +298,15 @@ class StereoContext:
         return a
 
     def segment_tree_stereo(self, left_bgr, right_bgr, num_disp: int, sigma: float = 0.1, tau: float = 1200.0,
-                            median_radius: int = 3, scale: int = 1) -> np.ndarray:
+                            median_radius: int = 3, scale: int = 1, refined: bool = False) -> np.ndarray:
         """== stereo_disparity_normal (STMatching/StereoDisparity.cpp:58-90): colour+gradient cost -> segment-tree
-        aggregation -> WTA -> median -> * scale; u8 [rows, cols]."""
+        aggregation -> WTA -> median -> * scale; u8 [rows, cols].  refined=True: stereo_disparity_iteration (:92-160),
+        the two-pass version with the L-R check and the colour+depth tree."""
         L, R = self._bgr(left_bgr, "left_bgr"), self._bgr(right_bgr, "right_bgr")
         if L.shape != R.shape:
             raise ValueError("left / right differ in shape")
         out = np.empty(L.shape[:2], np.uint8)
-        p = GsmStParams(int(num_disp), float(sigma), float(tau), int(median_radius), int(scale))
+        p = GsmStParams(int(num_disp), float(sigma), float(tau), int(median_radius), int(scale), int(bool(refined)))
         _l.check(self._lib.gsm_segment_tree_stereo(self._h, C.byref(p), _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1]))
         return out
 

@@ -1130,8 +1130,8 @@ extern "C" int gsm_set_rectification(gsm_ctx* c, const float* mxl, const float* 
 // ---- segment-tree stereo (kernels in gsm_st.cuh, tree in gsm_st_host.hpp) --------------------------
 namespace {
 struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
-  u8 *L3, *R3, *med, *wr, *wu, *nchild, *disp, *disp2;
-  float *gL, *gR, *fw, *buf, *fin, *vol;
+  u8 *L3, *R3, *med, *wr, *wu, *nchild, *disp, *disp2, *dispL, *dispR, *mask;
+  float *gL, *gR, *fw, *buf, *fin, *vol, *wrf, *wuf;
   int *order, *father, *child0, *level_off, *pos;
   size_t bytes;
   StArena(void* base, size_t n, int D, bool with_vol) {
@@ -1139,7 +1139,9 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
     auto take = [&](size_t b) { void* p = base ? (char*)base + o : nullptr; o += (b + 255) / 256 * 256; return p; };
     L3 = (u8*)take(3 * n); R3 = (u8*)take(3 * n); med = (u8*)take(3 * n);
     wr = (u8*)take(n); wu = (u8*)take(n); nchild = (u8*)take(n); disp = (u8*)take(n); disp2 = (u8*)take(n);
+    dispL = (u8*)take(n); dispR = (u8*)take(n); mask = (u8*)take(n);
     gL = (float*)take(4 * n); gR = (float*)take(4 * n); fw = (float*)take(4 * n);
+    wrf = (float*)take(4 * n); wuf = (float*)take(4 * n);
     order = (int*)take(4 * n); father = (int*)take(4 * n); child0 = (int*)take(4 * n); pos = (int*)take(4 * n);
     level_off = (int*)take(4 * (n + 2));
     buf = (float*)take(4 * n * D); fin = (float*)take(4 * n * D);
@@ -1164,20 +1166,33 @@ int st_check(const gsm_ctx* c, int rows, int cols, int D) {
   if (D < 1 || D > MAX_DISP) return fail(GSM_ERR_INVALID, "num_disp %d not in 1..256", D);
   return GSM_OK;
 }
-// images (device, interleaved 3-channel) -> the ordered tree on the device; fills t (host) as well
+// image (device, interleaved 3-channel) -> the ordered tree on the device; fills t (host) as well.  With disp / mask
+// (device u8 maps) the edge weights are CColorDepthWeight's (SegmentTree.cpp:197-218, scale 255), else CColorWeight's.
 int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, float sigma, float tau, gsm_st::Tree& t,
-            StTree* dt, cudaStream_t s) {
+            StTree* dt, cudaStream_t s, const u8* disp = nullptr, const u8* mask = nullptr, int level = 0) {
   const size_t n = (size_t)rows * cols;
   const dim3 blk(128), grd((cols + 127) / 128, rows);
   st_median3_kernel<<<grd, blk, 0, s>>>(img3, a.med, rows, cols);
-  st_edge_weight_kernel<<<grd, blk, 0, s>>>(a.med, a.wr, a.wu, rows, cols);
-  c->launches += 2;
-  CK(cudaGetLastError());
-  std::vector<u8> wr(n), wu(n);
-  CK(cudaMemcpyAsync(wr.data(), a.wr, n, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(wu.data(), a.wu, n, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  gsm_st::build_tree(wr.data(), wu.data(), rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t);
+  c->launches++;
+  if (disp) {
+    st_edge_weight_depth_kernel<<<grd, blk, 0, s>>>(a.med, disp, mask, (float)level, a.wrf, a.wuf, rows, cols);
+    c->launches++;
+    CK(cudaGetLastError());
+    std::vector<float> wr(n), wu(n);
+    CK(cudaMemcpyAsync(wr.data(), a.wrf, 4 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(wu.data(), a.wuf, 4 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    gsm_st::build_tree_f(wr.data(), wu.data(), rows, cols, tau, /*CColorDepthWeight::GetScale*/ 255.0f, t);
+  } else {
+    st_edge_weight_kernel<<<grd, blk, 0, s>>>(a.med, a.wr, a.wu, rows, cols);
+    c->launches++;
+    CK(cudaGetLastError());
+    std::vector<u8> wr(n), wu(n);
+    CK(cudaMemcpyAsync(wr.data(), a.wr, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(wu.data(), a.wu, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    gsm_st::build_tree(wr.data(), wu.data(), rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t);
+  }
   float table[256];
   gsm_st::weight_table(sigma, table);
   std::vector<float> fw(n);
@@ -1293,16 +1308,42 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   c->launches += 2;
   gsm_st::Tree t;
   StTree dt;
-  if ((rc = st_tree(c, a, a.L3, rows, cols, p->sigma, p->tau > 0.f ? p->tau : 1200.f, t, &dt, s))) return rc;
-  // the cost kernel writes straight into the [D][BFS position] layout the filter works on
-  st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
-  st_filter_kernel<<<D, 256, 0, s>>>(a.buf, a.fin, dt);
-  st_wta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.fin, a.order, a.disp, (int)n, D);
-  c->launches += 3;
-  u8* out = a.disp;
-  if (p->median_radius > 0) {
-    if ((rc = median_launch(c, a.disp, a.disp2, 1, rows, cols, p->median_radius, s))) return rc;
-    out = a.disp2;
+  const float tau = p->tau > 0.f ? p->tau : 1200.f;
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  // aggregate the cost of one view over the tree of `img` and take the winner (+ median): -> a.disp / a.disp2
+  auto view = [&](const u8* img, int right, float sigma, const u8* tdisp, const u8* tmask, u8** out) -> int {
+    int r;
+    if ((r = st_tree(c, a, img, rows, cols, sigma, tau, t, &dt, s, tdisp, tmask, D))) return r;
+    // the cost kernel writes straight into the [D][BFS position] layout the filter works on
+    if (right) st_cost_right_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
+    else st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
+    st_filter_kernel<<<D, 256, 0, s>>>(a.buf, a.fin, dt);
+    st_wta_kernel<<<gn, 256, 0, s>>>(a.fin, a.order, a.disp, (int)n, D);
+    c->launches += 3;
+    *out = a.disp;
+    if (p->median_radius > 0) {
+      if ((r = median_launch(c, a.disp, a.disp2, 1, rows, cols, p->median_radius, s))) return r;
+      *out = a.disp2;
+    }
+    CK(cudaGetLastError());
+    return GSM_OK;
+  };
+  u8* out = nullptr;
+  if (!p->refined) {
+    if ((rc = view(a.L3, 0, p->sigma, nullptr, nullptr, &out))) return rc;
+  } else {
+    // stereo_disparity_iteration (StereoDisparity.cpp:92-160): both views with SIGMA_ONE (Toolkit.h:34), L-R check
+    // (:128-147), then a second left pass over the tree of CColorDepthWeight(left image, left disparity, mask)
+    if (D > cols) return fail(GSM_ERR_INVALID, "refined segment-tree stereo needs num_disp <= cols (StereoHelper.cpp:162-177)");
+    const float SIGMA_ONE = 0.08f;
+    if ((rc = view(a.L3, 0, SIGMA_ONE, nullptr, nullptr, &out))) return rc;
+    CK(cudaMemcpyAsync(a.dispL, out, n, cudaMemcpyDeviceToDevice, s));
+    if ((rc = view(a.R3, 1, SIGMA_ONE, nullptr, nullptr, &out))) return rc;
+    CK(cudaMemcpyAsync(a.dispR, out, n, cudaMemcpyDeviceToDevice, s));
+    lr_check_kernel<<<dim3((cols + 255) / 256, rows, 1), 256, 0, s>>>(a.dispL, a.dispR, nullptr, a.mask, nullptr, rows, cols, 1,
+                                                                        nullptr);
+    c->launches++;
+    if ((rc = view(a.L3, 0, p->sigma, a.dispL, a.mask, &out))) return rc;
   }
   if (p->scale != 1) {
     st_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, n, p->scale);

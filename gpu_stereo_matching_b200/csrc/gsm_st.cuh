@@ -57,6 +57,29 @@ __global__ void st_cost_kernel(const u8* __restrict__ L, const u8* __restrict__ 
   }
 }
 
+// GetRightMatchingCostFromLeft (StereoHelper.cpp:156-180) applied to GetMatchingCost: CR(y, x, d) = CL(y, x + dd, dd) with
+// dd = min(d, W - 1 - x) (past the right border the last valid disparity is repeated), and CL(y, x + dd, dd) compares
+// left pixel x + dd with right pixel x.  Same arithmetic as st_cost_kernel.  Needs D <= W like the reference.
+__global__ void st_cost_right_kernel(const u8* __restrict__ L, const u8* __restrict__ R, const float* __restrict__ gL,
+                                     const float* __restrict__ gR, float* __restrict__ out, const int* __restrict__ pos,
+                                     size_t dstride, int H, int W, int D) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const size_t p = (size_t)y * W + x;
+  const u8* r = R + p * 3;
+  const float gr = gR[p];
+  const size_t o = (size_t)pos[p];
+  const double wc = 0.11, wg = 1.0 - 0.11;
+  for (int d = 0; d < D; ++d) {
+    const int xl = x + min(d, W - 1 - x);
+    const u8* l = L + ((size_t)y * W + xl) * 3;
+    const int sad = abs((int)l[0] - (int)r[0]) + abs((int)l[1] - (int)r[1]) + abs((int)l[2] - (int)r[2]);
+    const double cc = fmin(__ddiv_rn((double)sad, 3.0), 7.0);
+    const double cg = fmin((double)fabsf(__fsub_rn(gL[(size_t)y * W + xl], gr)), 2.0);
+    out[(size_t)d * dstride + o] = (float)__dadd_rn(__dmul_rn(wc, cc), __dmul_rn(wg, cg));
+  }
+}
+
 // MeanFilter(img, img, 1) of CColorWeight (SegmentTree.cpp:185; ctmf with r = 1 on 3 interleaved channels): 3x3 median
 // per channel, replicate border.
 __global__ void st_median3_kernel(const u8* __restrict__ src, u8* __restrict__ dst, int H, int W) {
@@ -96,6 +119,30 @@ __global__ void st_edge_weight_kernel(const u8* __restrict__ img, u8* __restrict
   auto wgt = [&](const u8* b) { return max(max(abs((int)a[0] - (int)b[0]), abs((int)a[1] - (int)b[1])), abs((int)a[2] - (int)b[2])); };
   wr[p] = x + 1 < W ? (u8)wgt(a + 3) : (u8)255;
   wu[p] = y >= 1 ? (u8)wgt(a - (size_t)W * 3) : (u8)255;
+}
+
+// CColorDepthWeight::GetWeight (SegmentTree.cpp:204-218): where both pixels passed the L-R check,
+// 0.5 |d0 - d1| / level + (1 - 0.5) colour / 255, else colour / 255 (colour = max channel difference of the
+// median-filtered image); float, one rounding per operation.
+__global__ void st_edge_weight_depth_kernel(const u8* __restrict__ img, const u8* __restrict__ disp,
+                                            const u8* __restrict__ mask, float level, float* __restrict__ wr,
+                                            float* __restrict__ wu, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const size_t p = (size_t)y * W + x;
+  const u8* a = img + p * 3;
+  auto wgt = [&](size_t q) {
+    const u8* b = img + q * 3;
+    const int col = max(max(abs((int)a[0] - (int)b[0]), abs((int)a[1] - (int)b[1])), abs((int)a[2] - (int)b[2]));
+    const float cv = __fdiv_rn((float)col, 255.0f);
+    if (mask[p] && mask[q]) {
+      const float dv = __fdiv_rn((float)abs((int)disp[p] - (int)disp[q]), level);
+      return __fadd_rn(__fmul_rn(0.5f, dv), __fmul_rn(1.0f - 0.5f, cv));
+    }
+    return cv;
+  };
+  wr[p] = x + 1 < W ? wgt(p + 1) : 0.f;
+  wu[p] = y >= 1 ? wgt(p - W) : 0.f;
 }
 
 // The ordered tree (breadth-first from pixel 0, SegmentTree.cpp:97-131) as arrays indexed by BFS position:

@@ -43,11 +43,17 @@ struct DisjointSets {  // union by rank with one-step path compression (disjoint
   }
 };
 
+struct Edge {
+  int a, b;
+  float w;
+};
+
+inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float scale, Tree& t);
+
 // wr[p]: weight of edge (p, p+1) for x < W-1; wu[p]: weight of edge (p, p-W) for y >= 1 (st_edge_weight_kernel).
 // tau: the constant c of the threshold function c / size (TAU = 1200 in Toolkit.h:33); scale: CWeightProvider::GetScale().
 inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t) {
   const int n = H * W;
-  struct Edge { int a, b; float w; };
   // ---- edges in the reference's sorted order: by weight, then by b, then by a (segment-graph.h:33-41)
   std::vector<int> cnt(257, 0);
   for (int y = 0; y < H; ++y)
@@ -67,6 +73,30 @@ inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float
       if (y + 1 < H) { const int a = b + W; Edge& d = e[at[wu[a]]++]; d.a = a; d.b = b; d.w = (float)wu[a]; }       // (a, a-W)
     }
   }
+  finish_tree(e, H, W, tau, scale, t);
+}
+
+// The same for real-valued weights (CColorDepthWeight, SegmentTree.cpp:204-218): a comparison sort by (w, b, a).
+inline void build_tree_f(const float* wr, const float* wu, int H, int W, float tau, float scale, Tree& t) {
+  std::vector<Edge> e;
+  e.reserve(2 * (size_t)H * W);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const int p = y * W + x;
+      if (x < W - 1) e.push_back(Edge{p, p + 1, wr[p]});
+      if (y >= 1) e.push_back(Edge{p, p - W, wu[p]});
+    }
+  std::sort(e.begin(), e.end(), [](const Edge& x, const Edge& y) {
+    if (x.w != y.w) return x.w < y.w;
+    if (x.b != y.b) return x.b < y.b;
+    return x.a < y.a;
+  });
+  finish_tree(e, H, W, tau, scale, t);
+}
+
+inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float scale, Tree& t) {
+  const int n = H * W;
+  const int m = (int)e.size();
   // ---- segment_graph (segment-graph.h:48-101): adaptive-threshold Kruskal, then the remaining edges in the same order
   // join the segments into ONE tree; an edge between two segments of more than MIN_SIZE_SEG pixels is penalised
   std::vector<uint8_t> used(m, 0);

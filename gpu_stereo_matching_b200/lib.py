@@ -35,7 +35,7 @@ class GsmParams(C.Structure):
 class GsmStParams(C.Structure):
     """struct gsm_st_params (include/gsm.h)."""
     _fields_ = [("num_disp", C.c_int), ("sigma", C.c_float), ("tau", C.c_float), ("median_radius", C.c_int),
-                ("scale", C.c_int)]
+                ("scale", C.c_int), ("refined", C.c_int)]
 
 
 class GsmError(RuntimeError):

@@ -207,6 +207,10 @@ typedef struct gsm_st_params {
   float tau;         /* constant of the merge threshold tau / size (TAU = 1200, Toolkit.h:33); <= 0 selects 1200 */
   int median_radius; /* 3 in the reference (StereoDisparity.cpp:85); 0 = none */
   int scale;         /* final map = disparity * scale, saturated to 255 (StereoDisparity.cpp:87); >= 1 */
+  int refined;       /* 0: stereo_disparity_normal (ST-1, the default of STMatching/main.cpp:52); 1:
+                        stereo_disparity_iteration (ST-2, StereoDisparity.cpp:92-160): both views aggregated with
+                        sigma 0.08, L-R check (:128-147), then a second pass over the tree of CColorDepthWeight
+                        (left image, left disparity, mask; SegmentTree.cpp:197-218); needs num_disp <= cols */
 } gsm_st_params;
 int gsm_segment_tree_stereo(gsm_ctx* ctx, const gsm_st_params* p, const uint8_t* left3, const uint8_t* right3,
                             uint8_t* disparity, int rows, int cols);

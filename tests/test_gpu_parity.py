@@ -576,6 +576,12 @@ def test_segment_tree_stereo_bit_exact(ctx, orc):
         for scale, sigma in ((1, 0.1), (4, 0.1), (3, 0.05)):
             d = ctx.segment_tree_stereo(a, b, D, sigma=sigma, scale=scale)
             assert np.array_equal(d, orc.ref_st_routine(a, b, D, scale, sigma)), (name, "pipeline", scale, sigma)
+    # ST-2 (stereo_disparity_iteration, StereoDisparity.cpp:92-160): both views, the reference's own L-R check loop
+    # (:128-147) in situ, the colour+depth tree (real-valued edge weights) -- bit for bit
+    for name, (a, b), D in (("art_demo", (L, R), 64), ("synthetic", (Ls, Rs), 48), ("noise_odd", (noise, np.roll(noise, -3, 1)), 20)):
+        for scale, sigma in ((4, 0.1), (1, 0.05)):
+            d = ctx.segment_tree_stereo(a, b, D, sigma=sigma, scale=scale, refined=True)
+            assert np.array_equal(d, orc.ref_st_routine(a, b, D, scale, sigma, refined=True)), (name, "ST-2", scale, sigma)
     # deterministic, and independent of what the arena held before
     d1 = ctx.segment_tree_stereo(L, R, 64, scale=4)
     ctx.segment_tree_stereo(Ls, Rs, 32)
