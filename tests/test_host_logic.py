@@ -169,3 +169,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["config"]["workload"].startswith("config3") and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_dsplit_row_bands_fills_the_gpu():
+    """Row bands of a disparity split: every rank passes the same value; enough CTAs (strips x chunks x bands) for 148
+    SMs at 8 ranks on the 4K config, the single-GPU choice at world 1, never more bands than rows."""
+    assert gdist.dsplit_row_bands(2160, 3840, 256, 1) == 3      # 768-row cap of the fp32 running sums
+    b8 = gdist.dsplit_row_bands(2160, 3840, 256, 8)
+    assert 24 * 1 * b8 >= 140 and b8 >= 3
+    for world in (1, 2, 3, 4, 8):
+        for (h, w, d) in ((2160, 3840, 256), (720, 1280, 128), (40, 50, 33), (1, 16, 1)):
+            b = gdist.dsplit_row_bands(h, w, d, world)
+            assert 1 <= b <= max(1, h)
+    with pytest.raises(ValueError):
+        gdist.dsplit_row_bands(0, 10, 10, 1)
+
+
+def test_python_binding_rejects_mismatched_buffers():
+    """The C ABI takes raw pointers and ONE rows x cols: the binding must refuse arrays whose shapes, dtypes or layout
+    disagree instead of letting a copy run past the end of a host buffer."""
+    from gpu_stereo_matching_b200 import api
+    a = np.zeros((4, 8, 8), np.uint8)
+    assert api._same_shape(3, left=a, right=a.copy(), out=a.copy(), mask_out=None) == (4, 8, 8)
+    with pytest.raises(ValueError):
+        api._same_shape(3, left=a, right=a[:, :, :7].copy())
+    with pytest.raises(ValueError):
+        api._same_shape(3, left=a, right=a[:, ::2, :])          # not contiguous
+    with pytest.raises(TypeError):
+        api._same_shape(3, left=a, right=a.astype(np.int16))
+    with pytest.raises(ValueError):
+        api._same_shape(3, left=a, out=a[0])                    # wrong rank
