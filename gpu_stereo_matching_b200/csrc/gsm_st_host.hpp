@@ -25,20 +25,25 @@ struct Tree {
   std::vector<int> level_off;   // level l = BFS positions [level_off[l], level_off[l+1])
 };
 
-struct DisjointSets {  // union by rank with one-step path compression (disjoint-set.h:36-82); only connectivity and
-  std::vector<int> p, rank, size;  // component sizes are observable, and those do not depend on the variant
-  explicit DisjointSets(int n) : p(n), rank(n, 0), size(n, 1) { for (int i = 0; i < n; ++i) p[i] = i; }
+struct DisjointSets {  // union by rank with path compression (disjoint-set.h:36-82); only connectivity and component
+  std::vector<int> p;   // sizes are observable, and those do not depend on the variant.  The parent array is on its own
+  struct Info { int size, rank; float thr; };  // (find touches nothing else); size, rank and the component's merge
+  std::vector<Info> info;                       // threshold are only read at roots
+  DisjointSets(int n, float thr0) : p(n), info(n) {
+    for (int i = 0; i < n; ++i) { p[i] = i; info[i].size = 1; info[i].rank = 0; info[i].thr = thr0; }
+  }
   int find(int x) {
-    int y = x;
+    int y = p[x];
+    if (y == x) return x;
     while (y != p[y]) y = p[y];
     while (p[x] != y) { const int nx = p[x]; p[x] = y; x = nx; }
     return y;
   }
   int join(int a, int b) {  // a, b roots; returns the new root
-    if (rank[a] > rank[b]) std::swap(a, b);
+    if (info[a].rank > info[b].rank) std::swap(a, b);
     p[a] = b;
-    size[b] += size[a];
-    if (rank[a] == rank[b]) rank[b]++;
+    info[b].size += info[a].size;
+    if (info[a].rank == info[b].rank) info[b].rank++;
     return b;
   }
 };
@@ -67,11 +72,11 @@ inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float
   std::vector<Edge> e(m);
   {
     std::vector<int> at(cnt.begin(), cnt.begin() + 256);
-    for (int b = 0; b < n; ++b) {  // edges whose second endpoint is b, by increasing first endpoint a
-      const int x = b % W, y = b / W;
-      if (x >= 1) { const int a = b - 1; Edge& d = e[at[wr[a]]++]; d.a = a; d.b = b; d.w = (float)wr[a]; }          // (a, a+1)
-      if (y + 1 < H) { const int a = b + W; Edge& d = e[at[wu[a]]++]; d.a = a; d.b = b; d.w = (float)wu[a]; }       // (a, a-W)
-    }
+    for (int y = 0, b = 0; y < H; ++y)  // edges whose second endpoint is b, by increasing first endpoint a
+      for (int x = 0; x < W; ++x, ++b) {
+        if (x >= 1) { const int a = b - 1; Edge& d = e[at[wr[a]]++]; d.a = a; d.b = b; d.w = (float)wr[a]; }          // (a, a+1)
+        if (y + 1 < H) { const int a = b + W; Edge& d = e[at[wu[a]]++]; d.a = a; d.b = b; d.w = (float)wu[a]; }       // (a, a-W)
+      }
   }
   finish_tree(e, H, W, tau, scale, t);
 }
@@ -101,22 +106,25 @@ inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float sca
   // join the segments into ONE tree; an edge between two segments of more than MIN_SIZE_SEG pixels is penalised
   std::vector<uint8_t> used(m, 0);
   {
-    DisjointSets u(n);
-    std::vector<float> thr(n, tau / 1.0f);
+    DisjointSets u(n, tau / 1.0f);
+    int sets = n;
     for (int i = 0; i < m; ++i) {
       const int a = u.find(e[i].a), b = u.find(e[i].b);
-      if (a != b && e[i].w <= thr[a] && e[i].w <= thr[b]) {
+      if (a != b && e[i].w <= u.info[a].thr && e[i].w <= u.info[b].thr) {
         used[i] = 1;
         const int r = u.join(a, b);
-        thr[r] = e[i].w + tau / (float)u.size[r];
+        u.info[r].thr = e[i].w + tau / (float)u.info[r].size;
+        --sets;
       }
     }
-    for (int i = 0; i < m; ++i) {
+    for (int i = 0; i < m && sets > 1; ++i) {  // once one component is left no further edge can join anything
+      if (used[i]) continue;                   // its endpoints are already connected
       const int a = u.find(e[i].a), b = u.find(e[i].b);
       if (a != b) {
-        const int size_min = std::min(u.size[a], u.size[b]);
+        const int size_min = std::min(u.info[a].size, u.info[b].size);
         u.join(a, b);
         used[i] = 1;
+        --sets;
         if (size_min > 50) e[i].w += 5.0f;  // MIN_SIZE_SEG, PENALTY_CROSS_SEG
       }
     }
