@@ -268,8 +268,8 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
     barrier per frame in a stream of frames.  Speed-up is against the same process's single-GPU pass with ITS best
     (automatic) row bands; the map is checked bit for bit against the single-GPU pass with the SAME row bands and
     against the NCCL all-reduce combine."""
-    from gpu_stereo_matching_b200.dist import (DsplitStream, PeerPlanes, dsplit_row_bands, dsplit_stereo,
-                                              torch_stream_handle)
+    from gpu_stereo_matching_b200.dist import (DsplitStream, PeerPlanes, dsplit_row_bands, dsplit_spare_sms,
+                                              dsplit_stereo, torch_stream_handle)
     h, w, d = 2160, 3840, 256
     path = "/tmp/gsm_bench_c5_pair.npz"
     try:
@@ -300,7 +300,9 @@ def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
     planes, pipe, combine = None, None, "nccl all-reduce(MIN) of the int64 packed (cost,d) plane"
     try:
         planes = PeerPlanes(h * w, views=1, slots=3)
-        pipe = DsplitStream(ctx, partial, planes, p, stream, torch.cuda.Stream(), timing=True)
+        spare = dsplit_spare_sms(h, w, d, world, bands, torch.cuda.get_device_properties(local_rank).multi_processor_count)
+        rec["spare_sms_running_the_combine"] = spare
+        pipe = DsplitStream(ctx, partial, planes, p, stream, torch.cuda.Stream(), timing=True, spare_sms=spare)
         combine = ("peer memory over NVLink: reduce-scatter + finalize + all-gather of the u8 map in one kernel "
                    "(gsm_reduce_keys_p2p) on a second stream, overlapping the next frame's kernels; one cross-rank "
                    "barrier per frame (dist.DsplitStream)")

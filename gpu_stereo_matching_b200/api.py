@@ -199,13 +199,15 @@ class StereoContext:
                                                  C.c_void_p(disp_right_ptr or None), C.c_void_p(disp_ptr),
                                                  C.c_void_p(mask_ptr or None), rows, cols, C.c_void_p(stream or None)))
 
-    def reduce_keys_p2p(self, key_ptrs, disp_ptrs, rank: int, npx: int, stream=0):
-        """Peer-memory combine of a disparity split (gsm_reduce_keys_p2p): key_ptrs / disp_ptrs are the device
-        pointers of every rank's packed-min plane / disparity map as mapped into this process."""
+    def reduce_keys_p2p(self, key_ptrs, disp_ptrs, rank: int, npx: int, stream=0, max_blocks: int = 0):
+        """Peer-memory combine of a disparity split (gsm_reduce_keys_p2p[_ex]): key_ptrs / disp_ptrs are the device
+        pointers of every rank's packed-min plane / disparity map as mapped into this process.  max_blocks > 0 confines
+        the kernel to that many SMs so that it runs beside a fused kernel that leaves them idle."""
         world = len(key_ptrs)
         ka = (C.c_void_p * world)(*[int(x) for x in key_ptrs])
         da = (C.c_void_p * world)(*[int(x) for x in disp_ptrs])
-        _l.check(self._lib.gsm_reduce_keys_p2p(self._h, ka, da, world, rank, npx, C.c_void_p(stream or None)))
+        _l.check(self._lib.gsm_reduce_keys_p2p_ex(self._h, ka, da, world, rank, npx, C.c_void_p(stream or None),
+                                                  int(max_blocks)))
 
     def ad_volume(self, left, right, num_disp: int) -> np.ndarray:
         """== PreCal (BlockMatching.cpp:89-109): u8 [D][rows][cols]."""

@@ -873,8 +873,8 @@ extern "C" int gsm_postfilter_device(gsm_ctx* c, const gsm_params* p, const void
                    (u8*)disparity_dev, (u8*)mask_dev, s, nullptr, (size_t)rows * cols);
 }
 
-extern "C" int gsm_reduce_keys_p2p(gsm_ctx* c, const void* const* key_ptrs, void* const* disp_ptrs, int world,
-                                   int rank, long long npx, void* stream) {
+static int reduce_keys_p2p(gsm_ctx* c, const void* const* key_ptrs, void* const* disp_ptrs, int world, int rank,
+                           long long npx, void* stream, int max_blocks) {
   if (!c) return fail(GSM_ERR_INVALID, "null ctx");
   if (!key_ptrs || !disp_ptrs || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world || npx < 1)
     return fail(GSM_ERR_INVALID, "gsm_reduce_keys_p2p: world=%d rank=%d npx=%lld", world, rank, npx);
@@ -893,13 +893,33 @@ extern "C" int gsm_reduce_keys_p2p(gsm_ctx* c, const void* const* key_ptrs, void
   CK(cudaSetDevice(c->device));
   cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
   if (end > begin) {
-    const size_t chunks = (end - begin + 511) / 512;  // one warp per 512-pixel chunk, eight warps per block
-    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((chunks + 7) / 8, 148 * 8));
-    reduce_keys_p2p_kernel<<<blocks, 256, 0, s>>>(pp, world, rank, begin, end);
+    const size_t chunks = (end - begin + 511) / 512;  // one warp per 512-pixel chunk
+    if (max_blocks > 0) {
+      // confined to a few SMs (one 16-warp block each): runs BESIDE a fused kernel that leaves that many SMs idle
+      reduce_keys_p2p_kernel<16><<<(unsigned)std::max(1, std::min<int>(max_blocks, (int)((chunks + 15) / 16))), 512, 0, s>>>(
+          pp, world, rank, begin, end);
+    } else {
+      const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((chunks + 7) / 8, 148 * 8));
+      reduce_keys_p2p_kernel<8><<<blocks, 256, 0, s>>>(pp, world, rank, begin, end);
+    }
     c->launches++;
     CK(cudaGetLastError());
   }
   return GSM_OK;
+}
+
+extern "C" int gsm_reduce_keys_p2p(gsm_ctx* c, const void* const* key_ptrs, void* const* disp_ptrs, int world,
+                                   int rank, long long npx, void* stream) {
+  return reduce_keys_p2p(c, key_ptrs, disp_ptrs, world, rank, npx, stream, 0);
+}
+
+// Same, confined to at most max_blocks thread blocks of 512 threads (one per SM).  The fused aggregation kernel owns
+// every register of the SMs it runs on; when its grid leaves a few SMs idle (config 5 at 8 ranks: 24 strips x 1 chunk
+// x 6 bands = 144 CTAs on 148 SMs) the combine of the previous frame fits on those and runs beside it -- it is bound by
+// NVLink latency x bytes in flight, not by SMs.
+extern "C" int gsm_reduce_keys_p2p_ex(gsm_ctx* c, const void* const* key_ptrs, void* const* disp_ptrs, int world,
+                                      int rank, long long npx, void* stream, int max_blocks) {
+  return reduce_keys_p2p(c, key_ptrs, disp_ptrs, world, rank, npx, stream, max_blocks);
 }
 
 // ---- cost-stage exports ------------------------------------------------------------------------

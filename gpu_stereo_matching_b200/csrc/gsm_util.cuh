@@ -93,13 +93,14 @@ struct PeerPlanes {
 // (whole 128-byte lines over NVLink instead of 32 scattered 16-byte pieces), the next peer's eight vectors are in
 // flight while the current peer's are reduced, the 512 winners are transposed through 512 bytes of shared memory so
 // that every lane stores 16 contiguous bytes per map.
-__global__ void __launch_bounds__(256)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 reduce_keys_p2p_kernel(PeerPlanes pp, int world, int rank, size_t begin, size_t end) {
-  __shared__ __align__(16) u8 tr[8][512];
+  __shared__ __align__(16) u8 tr[WARPS][512];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const size_t nwarps = (size_t)gridDim.x * 8;
+  const size_t nwarps = (size_t)gridDim.x * WARPS;
   const size_t nchunks = (end - begin) / 512;
-  for (size_t ch = (size_t)blockIdx.x * 8 + wib; ch < nchunks; ch += nwarps) {
+  for (size_t ch = (size_t)blockIdx.x * WARPS + wib; ch < nchunks; ch += nwarps) {
     const size_t base = begin + ch * 512;
     longlong2 m[8], nx[8];
     const longlong2* own = reinterpret_cast<const longlong2*>(pp.keys[rank] + base) + lane;

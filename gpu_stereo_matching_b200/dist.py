@@ -60,6 +60,17 @@ def dsplit_row_bands(rows: int, cols: int, num_disp: int, world: int, radius: in
     return max(1, min(best, rows))
 
 
+def dsplit_spare_sms(rows: int, cols: int, num_disp: int, world: int, row_bands: int, sms: int = 148,
+                     strip_out_cols: int = 160) -> int:
+    """SMs the fused kernel of ONE rank of a disparity split leaves idle when its whole grid (strips x 32-disparity
+    chunks x row bands, one CTA per SM) fits the GPU in a single wave; 0 otherwise.  DsplitStream runs the peer-memory
+    combine on them."""
+    strips = -(-cols // strip_out_cols)
+    chunks_rank = -(-(-(-num_disp // WARP)) // world)
+    ctas = strips * chunks_rank * max(1, row_bands)
+    return sms - ctas if 0 < sms - ctas <= 16 else 0
+
+
 def key_init(mode: int, radius: int) -> int:
     """Initial packed word of the min plane (must be identical on every rank)."""
     if mode == 0:  # SAD: acceptance threshold 50*(2r+1)^2, d = 0  (BlockMatching.cpp:157-158)
@@ -225,9 +236,13 @@ class DsplitStream:
     """
 
     def __init__(self, ctx, partial_keys: Callable, planes: PeerPlanes, params, compute_stream, combine_stream,
-                 timing: bool = False):
+                 timing: bool = False, spare_sms: int = 0):
         import torch
         self.timing, self._marks = bool(timing), []
+        # SMs the fused kernel's grid leaves idle (0 = none / unknown).  With spare SMs the combine is confined to them
+        # and runs BESIDE the next frame's fused kernel; without, the fused kernel waits for the combine (they cannot
+        # share an SM: the fused kernel owns its whole register file) and only the passes in front of it overlap.
+        self.spare_sms = int(spare_sms)
         if planes.slots < 3:
             raise ValueError("DsplitStream needs PeerPlanes(slots=3)")
         if params.lr_check or params.median_radius:
@@ -253,7 +268,7 @@ class DsplitStream:
             if d1 > d0:
                 # the fused kernel owns every register of the SMs it runs on, so it cannot share them with the
                 # previous frame's combine: it waits for that combine, the passes in front of it run beside it
-                prev = self._combined
+                prev = self._combined if self.spare_sms <= 0 else None
                 self.partial(0, d0, d1, keys, prev.cuda_event if prev is not None else 0)
             else:
                 keys.fill_(key_init(self.params.mode, self.params.radius))
@@ -265,7 +280,8 @@ class DsplitStream:
             passed = torch.cuda.Event(enable_timing=self.timing)
             passed.record(self.s_side)
             self._passed[k] = passed
-            self.ctx.reduce_keys_p2p(pl.key_ptrs(slot, 0), pl.disp_ptrs(slot, 0), pl.rank, pl.npx, self.h_side)
+            self.ctx.reduce_keys_p2p(pl.key_ptrs(slot, 0), pl.disp_ptrs(slot, 0), pl.rank, pl.npx, self.h_side,
+                                     max_blocks=self.spare_sms)
             self._combined = torch.cuda.Event(enable_timing=self.timing)
             self._combined.record(self.s_side)
         if self.timing:

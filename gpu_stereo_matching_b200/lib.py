@@ -65,6 +65,7 @@ SYMBOLS = {
     "gsm_partial_keys_device_ex": (C.c_int, [_P, _PP, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "gsm_finalize_keys_device": (C.c_int, [_P, _PP, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "gsm_reduce_keys_p2p": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_int, C.c_longlong, _P]),
+    "gsm_reduce_keys_p2p_ex": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_int, C.c_longlong, _P, C.c_int]),
     "gsm_ad_volume": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "gsm_cost_slices": (C.c_int, [_P, _PP, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int]),
     "gsm_all_sad": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -154,6 +154,13 @@ int gsm_postfilter_device(gsm_ctx* ctx, const gsm_params* p, const void* disp_le
 int gsm_reduce_keys_p2p(gsm_ctx* ctx, const void* const* key_ptrs, void* const* disp_ptrs, int world, int rank,
                         long long npx, void* stream);
 
+/* Same, confined to at most max_blocks thread blocks (512 threads, one per SM; <= 0: unlimited).  The fused kernel owns
+ * every register of the SMs it runs on, so a concurrent combine only makes progress on SMs the fused grid leaves idle:
+ * with max_blocks = that number (config 5 at 8 ranks: 148 - 144 = 4) the combine of frame k runs beside the fused
+ * kernel of frame k+1 (dist.DsplitStream). */
+int gsm_reduce_keys_p2p_ex(gsm_ctx* ctx, const void* const* key_ptrs, void* const* disp_ptrs, int world, int rank,
+                           long long npx, void* stream, int max_blocks);
+
 /* ---- cost-stage exports (keep the reference's compareDiff / compareSAD checks possible) ------ */
 /* AD volume u8 [D][rows][cols] == PreCal, BlockMatching.cpp:89-109 (what compareDiff :263-276 checks). */
 int gsm_ad_volume(gsm_ctx* ctx, const uint8_t* left, const uint8_t* right, uint8_t* volume, int rows, int cols,

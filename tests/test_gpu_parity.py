@@ -868,13 +868,15 @@ def _p2p_worker(rank, world, port, out):
             c.partial_keys_device(Ld.data_ptr(), Rd.data_ptr(), keys.data_ptr(), h, w,
                                   g.make_params("gf", 9, D, row_bands=bands, d_begin=d0, d_end=d1), view, sh, wait_event)
 
-        pipe = DsplitStream(c, partial3, planes3, p, st, torch.cuda.Stream())
-        frames = [pipe.submit() for _ in range(7)]
-        pipe.flush()
-        st.synchronize()
         one, _ = c.stereo_batch(L, R, p)
-        for k in frames[-3:]:  # the three slots hold the last three frames
-            ok = ok and bool(np.array_equal(pipe.result(k).cpu().numpy().reshape(h, w), one))
+        for spare in (0, 4):  # 4: the combine confined to four SMs, running beside the next frame's fused kernel
+            pipe = DsplitStream(c, partial3, planes3, p, st, torch.cuda.Stream(), spare_sms=spare)
+            pipe.k = planes3.frame = 0
+            frames = [pipe.submit() for _ in range(7)]
+            pipe.flush()
+            st.synchronize()
+            for k in frames[-3:]:  # the three slots hold the last three frames
+                ok = ok and bool(np.array_equal(pipe.result(k).cpu().numpy().reshape(h, w), one))
         with open(out + f".{rank}", "w") as f:
             f.write("ok" if ok else "mismatch")
     finally:
