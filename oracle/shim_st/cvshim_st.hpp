@@ -51,8 +51,9 @@ struct Mat {
   Mat(Size s, int t) { create(s.height, s.width, t); }
   Mat(Size s, int t, const Scalar& v) {
     create(s.height, s.width, t);
-    assert(t == CV_32F);
-    for (size_t i = 0; i < (size_t)rows * cols; ++i) ((float*)data)[i] = (float)v.v;
+    assert(t == CV_32F || t == CV_8U);
+    if (t == CV_32F) for (size_t i = 0; i < (size_t)rows * cols; ++i) ((float*)data)[i] = (float)v.v;
+    else memset(data, (int)v.v, (size_t)rows * cols);
   }
   Mat(int r, int c, int t, void* d) : rows(r), cols(c), type_(t), data((uchar*)d) {}
   void create(int r, int c, int t) {
