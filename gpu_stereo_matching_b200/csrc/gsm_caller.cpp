@@ -4,6 +4,7 @@
 //   gsm_caller remapTest left right maps.f32 out_left [out_right]
 //   gsm_caller cvtColorTest src gray [--truncate]
 //   gsm_caller depth disp fB depth.f32
+//   gsm_caller stmatching left right disp [maxLevel=60] [scale=4] [sigma=0.1] [method=0|1]   (STMatching/main.cpp:37-70)
 //   gsm_caller gray src gray                          (host only: imread + cvtColor(BGR2GRAY) of Caller.cpp:12-16)
 //   gsm_caller batch list.txt [same options as singleFrame]
 //   gsm_caller                      (no arguments: the reference's singleFrame() with its own relative paths)
@@ -39,6 +40,10 @@ int main(int argc, char** argv) {
   if (!std::strcmp(cmd, "cvtColorTest") && argc >= 4)
     return gsm_caller::cvtColorTest(argv[2], argv[3], argc > 4 && !std::strcmp(argv[4], "--truncate"));
   if (!std::strcmp(cmd, "depth") && argc >= 5) return gsm_caller::depthFromDisparity(argv[2], (float)std::atof(argv[3]), argv[4]);
+  if (!std::strcmp(cmd, "stmatching") && argc >= 5)
+    return gsm_caller::segmentTreeStereo(argv[2], argv[3], argv[4], argc > 5 ? std::atoi(argv[5]) : 60,
+                                         argc > 6 ? std::atoi(argv[6]) : 4, argc > 7 ? (float)std::atof(argv[7]) : 0.1f,
+                                         argc > 8 ? std::atoi(argv[8]) : 0);
   if (!std::strcmp(cmd, "gray") && argc >= 4) {
     gsm_io::Image img;
     std::string err;
@@ -52,6 +57,7 @@ int main(int argc, char** argv) {
                "       gsm_caller remapTest left right maps.f32 out_left [out_right]\n"
                "       gsm_caller cvtColorTest src gray [--truncate]\n"
                "       gsm_caller depth disp fB depth.f32\n"
+               "       gsm_caller stmatching left right disp [maxLevel] [scale] [sigma] [method]\n"
                "       gsm_caller gray src gray\n"
                "       gsm_caller batch list.txt [options]\n");
   return 2;

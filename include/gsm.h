@@ -45,8 +45,12 @@ typedef enum {
 typedef enum {
   GSM_MODE_SAD = 0, /* clipped-window SAD + WTA with the reference quirks: bit-exact to getDisp,
                        BlockMatching.cpp:111-189 / kernalFindCorr, Device.cu:34-64 */
-  GSM_MODE_GF = 1   /* guided-filter aggregation (north_star; no reference implementation) + WTA over
-                       all d, strict '<' (STMatching/StereoHelper.cpp:131-154) */
+  GSM_MODE_GF = 1   /* guided-filter aggregation (north_star; no reference implementation: parity unpinned) + WTA
+                       over all d, lowest d on ties (STMatching/StereoHelper.cpp:131-154).  The WTA compares the
+                       fp32 cost with its 5 low mantissa bits cleared (they carry the lane index inside the warp
+                       reduction): costs closer than 2^-18 relative count as ties and resolve to the lowest d,
+                       where the reference's strict '<' on exact floats would keep the smaller one.  That is two
+                       orders of magnitude below the 1e-4 tolerance of the costs themselves. */
 } gsm_mode;
 
 /* Parameters of one stereo pass.  Zero-initialise, then set what you need. */

@@ -153,6 +153,38 @@ inline int depthFromDisparity(const char* disp_path, float fB, const char* depth
   return 0;
 }
 
+// ---- STMatching/main.cpp:37-70 (stereo_routine, StereoDisparity.cpp:41-56): segment-tree stereo, files in, file out --
+// leftImgPath rightImgPath dispImgPath [maxLevel = 60] [scale = 4] [sigma = 0.1] [method = 0 (ST-1) | 1 (ST-2)]
+inline int segmentTreeStereo(const char* left_path, const char* right_path, const char* disp_path, int max_level = 60,
+                             int scale = 4, float sigma = 0.1f, int method = 0, int device = 0) {
+  gsm_io::Image L, R;
+  std::string err;
+  if (!gsm_io::read_image(left_path, L, err) || !gsm_io::read_image(right_path, R, err)) return fail("segmentTreeStereo", err);
+  if (L.rows != R.rows || L.cols != R.cols) return fail("segmentTreeStereo", "left and right images differ in size");
+  if (L.channels < 3 || R.channels < 3) return fail("segmentTreeStereo", "3-channel images are expected (cv::imread default)");
+  const size_t n = (size_t)L.rows * L.cols;
+  std::vector<unsigned char> l3(3 * n), r3(3 * n), disp(n);
+  for (size_t i = 0; i < n; ++i)
+    for (int ch = 0; ch < 3; ++ch) {  // file order R, G, B -> cv::imread's B, G, R; alpha dropped
+      l3[3 * i + ch] = L.data[i * L.channels + 2 - ch];
+      r3[3 * i + ch] = R.data[i * R.channels + 2 - ch];
+    }
+  Ctx ctx(device, L.rows, L.cols, max_level, 1);
+  if (!ctx.c) return fail("segmentTreeStereo", gsm_last_error());
+  gsm_st_params p = {};
+  p.num_disp = max_level;
+  p.sigma = sigma;
+  p.tau = 1200.f;  // TAU, Toolkit.h:33
+  p.median_radius = 3;
+  p.scale = scale;
+  p.refined = method ? 1 : 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (gsm_segment_tree_stereo(ctx.c, &p, l3.data(), r3.data(), disp.data(), L.rows, L.cols) != GSM_OK)
+    return fail("segmentTreeStereo", gsm_last_error());
+  std::printf("GPU : %g\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  return gsm_io::write_gray(disp_path, disp.data(), L.rows, L.cols, err) ? 0 : fail("segmentTreeStereo", err);
+}
+
 // ---- batch front-end: a list of stereo pairs (any mix of sizes) in, one disparity file per pair out -------------------
 // list_path: one pair per line, "left right out"; the whole list runs as mixed-size batches (gsm_stereo_batch_v).
 inline int batchFrames(const char* list_path, const Options& o = Options(), int max_batch = 16) {

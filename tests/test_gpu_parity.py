@@ -206,6 +206,12 @@ def test_caller_frontend_from_disk(ctx, fx, orc, tmp_path):
         want = np.where(d > 0, fB / d.astype(np.float32), np.float32(0)).astype(np.float32)
     assert np.array_equal(depth, want)
     assert np.array_equal(ctx.disparity_to_depth(d, 52554.0), want)
+    # STMatching's command line (main.cpp:37-70) on the demo PNGs: == the library call on cv2.imread's BGR arrays
+    import cv2
+    subprocess.run([cli, "stmatching", os.path.join(art, "view1_.png"), os.path.join(art, "view5_.png"),
+                    str(tmp_path / "st.pgm"), "60", "4", "0.1", "1"], check=True, capture_output=True)
+    Lb, Rb = cv2.imread(os.path.join(art, "view1_.png")), cv2.imread(os.path.join(art, "view5_.png"))
+    assert np.array_equal(_read_pgm(tmp_path / "st.pgm"), ctx.segment_tree_stereo(Lb, Rb, 60, sigma=0.1, scale=4, refined=True))
     # batch front-end: the nine sets (three sizes) from a list file, one mixed-size batch
     lines = []
     for s_ in SETS:
