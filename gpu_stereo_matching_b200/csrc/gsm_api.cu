@@ -57,7 +57,8 @@ struct gsm_ctx {
   size_t st_bytes = 0;
   float* ring = nullptr;                                          // gf5_wta_kernel: per-SM rings of (a, b) rows (gsm_gf5.cuh)
   int ring_slots = 0;                                             // == %nsmid of the device
-  size_t ring_bytes = 0;
+  size_t ring_bytes = 0, l2_bytes = 0;
+  unsigned attr_gf5[2] = {0, 0};
   cudaEvent_t fused_wait = nullptr;                                // one-shot: the next fused kernel waits for it (gsm_partial_keys_device_ex)
   FrameDesc* ft_dev = nullptr;                                    // per-frame sizes of a mixed-size batch (max_batch entries)
   unsigned attr_sad[2] = {0, 0}, attr_gf[2] = {0, 0};             // radii whose kernels already carry the smem attribute
@@ -87,10 +88,22 @@ static int stage_halo_of(int /*mode*/, int radius) { return radius; }  // GF: st
 #ifndef GSM_GF_LPR
 #define GSM_GF_LPR 32
 #endif
+// GSM_GF_RING: which guided-filter kernel a launch uses.
+//   0: always gf3_wta_kernel (recomputes the (a, b) row that leaves the vertical window);
+//   2 (product): gf5_wta_kernel (gsm_gf5.cuh: reads that row back from a per-SM ring in global memory) for the radii
+//      whose rings stay in the L2 -- 148 rings x (2r+1) rows x 48 KB within 55 % of the L2: r <= 4 on a B200, where it is
+//      a tenth faster -- and gf3_wta_kernel for the larger radii, where the rings overflow the L2 and the ring kernel is
+//      HBM-bound (profiles/experiments_r02/ab_results.txt, calls 5-9);
+//   1 (experiments): gf5_wta_kernel for every radius.
 #ifndef GSM_GF_RING
-#define GSM_GF_RING 0  // 0 (product): gf3_wta_kernel recomputes the leaving (a, b) row; 1 (experiment, make EXTRA=-DGSM_GF_RING=1):
-                       // gf5_wta_kernel reads it back from a per-SM ring in global memory -- parity-green but HBM-bound (the
-                       // 138 MB of rings do not stay in the 126 MB L2): profiles/experiments_r02/ab_results.txt
+#define GSM_GF_RING 2
+#endif
+#if GSM_GF_RING == 1
+#define GSM_GF_RING_MAXR 9
+#elif GSM_GF_RING == 2
+#define GSM_GF_RING_MAXR 5  // gf5 is instantiated up to this radius; the L2 test below decides per device
+#else
+#define GSM_GF_RING_MAXR 0
 #endif
 #if GSM_GF_RING
 #include "gsm_gf5.cuh"
@@ -214,7 +227,8 @@ extern "C" int gsm_create(gsm_ctx** out, int device, int max_rows, int max_cols,
       if (st == cudaSuccess) st = cudaMemsetAsync(c->peak_buf, 0, sizeof(u32), c->stream);
     }
     c->ring_slots = (int)std::max<u32>(nsm, (u32)prop.multiProcessorCount);
-    c->ring_bytes = (size_t)c->ring_slots * 19 * gf5_ring_row_floats(GSM_GF_RUNS, GSM_GF_K, GSM_GF_LPR) * sizeof(float);
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    c->ring_bytes = (size_t)c->ring_slots * (2 * GSM_GF_RING_MAXR + 1) * gf5_ring_row_floats(GSM_GF_RUNS, GSM_GF_K, GSM_GF_LPR) * sizeof(float);
     A((void**)&c->ring, c->ring_bytes);
   }
 #endif
@@ -408,6 +422,34 @@ static int launch_sad(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols
 #define GF_KERNEL gf3_wta_kernel
 #define GF_CASES(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 
+// one radius instantiation of the guided-filter kernel(s)
+template <int r, bool EXPORT>
+static int launch_gf_r(gsm_ctx* c, const Plan& pl, bool use_ring, const u8* G, const u8* O, const float* stats, i64* keys,
+                       cudaStream_t s) {
+  constexpr int K = GSM_GF_K, runs = GSM_GF_RUNS, lpr = GSM_GF_LPR;
+#if GSM_GF_RING
+  if constexpr (r <= GSM_GF_RING_MAXR) {
+    if (use_ring) {
+      auto kfn = gf5_wta_kernel<r, K, runs, lpr, EXPORT>;
+      const size_t smem = gf5_smem_bytes(runs, K, (r + 3) / 4 * 4, lpr);
+      if (!(c->attr_gf5[EXPORT] >> r & 1u)) {
+        CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->attr_gf5[EXPORT] |= 1u << r;
+      }
+      kfn<<<pl.grid, pl.block, smem, s>>>(G, O, stats, keys, c->ring, pl.g);
+      return GSM_OK;
+    }
+  }
+#endif
+  auto kfn = gf3_wta_kernel<r, K, runs, lpr, EXPORT>;
+  if (!(c->attr_gf[EXPORT] >> r & 1u)) {  // once per context and kernel, not per launch
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    c->attr_gf[EXPORT] |= 1u << r;
+  }
+  kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);
+  return GSM_OK;
+}
+
 template <bool EXPORT>
 static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols, int d_begin, int d_end, float eps,
                      int view, const u8* G, const u8* O, i64* keys, cudaStream_t s, void* export_ptr, int ed0,
@@ -419,11 +461,7 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
   const int R = p->radius;
   const int HL4 = (R + 3) / 4 * 4;
   Plan pl = make_plan(p, n, rows, cols, d_begin, d_end, view, K, runs, stage_halo_of(GSM_MODE_GF, R), 6, HL4, lpr);
-#if GSM_GF_RING
-  pl.smem = gf5_smem_bytes(runs, K, HL4, lpr);
-#else
   pl.smem = gf3_smem_bytes(runs, K, HL4, lpr);
-#endif
   pl.g.ft = ft;
   pl.g.export_ptr = export_ptr;
   pl.g.export_d0 = ed0;
@@ -458,30 +496,20 @@ static int launch_gf(gsm_ctx* c, const gsm_params* p, int n, int rows, int cols,
     c->fused_wait = nullptr;
   }
   if ((rc = timing_begin(c, s))) return rc;
-  switch (R) {
+  // the ring kernel where the rings of this radius stay in the L2 (or always, in the experiment build)
+  bool use_ring = false;
 #if GSM_GF_RING
-#define X(r)                                                                                       \
-  case r: {                                                                                        \
-    auto kfn = gf5_wta_kernel<r, K, runs, lpr, EXPORT>;                                            \
-    if (!(c->attr_gf[EXPORT] >> r & 1u)) {                                                         \
-      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));    \
-      c->attr_gf[EXPORT] |= 1u << r;                                                               \
-    }                                                                                              \
-    kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, c->ring, pl.g);                      \
-    break;                                                                                         \
-  }
-#else
-#define X(r)                                                                                       \
-  case r: {                                                                                        \
-    auto kfn = gf3_wta_kernel<r, K, runs, lpr, EXPORT>;                                            \
-    if (!(c->attr_gf[EXPORT] >> r & 1u)) { /* once per context and kernel, not per launch */       \
-      CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));    \
-      c->attr_gf[EXPORT] |= 1u << r;                                                               \
-    }                                                                                              \
-    kfn<<<pl.grid, pl.block, pl.smem, s>>>(G, O, stats, keys, pl.g);                               \
-    break;                                                                                         \
+  if (c->ring && R <= GSM_GF_RING_MAXR) {
+    const size_t rings = (size_t)c->ring_slots * (2 * R + 1) * gf5_ring_row_floats(runs, K, lpr) * sizeof(float);
+    use_ring = GSM_GF_RING == 1 || (double)rings <= 0.55 * (double)c->l2_bytes;
   }
 #endif
+  switch (R) {
+#define X(r)                                                                                       \
+  case r: {                                                                                        \
+    if ((rc = launch_gf_r<r, EXPORT>(c, pl, use_ring, G, O, stats, keys, s))) return rc;           \
+    break;                                                                                         \
+  }
     GF_CASES(X)
 #undef X
     default:
