@@ -900,6 +900,19 @@ def test_peer_memory_combine_two_gpus(tmp_path):
     assert [open(out + f".{r}").read() for r in range(2)] == ["ok", "ok"]
 
 
+def test_peer_memory_streams_single_rank(tmp_path):
+    """The same worker with ONE rank (symmetric memory of a 1-rank group on one GPU): exercises dsplit_stereo_p2p (LR +
+    median, one barrier per frame) and both DsplitStream modes -- slots, cross-stream events, gsm_partial_keys_device_ex,
+    the combine confined to spare SMs -- on boxes with a single GPU, where the two-GPU test is skipped."""
+    import torch
+    import torch.multiprocessing as mp
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    out = str(tmp_path / "p2p1")
+    mp.spawn(_p2p_worker, args=(1, 29741, out), nprocs=1, join=True)
+    assert open(out + ".0").read() == "ok"
+
+
 def test_reference_gpu_code_agrees(ctx, fx, orc):
     """The reference's OWN CUDA code -- BlockMatching/Device.cu compiled unmodified for sm_100a into
     oracle/_ref/libdevref.so (`make -C oracle devref`, test infrastructure) -- run on this GPU: blockMatching_gpu,
