@@ -60,6 +60,7 @@ inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float sca
 inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t) {
   const int n = H * W;
   // ---- edges in the reference's sorted order: by weight, then by b, then by a (segment-graph.h:33-41)
+  static thread_local std::vector<Edge> e;  // work space reused across calls: fresh 4 MB allocations page-fault every time
   std::vector<int> cnt(257, 0);
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
@@ -69,7 +70,7 @@ inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float
     }
   for (int i = 0; i < 256; ++i) cnt[i + 1] += cnt[i];
   const int m = cnt[256];
-  std::vector<Edge> e(m);
+  e.resize(m);
   {
     std::vector<int> at(cnt.begin(), cnt.begin() + 256);
     for (int y = 0, b = 0; y < H; ++y)  // edges whose second endpoint is b, by increasing first endpoint a
@@ -104,7 +105,9 @@ inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float sca
   const int m = (int)e.size();
   // ---- segment_graph (segment-graph.h:48-101): adaptive-threshold Kruskal, then the remaining edges in the same order
   // join the segments into ONE tree; an edge between two segments of more than MIN_SIZE_SEG pixels is penalised
-  std::vector<uint8_t> used(m, 0);
+  static thread_local std::vector<uint8_t> used, adjd, deg, seen;
+  static thread_local std::vector<int> adj, depth;
+  used.assign(m, 0);
   {
     DisjointSets u(n, tau / 1.0f);
     int sets = n;
@@ -130,8 +133,9 @@ inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float sca
     }
   }
   // ---- adjacency in edge order (SegmentTree.cpp:70-94): at most 4 neighbours per pixel
-  std::vector<int> adj(4 * (size_t)n);
-  std::vector<uint8_t> adjd(4 * (size_t)n), deg(n, 0);
+  adj.resize(4 * (size_t)n);
+  adjd.resize(4 * (size_t)n);
+  deg.assign(n, 0);
   for (int i = 0; i < m; ++i) {
     if (!used[i]) continue;
     const int dis = std::min((int)(e[i].w * scale + 0.5f), 255);
@@ -142,8 +146,8 @@ inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float sca
   // ---- ordered tree: breadth-first from pixel 0 (SegmentTree.cpp:97-131)
   t.order.assign(n, 0); t.father.assign(n, -1); t.father_id.assign(n, 0); t.fdist.assign(n, 0);
   t.child0.assign(n, 0); t.nchild.assign(n, 0); t.level_off.clear();
-  std::vector<int> depth(n, 0);
-  std::vector<uint8_t> seen(n, 0);
+  depth.assign(n, 0);
+  seen.assign(n, 0);
   seen[0] = 1;
   int start = 0, end = 1;
   while (start < end) {
