@@ -51,6 +51,9 @@ struct Gf3Stage {
 #define GSM_GF_STAGES 3
 #endif
 constexpr int GF3_NST = GSM_GF_STAGES;
+#ifndef GSM_GF_INIT2
+#define GSM_GF_INIT2 1
+#endif
 #ifndef GSM_GF_MINB
 #define GSM_GF_MINB 1  // CTAs per SM the register allocation is sized for
 #endif
@@ -101,6 +104,20 @@ __host__ __device__ constexpr u32 range_mask(int i) {
 template <int R, int WW>
 __device__ __forceinline__ void gf3_init_sums(const u32 (&g)[WW], const u32 (&p)[WW], int& hp, int& hip) {
   constexpr int LO = 12 - R, HI = 12 + R;
+#if GSM_GF_INIT2
+  // two accumulators per sum: the dp4a chains are half as long (exact integers: the order does not matter)
+  u32 sp[2] = {0, 0}, sip[2] = {0, 0};
+#pragma unroll
+  for (int i = 0; i < WW; ++i) {
+    const u32 m = range_mask<LO, HI>(i);
+    if (m != 0) {
+      sp[i & 1] = __dp4a(p[i], m & 0x01010101u, sp[i & 1]);
+      sip[i & 1] = __dp4a(g[i] & m, p[i], sip[i & 1]);
+    }
+  }
+  hp = (int)(sp[0] + sp[1]);
+  hip = (int)(sip[0] + sip[1]);
+#else
   u32 sp = 0, sip = 0;
 #pragma unroll
   for (int i = 0; i < WW; ++i) {
@@ -112,6 +129,7 @@ __device__ __forceinline__ void gf3_init_sums(const u32 (&g)[WW], const u32 (&p)
   }
   hp = (int)sp;
   hip = (int)sip;
+#endif
 }
 
 #ifdef GSM_GF_PROFILE
