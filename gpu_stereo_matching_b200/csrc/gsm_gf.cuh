@@ -209,12 +209,14 @@ __device__ __forceinline__ void slide_ab(const u32 (&winA)[HL4 + K + HL4], const
   static_assert(R < K, "window must not reach beyond the adjacent runs");
   // One sliding chain over the K columns.  a: whole window sum of V_A; aL / aR: the part of it owned by the left /
   // right neighbour run (aL only shrinks, aR only grows as the window moves right); b: window sum of V_B.
-  float aL = 0.f, aO = 0.f, b = wsum_f<-R, R>(winB, HL4);
+  float aL = 0.f, aO = 0.f;
+  // the run's own columns first (registers), the neighbours' halo second (shared-memory loads still in flight); the two
+  // partial sums are separate accumulators, so the order changes nothing numerically
 #pragma unroll
-  for (int j = -R; j <= R; ++j) {
-    const float va = __uint_as_float(winA[HL4 + j]);
-    if (j < 0) aL += va; else aO += va;
-  }
+  for (int j = 0; j <= R; ++j) aO += __uint_as_float(winA[HL4 + j]);
+#pragma unroll
+  for (int j = -R; j < 0; ++j) aL += __uint_as_float(winA[HL4 + j]);
+  float b = wsum_f<-R, R>(winB, HL4);
   float a = aL + aO, aR = 0.f;
   A[0] = a;
   B[0] = fmaf(dl, aL, b);
