@@ -1180,7 +1180,8 @@ namespace {
 struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
   u8 *L3, *R3, *med, *wr, *wu, *nchild, *disp, *disp2, *dispL, *dispR, *mask;
   float *gL, *gR, *fw, *buf, *fin, *vol, *wrf, *wuf;
-  int *order, *father, *child0, *level_off, *pos;
+  int *order, *level_off, *pos;
+  int2 *up, *down;
   size_t bytes;
   StArena(void* base, size_t n, int D, bool with_vol) {
     size_t o = 0;
@@ -1190,7 +1191,7 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
     dispL = (u8*)take(n); dispR = (u8*)take(n); mask = (u8*)take(n);
     gL = (float*)take(4 * n); gR = (float*)take(4 * n); fw = (float*)take(4 * n);
     wrf = (float*)take(4 * n); wuf = (float*)take(4 * n);
-    order = (int*)take(4 * n); father = (int*)take(4 * n); child0 = (int*)take(4 * n); pos = (int*)take(4 * n);
+    order = (int*)take(4 * n); up = (int2*)take(8 * n); down = (int2*)take(8 * n); pos = (int*)take(4 * n);
     level_off = (int*)take(4 * (n + 2));
     buf = (float*)take(4 * n * D); fin = (float*)take(4 * n * D);
     vol = with_vol ? (float*)take(4 * n * D) : nullptr;
@@ -1245,16 +1246,23 @@ int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, fl
   gsm_st::weight_table(sigma, table);
   std::vector<float> fw(n);
   std::vector<int> pos(n);
-  for (size_t i = 0; i < n; ++i) { fw[i] = table[t.fdist[i]]; pos[t.order[i]] = (int)i; }
+  std::vector<int2> up(n), down(n);
+  for (size_t i = 0; i < n; ++i) {
+    fw[i] = table[t.fdist[i]];
+    pos[t.order[i]] = (int)i;
+    up[i] = make_int2(t.child0[i], (int)t.nchild[i]);
+    int wbits;
+    memcpy(&wbits, &fw[i], 4);
+    down[i] = make_int2(t.father[i], wbits);
+  }
   CK(cudaMemcpyAsync(a.order, t.order.data(), 4 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.father, t.father.data(), 4 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.child0, t.child0.data(), 4 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.nchild, t.nchild.data(), n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.up, up.data(), 8 * n, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(a.down, down.data(), 8 * n, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(a.fw, fw.data(), 4 * n, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(a.pos, pos.data(), 4 * n, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(a.level_off, t.level_off.data(), 4 * t.level_off.size(), cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));  // the host vectors go out of scope
-  dt->father = a.father; dt->fw = a.fw; dt->child0 = a.child0; dt->nchild = a.nchild; dt->level_off = a.level_off;
+  dt->up = a.up; dt->down = a.down; dt->fw = a.fw; dt->level_off = a.level_off;
   dt->levels = (int)t.level_off.size() - 1;
   dt->n = (int)n;
   return GSM_OK;

@@ -148,13 +148,13 @@ __global__ void st_edge_weight_depth_kernel(const u8* __restrict__ img, const u8
 // The ordered tree (breadth-first from pixel 0, SegmentTree.cpp:97-131) as arrays indexed by BFS position:
 //   father[i]  BFS position of the father (root: -1)      fw[i]  m_table[father.dist] = exp(-dist / (255 sigma))
 //   child0[i]  BFS position of the first child             nchild[i]  number of children
+// packed two per 8-byte word so that a node costs one load per pass
 // (children of a node are consecutive in BFS order, and in the order the reference's Filter visits them);
 // level_off[l] .. level_off[l+1] = the nodes of depth l.
 struct StTree {
-  const int* father;
-  const float* fw;
-  const int* child0;
-  const u8* nchild;
+  const int2* up;    // [i] = {child0, nchild}: pass 1 reads one 8-byte word per node
+  const int2* down;  // [i] = {father, float bits of the edge weight to the father}: pass 2 likewise
+  const float* fw;   // [i] = weight of the edge to the father (children's weights are contiguous: fw[child0 + z])
   const int* level_off;
   int levels, n;
 };
@@ -163,17 +163,17 @@ struct StTree {
 // Pass 1, leaves to root, level by level:  buf[i] += sum_z buf[child_z] * w_z   (children in list order, mul and add
 // rounded separately).  Pass 2, root to leaves:  fin[i] = w (fin[father] - w buf[i]) + buf[i].
 // One __syncthreads per level: a level only depends on the next / previous one, and the channels are independent.
+// Each level is two dependent rounds of L2 loads (node word + own value, then the children / the father).
 __global__ void __launch_bounds__(256) st_filter_kernel(float* __restrict__ buf, float* __restrict__ fin, StTree t) {
   float* b = buf + (size_t)blockIdx.x * t.n;
   float* f = fin + (size_t)blockIdx.x * t.n;
   for (int l = t.levels - 2; l >= 0; --l) {  // the deepest level has no children
     const int lo = t.level_off[l], hi = t.level_off[l + 1];
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      const int nc = t.nchild[i];
-      if (nc) {
-        float c = b[i];
-        const int c0 = t.child0[i];
-        for (int z = 0; z < nc; ++z) c = __fadd_rn(c, __fmul_rn(b[c0 + z], t.fw[c0 + z]));
+      const int2 u = t.up[i];
+      float c = b[i];
+      if (u.y) {
+        for (int z = 0; z < u.y; ++z) c = __fadd_rn(c, __fmul_rn(b[u.x + z], t.fw[u.x + z]));
         b[i] = c;
       }
     }
@@ -184,8 +184,9 @@ __global__ void __launch_bounds__(256) st_filter_kernel(float* __restrict__ buf,
   for (int l = 1; l < t.levels; ++l) {
     const int lo = t.level_off[l], hi = t.level_off[l + 1];
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      const float w = t.fw[i], cur = b[i];
-      f[i] = __fadd_rn(__fmul_rn(w, __fsub_rn(f[t.father[i]], __fmul_rn(w, cur))), cur);
+      const int2 dn = t.down[i];
+      const float w = __int_as_float(dn.y), cur = b[i];
+      f[i] = __fadd_rn(__fmul_rn(w, __fsub_rn(f[dn.x], __fmul_rn(w, cur))), cur);
     }
     __syncthreads();
   }
