@@ -54,7 +54,10 @@ struct gsm_ctx {
   struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
   // segment-tree stereo (gsm_st.cuh): one device arena, grown on demand
   void* st_buf = nullptr;
+  void* st_pin = nullptr;  // pinned host mirror of the arena's tree block + the weight / disparity read-back
+  size_t st_pin_bytes = 0;
   size_t st_bytes = 0;
+  int st_ring_smem[3] = {-1, -1, -1};  // dynamic shared memory st_filter_ring_kernel<16 / 8 / 4> may use, -1 = not asked yet
   float* ring = nullptr;                                          // gf5_wta_kernel: per-SM rings of (a, b) rows (gsm_gf5.cuh)
   int ring_slots = 0;                                             // == %nsmid of the device
   size_t ring_bytes = 0, l2_bytes = 0;
@@ -142,6 +145,7 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
                   c->ft_dev, c->ring, c->st_buf};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  if (c->st_pin) cudaFreeHost(c->st_pin);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
@@ -1177,9 +1181,20 @@ extern "C" int gsm_set_rectification(gsm_ctx* c, const float* mxl, const float* 
 
 // ---- segment-tree stereo (kernels in gsm_st.cuh, tree in gsm_st_host.hpp) --------------------------
 namespace {
+// The ordered tree as the device wants it, one contiguous block (same layout in the pinned host mirror: ONE copy).
+struct StTreeBlock {
+  size_t o_up, o_down, o_order, o_pos, o_level, bytes;
+  explicit StTreeBlock(size_t n) {
+    size_t o = 0;
+    auto take = [&](size_t b) { const size_t at = o; o += (b + 255) / 256 * 256; return at; };
+    o_up = take(8 * n); o_down = take(8 * n); o_order = take(4 * n); o_pos = take(4 * n); o_level = take(4 * (n + 2));
+    bytes = o;
+  }
+};
 struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
-  u8 *L3, *R3, *med, *wr, *wu, *nchild, *disp, *disp2, *dispL, *dispR, *mask;
-  float *gL, *gR, *fw, *buf, *fin, *vol, *wrf, *wuf;
+  u8 *L3, *R3, *med, *wr, *wu, *disp, *disp2, *dispL, *dispR, *mask;
+  float *gL, *gR, *buf, *fin, *vol, *wrf, *wuf;
+  char* tree;  // StTreeBlock
   int *order, *level_off, *pos;
   int2 *up, *down;
   size_t bytes;
@@ -1187,18 +1202,28 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
     size_t o = 0;
     auto take = [&](size_t b) { void* p = base ? (char*)base + o : nullptr; o += (b + 255) / 256 * 256; return p; };
     L3 = (u8*)take(3 * n); R3 = (u8*)take(3 * n); med = (u8*)take(3 * n);
-    wr = (u8*)take(n); wu = (u8*)take(n); nchild = (u8*)take(n); disp = (u8*)take(n); disp2 = (u8*)take(n);
+    wr = (u8*)take(n); wu = (u8*)take(n); disp = (u8*)take(n); disp2 = (u8*)take(n);
     dispL = (u8*)take(n); dispR = (u8*)take(n); mask = (u8*)take(n);
-    gL = (float*)take(4 * n); gR = (float*)take(4 * n); fw = (float*)take(4 * n);
+    gL = (float*)take(4 * n); gR = (float*)take(4 * n);
     wrf = (float*)take(4 * n); wuf = (float*)take(4 * n);
-    order = (int*)take(4 * n); up = (int2*)take(8 * n); down = (int2*)take(8 * n); pos = (int*)take(4 * n);
-    level_off = (int*)take(4 * (n + 2));
+    const StTreeBlock tb(n);
+    tree = (char*)take(tb.bytes);
+    up = (int2*)(tree + tb.o_up); down = (int2*)(tree + tb.o_down); order = (int*)(tree + tb.o_order);
+    pos = (int*)(tree + tb.o_pos); level_off = (int*)(tree + tb.o_level);
     buf = (float*)take(4 * n * D); fin = (float*)take(4 * n * D);
     vol = with_vol ? (float*)take(4 * n * D) : nullptr;
     bytes = o;
   }
 };
 int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol) {
+  const size_t pin = StTreeBlock(n).bytes + 8 * n;  // + two float weight planes (or two u8 ones)
+  if (c->st_pin_bytes < pin) {
+    if (c->st_pin) cudaFreeHost(c->st_pin);
+    c->st_pin = nullptr;
+    c->st_pin_bytes = 0;
+    CK(cudaHostAlloc(&c->st_pin, pin, cudaHostAllocDefault));
+    c->st_pin_bytes = pin;
+  }
   const size_t need = StArena(nullptr, n, D, with_vol).bytes;
   if (c->st_bytes >= need) return GSM_OK;
   if (c->st_buf) cudaFree(c->st_buf);
@@ -1221,50 +1246,81 @@ int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, fl
             StTree* dt, cudaStream_t s, const u8* disp = nullptr, const u8* mask = nullptr, int level = 0) {
   const size_t n = (size_t)rows * cols;
   const dim3 blk(128), grd((cols + 127) / 128, rows);
+  const StTreeBlock tb(n);
+  char* pin = (char*)c->st_pin;
+  char* pw = pin + tb.bytes;  // weight read-back area
   st_median3_kernel<<<grd, blk, 0, s>>>(img3, a.med, rows, cols);
   c->launches++;
   if (disp) {
     st_edge_weight_depth_kernel<<<grd, blk, 0, s>>>(a.med, disp, mask, (float)level, a.wrf, a.wuf, rows, cols);
     c->launches++;
     CK(cudaGetLastError());
-    std::vector<float> wr(n), wu(n);
-    CK(cudaMemcpyAsync(wr.data(), a.wrf, 4 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(wu.data(), a.wuf, 4 * n, cudaMemcpyDeviceToHost, s));
+    float *wr = (float*)pw, *wu = wr + n;
+    CK(cudaMemcpyAsync(wr, a.wrf, 4 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(wu, a.wuf, 4 * n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    gsm_st::build_tree_f(wr.data(), wu.data(), rows, cols, tau, /*CColorDepthWeight::GetScale*/ 255.0f, t);
+    gsm_st::build_tree_f(wr, wu, rows, cols, tau, /*CColorDepthWeight::GetScale*/ 255.0f, t);
   } else {
     st_edge_weight_kernel<<<grd, blk, 0, s>>>(a.med, a.wr, a.wu, rows, cols);
     c->launches++;
     CK(cudaGetLastError());
-    std::vector<u8> wr(n), wu(n);
-    CK(cudaMemcpyAsync(wr.data(), a.wr, n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(wu.data(), a.wu, n, cudaMemcpyDeviceToHost, s));
+    u8 *wr = (u8*)pw, *wu = wr + n;
+    CK(cudaMemcpyAsync(wr, a.wr, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(wu, a.wu, n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    gsm_st::build_tree(wr.data(), wu.data(), rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t);
+    gsm_st::build_tree(wr, wu, rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t);
   }
+  // the device form of the tree, written into the pinned mirror of the arena's tree block and sent as one copy
   float table[256];
   gsm_st::weight_table(sigma, table);
-  std::vector<float> fw(n);
-  std::vector<int> pos(n);
-  std::vector<int2> up(n), down(n);
+  int tbits[256];
+  memcpy(tbits, table, sizeof(tbits));
+  int2* up = (int2*)(pin + tb.o_up);
+  int2* down = (int2*)(pin + tb.o_down);
+  int* order = (int*)(pin + tb.o_order);
+  int* pos = (int*)(pin + tb.o_pos);
   for (size_t i = 0; i < n; ++i) {
-    fw[i] = table[t.fdist[i]];
-    pos[t.order[i]] = (int)i;
+    const int id = t.order[i];
+    order[i] = id;
+    pos[id] = (int)i;
     up[i] = make_int2(t.child0[i], (int)t.nchild[i]);
-    int wbits;
-    memcpy(&wbits, &fw[i], 4);
-    down[i] = make_int2(t.father[i], wbits);
+    down[i] = make_int2(t.father[i], tbits[t.fdist[i]]);
   }
-  CK(cudaMemcpyAsync(a.order, t.order.data(), 4 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.up, up.data(), 8 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.down, down.data(), 8 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.fw, fw.data(), 4 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.pos, pos.data(), 4 * n, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(a.level_off, t.level_off.data(), 4 * t.level_off.size(), cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));  // the host vectors go out of scope
-  dt->up = a.up; dt->down = a.down; dt->fw = a.fw; dt->level_off = a.level_off;
+  memcpy(pin + tb.o_level, t.level_off.data(), 4 * t.level_off.size());
+  CK(cudaMemcpyAsync(a.tree, pin, tb.o_level + 4 * t.level_off.size(), cudaMemcpyHostToDevice, s));
+  // (the pinned block is next written by the next st_tree call, which first synchronises on the weight read-back)
+  dt->up = a.up; dt->down = a.down; dt->level_off = a.level_off;
   dt->levels = (int)t.level_off.size() - 1;
   dt->n = (int)n;
+  dt->max_width = 0;
+  for (size_t l = 0; l + 1 < t.level_off.size(); ++l) dt->max_width = std::max(dt->max_width, t.level_off[l + 1] - t.level_off[l]);
+  return GSM_OK;
+}
+// the tree filter over D channels: the on-chip ring kernel with the deepest ring the widest level allows, else the plain one
+template <int RING>
+bool st_filter_ring_try(gsm_ctx* c, float* buf, float* fin, const StTree& dt, int D, cudaStream_t s, int slot) {
+  if (c->st_ring_smem[slot] < 0) {  // once per context: how much dynamic shared memory this instance may use
+    int optin = 0;
+    cudaFuncAttributes fa;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess ||
+        cudaFuncGetAttributes(&fa, st_filter_ring_kernel<RING>) != cudaSuccess)
+      return false;
+    const int dyn = optin - (int)fa.sharedSizeBytes;
+    if (cudaFuncSetAttribute(st_filter_ring_kernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn) != cudaSuccess) return false;
+    c->st_ring_smem[slot] = dyn;
+  }
+  const int cap = (dt.max_width + 3) & ~3;
+  const size_t smem = (size_t)RING * (cap + ST_PAD) * 16;
+  if (smem > (size_t)c->st_ring_smem[slot]) return false;
+  st_filter_ring_kernel<RING><<<D, 256, smem, s>>>(buf, fin, dt, cap);
+  return true;
+}
+int st_filter_launch(gsm_ctx* c, float* buf, float* fin, const StTree& dt, int D, cudaStream_t s) {
+  static const int force_plain = getenv("GSM_ST_PLAIN_FILTER") ? atoi(getenv("GSM_ST_PLAIN_FILTER")) : 0;
+  if (force_plain || !(st_filter_ring_try<16>(c, buf, fin, dt, D, s, 0) || st_filter_ring_try<8>(c, buf, fin, dt, D, s, 1) ||
+                       st_filter_ring_try<4>(c, buf, fin, dt, D, s, 2)))
+    st_filter_kernel<<<D, 256, 0, s>>>(buf, fin, dt);
+  c->launches++;
   return GSM_OK;
 }
 }  // namespace
@@ -1275,7 +1331,7 @@ int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, fl
 extern "C" int gsm_st_build_tree_host(const uint8_t* wr, const uint8_t* wu, int rows, int cols, float tau, int* order,
                                       int* father_id, uint8_t* father_dist, int* levels) {
   if (!wr || !wu || rows < 1 || cols < 1) return fail(GSM_ERR_INVALID, "gsm_st_build_tree_host: bad arguments");
-  gsm_st::Tree t;
+  static thread_local gsm_st::Tree t;
   gsm_st::build_tree(wr, wu, rows, cols, tau > 0.f ? tau : 1200.f, 1.0f, t);
   const size_t n = (size_t)rows * cols;
   if (order) memcpy(order, t.order.data(), 4 * n);
@@ -1321,7 +1377,7 @@ extern "C" int gsm_st_filter(gsm_ctx* c, const uint8_t* image3, float* cost, int
   const StArena a(c->st_buf, n, num_disp, true);
   cudaStream_t s = c->stream;
   CK(cudaMemcpyAsync(a.L3, image3, 3 * n, cudaMemcpyHostToDevice, s));
-  gsm_st::Tree t;
+  static thread_local gsm_st::Tree t;  // its arrays are reused: fresh ones page-fault on every call
   StTree dt;
   if ((rc = st_tree(c, a, a.L3, rows, cols, sigma, tau, t, &dt, s))) return rc;
   if (order) memcpy(order, t.order.data(), 4 * n);
@@ -1331,13 +1387,13 @@ extern "C" int gsm_st_filter(gsm_ctx* c, const uint8_t* image3, float* cost, int
     CK(cudaMemcpyAsync(a.vol, cost, 4 * n * num_disp, cudaMemcpyHostToDevice, s));
     const dim3 g2((unsigned)((n + 255) / 256), num_disp);
     st_permute_kernel<<<g2, 256, 0, s>>>(a.vol, a.order, a.buf, (int)n, num_disp);
-    st_filter_kernel<<<num_disp, 256, 0, s>>>(a.buf, a.fin, dt);
+    if ((rc = st_filter_launch(c, a.buf, a.fin, dt, num_disp, s))) return rc;
     st_unpermute_kernel<<<g2, 256, 0, s>>>(a.fin, a.order, a.vol, (int)n, num_disp);
-    c->launches += 3;
+    c->launches += 2;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cost, a.vol, 4 * n * num_disp, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
   }
+  CK(cudaStreamSynchronize(s));
   return GSM_OK;
 }
 
@@ -1362,7 +1418,7 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
   st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.R3, a.gR, rows, cols);
   c->launches += 2;
-  gsm_st::Tree t;
+  static thread_local gsm_st::Tree t;  // its arrays are reused: fresh ones page-fault on every call
   StTree dt;
   const float tau = p->tau > 0.f ? p->tau : 1200.f;
   const unsigned gn = (unsigned)((n + 255) / 256);
@@ -1373,9 +1429,9 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
     // the cost kernel writes straight into the [D][BFS position] layout the filter works on
     if (right) st_cost_right_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
     else st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
-    st_filter_kernel<<<D, 256, 0, s>>>(a.buf, a.fin, dt);
+    if ((r = st_filter_launch(c, a.buf, a.fin, dt, D, s))) return r;
     st_wta_kernel<<<gn, 256, 0, s>>>(a.fin, a.order, a.disp, (int)n, D);
-    c->launches += 3;
+    c->launches += 2;
     *out = a.disp;
     if (p->median_radius > 0) {
       if ((r = median_launch(c, a.disp, a.disp2, 1, rows, cols, p->median_radius, s))) return r;

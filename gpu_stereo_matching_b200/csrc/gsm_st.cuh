@@ -154,9 +154,9 @@ __global__ void st_edge_weight_depth_kernel(const u8* __restrict__ img, const u8
 struct StTree {
   const int2* up;    // [i] = {child0, nchild}: pass 1 reads one 8-byte word per node
   const int2* down;  // [i] = {father, float bits of the edge weight to the father}: pass 2 likewise
-  const float* fw;   // [i] = weight of the edge to the father (children's weights are contiguous: fw[child0 + z])
   const int* level_off;
   int levels, n;
+  int max_width;  // nodes of the widest level
 };
 
 // CSegmentTree::Filter (SegmentTree.cpp:148-181) for one disparity channel per CTA: buf / fin are [D][n] in BFS order.
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) st_filter_kernel(float* __restrict__ buf,
       const int2 u = t.up[i];
       float c = b[i];
       if (u.y) {
-        for (int z = 0; z < u.y; ++z) c = __fadd_rn(c, __fmul_rn(b[u.x + z], t.fw[u.x + z]));
+        for (int z = 0; z < u.y; ++z) c = __fadd_rn(c, __fmul_rn(b[u.x + z], __int_as_float(t.down[u.x + z].y)));
         b[i] = c;
       }
     }
@@ -189,6 +189,148 @@ __global__ void __launch_bounds__(256) st_filter_kernel(float* __restrict__ buf,
       f[i] = __fadd_rn(__fmul_rn(w, __fsub_rn(f[dn.x], __fmul_rn(w, cur))), cur);
     }
     __syncthreads();
+  }
+}
+
+// The same two passes with the level-to-level dependency kept ON CHIP.  A level only ever reads the level next to it
+// (its children in pass 1, its fathers in pass 2), and the nodes of a level are contiguous in BFS order, so:
+//   * everything a level needs that does NOT depend on the neighbouring level -- its node words, its own values, the
+//     edge weights -- is a set of contiguous ranges, fetched RING - 2 levels ahead with cp.async into a ring of RING
+//     level slots in shared memory (the level offsets themselves ride one step ahead in registers);
+//   * the values the neighbouring level produced are read from that level's ring slot, not from L2.
+// The per-level critical path drops from two dependent L2 round trips to a shared-memory read and one barrier.
+// `cap` = slot capacity in nodes (>= the widest level; the host picks RING, or st_filter_kernel when nothing fits).
+// Arithmetic and its order are those of st_filter_kernel (bit-identical results).
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Warps 0-3 compute, warps 4-7 fetch (the two halves meet at the one barrier per level): what bounds a level is the
+// instruction chain of the slowest warp, so the address arithmetic of the fetches is kept off the computing warps.
+constexpr int ST_PAD = 4;  // a slot is cap + ST_PAD entries: the branch-free child loop reads up to 3 entries past a level
+template <int RING>
+__global__ void __launch_bounds__(256) st_filter_ring_kernel(float* __restrict__ buf, float* __restrict__ fin, StTree t,
+                                                             int cap) {
+  static_assert(RING >= 4, "ring = the neighbouring level + the current one + at least two in flight");
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  const int slot = cap + ST_PAD;
+  int2* s_meta = reinterpret_cast<int2*>(st_smem);                     // [RING][slot] node words
+  float* s_val = reinterpret_cast<float*>(s_meta + (size_t)RING * slot);  // [RING][slot] own value -> pass-1 sum
+  float* s_aux = s_val + (size_t)RING * slot;                          // [RING][slot] pass 1: edge weights; pass 2: results
+  const u32 a_meta = smem_u32(s_meta), a_val = smem_u32(s_val), a_aux = smem_u32(s_aux);
+  float* b = buf + (size_t)blockIdx.x * t.n;
+  float* f = fin + (size_t)blockIdx.x * t.n;
+  const int L = t.levels;
+  const int* __restrict__ off = t.level_off;
+  constexpr int AHEAD = RING - 2, HALF = 128;
+  const bool producer = threadIdx.x >= HALF;
+  const int tid = threadIdx.x & (HALF - 1);
+  auto cp8 = [](u32 dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); };
+  auto cp4 = [](u32 dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); };
+
+  // ---- pass 1: leaves to root.  Levels run downwards, so level li is [off[li], hi) with hi = the previous level's lo.
+  if (producer) {
+    auto fetch = [&](int li, int lo, int hi) {
+      if (li >= 0) {
+        const int so = (li % RING) * slot;
+        for (int i = tid; i < hi - lo; i += HALF) {
+          cp8(a_meta + 8 * (so + i), t.up + lo + i);
+          cp4(a_val + 4 * (so + i), b + lo + i);
+          cp4(a_aux + 4 * (so + i), &t.down[lo + i].y);
+        }
+      }
+      cp_async_commit();
+    };
+    int f_hi = off[L], f_lo = off[L - 1];  // the level being fetched
+    for (int k = 0; k < AHEAD; ++k) {
+      fetch(L - 1 - k, f_lo, f_hi);
+      f_hi = f_lo;
+      f_lo = L - 2 - k >= 0 ? off[L - 2 - k] : 0;
+    }
+    int f_nlo = L - 2 - AHEAD >= 0 ? off[L - 2 - AHEAD] : 0;
+    for (int l = L - 1; l >= 0; --l) {
+      cp_async_wait<AHEAD - 1>();  // this thread's share of level l has landed
+      __syncthreads();             // level l+1 is complete, the slot of level l+2 is free
+      const int f_nn = l - AHEAD - 2 >= 0 ? off[l - AHEAD - 2] : 0;  // used two steps on
+      fetch(l - AHEAD, f_lo, f_hi);
+      f_hi = f_lo; f_lo = f_nlo; f_nlo = f_nn;
+    }
+    cp_async_wait<0>();
+  } else {
+    int c_hi = off[L], c_lo = off[L - 1], c_nlo = L >= 2 ? off[L - 2] : 0;  // the level being computed
+    for (int l = L - 1; l >= 0; --l) {
+      __syncthreads();
+      const int c_nn = l - 2 >= 0 ? off[l - 2] : 0;
+      const int so = (l % RING) * slot, co = ((l + 1) % RING) * slot - c_hi;  // children (level l+1) start at position c_hi
+      for (int i = tid; i < c_hi - c_lo; i += HALF) {
+        const int2 u = s_meta[so + i];
+        const float* cv = s_val + co + u.x;
+        const float* cw = s_aux + co + u.x;
+        float c = s_val[so + i];
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {  // a grid pixel has at most 4 neighbours; entries past u.y are read and dropped
+          const float cz = __fadd_rn(c, __fmul_rn(cv[z], cw[z]));
+          c = z < u.y ? cz : c;
+        }
+        if (u.y) {
+          s_val[so + i] = c;
+          b[c_lo + i] = c;
+        }
+      }
+      c_hi = c_lo; c_lo = c_nlo; c_nlo = c_nn;
+    }
+  }
+  __syncthreads();  // pass 1's global writes are visible to pass 2's fetches; every ring slot is free
+
+  // ---- pass 2: root to leaves
+  auto offc = [&](int li) { return off[min(li, L)]; };
+  if (producer) {
+    auto fetch = [&](int li, int lo, int hi) {
+      if (li < L) {
+        const int so = (li % RING) * slot;
+        for (int i = tid; i < hi - lo; i += HALF) {
+          cp8(a_meta + 8 * (so + i), t.down + lo + i);
+          cp4(a_val + 4 * (so + i), b + lo + i);
+        }
+      }
+      cp_async_commit();
+    };
+    int f_lo = 0, f_hi = offc(1);
+    for (int k = 0; k < AHEAD; ++k) {
+      fetch(k, f_lo, f_hi);
+      f_lo = f_hi;
+      f_hi = offc(k + 2);
+    }
+    int f_nhi = offc(AHEAD + 2);
+    for (int l = 0; l < L; ++l) {
+      cp_async_wait<AHEAD - 1>();
+      __syncthreads();
+      const int f_nn = offc(l + AHEAD + 3);
+      fetch(l + AHEAD, f_lo, f_hi);
+      f_lo = f_hi; f_hi = f_nhi; f_nhi = f_nn;
+    }
+    cp_async_wait<0>();
+  } else {
+    int c_lo = 0, c_hi = offc(1), c_nhi = offc(2), p_lo = 0;
+    for (int l = 0; l < L; ++l) {
+      __syncthreads();
+      const int c_nn = offc(l + 3);
+      const int so = (l % RING) * slot, po = ((l + RING - 1) % RING) * slot - p_lo;  // fathers (level l-1) start at p_lo
+      for (int i = tid; i < c_hi - c_lo; i += HALF) {
+        const int2 dn = s_meta[so + i];
+        const float w = __int_as_float(dn.y), cur = s_val[so + i];
+        const float r = l ? __fadd_rn(__fmul_rn(w, __fsub_rn(s_aux[po + dn.x], __fmul_rn(w, cur))), cur) : cur;
+        s_aux[so + i] = r;
+        f[c_lo + i] = r;
+      }
+      p_lo = c_lo; c_lo = c_hi; c_hi = c_nhi; c_nhi = c_nn;
+    }
   }
 }
 

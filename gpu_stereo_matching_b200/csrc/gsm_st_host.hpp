@@ -3,14 +3,23 @@
 // CSegmentTree::BuildSegmentTree (STMatching/SegmentTree.cpp:38-139) with segment_graph (segment-graph.h:48-101) is
 // Kruskal's algorithm with Felzenszwalb's adaptive merge threshold: whether an edge joins two components depends on
 // the sizes of the components all lighter edges have formed, i.e. on the sequential order of the sorted edge list.
-// It is therefore built on the host -- but in O(N): the edge weights of CColorWeight are integers 0..255, so the
-// reference's std::sort by (w, b, a) (segment-graph.h:33-41) is a counting sort over w whose buckets are filled in
-// (b, a) order by construction.  The result is the reference's ordered tree (breadth-first from pixel 0,
-// SegmentTree.cpp:97-131), node for node: same father, same quantised edge weight, same order of the children.
+// It is therefore built on the host -- in O(N), and around the fact that the graph is the pixel GRID:
+//   * an edge is one 32-bit word (lower/left pixel << 1 | direction); the reference's std::sort by (w, b, a)
+//     (segment-graph.h:33-41) is a stable counting sort (integer weights of CColorWeight) or a stable 3-pass radix sort
+//     (float weights of CColorDepthWeight) of the edges enumerated in (b, a) order;
+//   * which edges the two Kruskal passes keep (and which the second one penalises) is four bits per pixel;
+//   * the reference's adjacency lists "in edge order" (SegmentTree.cpp:70-94) are, per pixel, its <= 4 kept grid edges
+//     sorted by (w, b, a) -- a local sort done in one raster pass, no scattered list building;
+//   * the breadth-first ordering (SegmentTree.cpp:97-131) reads one 8-byte record per node; in a tree the only visited
+//     neighbour is the father, so there is no visited map.
+// The result is the reference's ordered tree node for node: same father, same quantised edge weight, same order of the
+// children (tests/test_oracle.py compares it with the reference's own tree).
 #pragma once
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <type_traits>
 #include <vector>
 
 namespace gsm_st {
@@ -25,150 +34,229 @@ struct Tree {
   std::vector<int> level_off;   // level l = BFS positions [level_off[l], level_off[l+1])
 };
 
-struct DisjointSets {  // union by rank with path compression (disjoint-set.h:36-82); only connectivity and component
-  std::vector<int> p;   // sizes are observable, and those do not depend on the variant.  The parent array is on its own
-  struct Info { int size, rank; float thr; };  // (find touches nothing else); size, rank and the component's merge
-  std::vector<Info> info;                       // threshold are only read at roots
-  DisjointSets(int n, float thr0) : p(n), info(n) {
-    for (int i = 0; i < n; ++i) { p[i] = i; info[i].size = 1; info[i].rank = 0; info[i].thr = thr0; }
-  }
-  int find(int x) {
-    int y = p[x];
-    if (y == x) return x;
-    while (y != p[y]) y = p[y];
-    while (p[x] != y) { const int nx = p[x]; p[x] = y; x = nx; }
+namespace detail {
+
+// Union-find with path compression (disjoint-set.h:36-82).  The reference unions by rank; only connectivity and the
+// component sizes are observable, and those do not depend on the variant -- union by size needs no rank array.
+// The chains stay short (0.7 hops per find on natural images), so what a textbook loop costs here is its branch
+// mispredictions, not its loads: find() always takes two hops (a root points at itself, extra hops are harmless) and
+// falls into a loop only when that was not enough.
+struct Sets {
+  int* p;
+  int* size;
+  float* thr;  // the component's merge threshold, read at roots only
+  int find(int x) const {
+    const int x1 = p[x];
+    int y = p[x1];
+    if (__builtin_expect(p[y] != y, 0)) {
+      while (y != p[y]) y = p[y];
+      int z = x1;
+      while (p[z] != y) { const int nz = p[z]; p[z] = y; z = nz; }
+    }
+    p[x] = y;
     return y;
   }
-  int join(int a, int b) {  // a, b roots; returns the new root
-    if (info[a].rank > info[b].rank) std::swap(a, b);
-    p[a] = b;
-    info[b].size += info[a].size;
-    if (info[a].rank == info[b].rank) info[b].rank++;
-    return b;
+};
+
+struct Work {  // reused across calls: fresh multi-megabyte allocations page-fault every time
+  std::vector<uint32_t> code, code2;
+  std::vector<float> ws;
+  std::vector<uint32_t> key, key2;
+  std::vector<int> p, size;
+  std::vector<float> thr;
+  std::vector<uint8_t> flags;
+  std::vector<uint64_t> rec;
+};
+inline Work& work() {
+  static thread_local Work w;
+  return w;
+}
+
+enum : uint8_t { USED_R = 1, USED_U = 2, PEN_R = 4, PEN_U = 8 };
+
+// code[i] (sorted by (w, b, a)), ws[i] = the edge's weight.  wgt(p, dir) = weight of pixel p's right (0) / up (1) edge.
+template <class W>
+inline void finish(int H, int Wd, int m, float tau, float scale, const W& wgt, Tree& t) {
+  Work& k = work();
+  const int n = H * Wd;
+  const uint32_t* code = k.code.data();
+  const float* ws = k.ws.data();
+  k.p.resize(n); k.size.resize(n); k.thr.resize(n);
+  k.flags.assign(n, 0);
+  uint8_t* flags = k.flags.data();
+  Sets u{k.p.data(), k.size.data(), k.thr.data()};
+  for (int i = 0; i < n; ++i) { u.p[i] = i; u.size[i] = 1; u.thr[i] = tau / 1.0f; }
+  // ---- segment_graph (segment-graph.h:48-101), pass 1: adaptive-threshold Kruskal
+  // (branch-free body: whether an edge merges is a coin flip the predictor loses; a rejected edge "joins" a root to itself)
+  int sets = n;
+  for (int i = 0; i < m; ++i) {
+    const int a = (int)(code[i] >> 1), dir = (int)(code[i] & 1), b = dir ? a - Wd : a + 1;
+    const int ra = u.find(a), rb = u.find(b);
+    const float w = ws[i];
+    const bool ok = (ra != rb) & (w <= u.thr[ra]) & (w <= u.thr[rb]);
+    const bool sw = u.size[ra] > u.size[rb];
+    const int sm = sw ? rb : ra, bg = sw ? ra : rb;  // the smaller root goes under the bigger one
+    u.p[sm] = ok ? bg : sm;
+    const int sz = u.size[bg] + (ok ? u.size[sm] : 0);
+    u.size[bg] = sz;
+    const float th = w + tau / (float)sz;
+    u.thr[bg] = ok ? th : u.thr[bg];
+    flags[a] |= (uint8_t)((int)ok << dir);  // USED_R / USED_U
+    sets -= (int)ok;
   }
-};
+  // ---- pass 2: the remaining edges, in the same order, join the segments into ONE tree; an edge between two segments
+  // of more than MIN_SIZE_SEG pixels is penalised.  Labels first: with every pixel pointing at its root, an edge inside
+  // a segment (most of them) is rejected by one comparison, and the finds that remain are one hop.
+  if (sets > 1) {
+    for (int i = 0; i < n; ++i) u.p[i] = u.find(i);
+    for (int i = 0; i < m && sets > 1; ++i) {  // once one component is left no further edge can join anything
+      const int a = (int)(code[i] >> 1), dir = (int)(code[i] & 1), b = dir ? a - Wd : a + 1;
+      if (u.p[a] == u.p[b]) continue;  // same segment (this also covers every edge pass 1 used)
+      const int ra = u.find(a), rb = u.find(b);
+      if (ra != rb) {
+        const int size_min = std::min(u.size[ra], u.size[rb]);
+        const bool sw = u.size[ra] > u.size[rb];
+        const int sm = sw ? rb : ra, bg = sw ? ra : rb;
+        u.p[sm] = bg;
+        u.size[bg] += u.size[sm];
+        --sets;
+        flags[a] |= (uint8_t)((USED_R << dir) | (size_min > 50 ? PEN_R << dir : 0));  // MIN_SIZE_SEG, PENALTY_CROSS_SEG
+      }
+    }
+  }
+  // ---- per pixel: its kept edges in edge-list order (SegmentTree.cpp:70-94).  Ties in w are ordered by (b, a): the
+  // up neighbour (b = p - W), the left one (b = p, a = p - 1), the one below (b = p, a = p + W), the right one (b = p + 1).
+  // rec = deg | dir codes (2 bits each) << 8 | quantised distances << 32
+  k.rec.resize(n);
+  uint64_t* rec = k.rec.data();
+  uint8_t qlut[261];  // integer weights: min((int)((w [+ 5]) * scale + 0.5f), 255), w + 5 is exact in float
+  for (int v = 0; v < 261; ++v) qlut[v] = (uint8_t)std::min((int)((float)v * scale + 0.5f), 255);
+  // item = sort key (weight bits, then tie rank) << 10 | direction << 8 | quantised distance; an absent edge sorts last
+  // (weights are >= 0: the bit pattern of the float orders like the value)
+  auto item = [&](bool used, bool pen, int q, int dir, uint64_t dcode) -> uint64_t {
+    const auto wq = wgt(q, dir);
+    uint64_t key, dq;
+    if (std::is_integral<decltype(wq)>::value) {
+      key = (uint64_t)wq;
+      dq = qlut[(int)wq + (pen ? 5 : 0)];
+    } else {
+      float w = (float)wq;
+      uint32_t wb;
+      std::memcpy(&wb, &w, 4);
+      key = wb;
+      if (pen) w += 5.0f;
+      dq = (uint64_t)std::min((int)(w * scale + 0.5f), 255);
+    }
+    const uint64_t it = key << 12 | dcode << 10 | dcode << 8 | dq;
+    return used ? it : ~0ull;
+  };
+  auto cswap = [](uint64_t& x, uint64_t& y) { const uint64_t lo = std::min(x, y), hi = std::max(x, y); x = lo; y = hi; };
+  for (int y = 0, p = 0; y < H; ++y)
+    for (int x = 0; x < Wd; ++x, ++p) {
+      const int f = flags[p], fl = x > 0 ? flags[p - 1] : 0, fd = y + 1 < H ? flags[p + Wd] : 0;
+      uint64_t i0 = item(f & USED_U, f & PEN_U, p, 1, 0);
+      uint64_t i1 = item(fl & USED_R, fl & PEN_R, x > 0 ? p - 1 : p, 0, 1);
+      uint64_t i2 = item(fd & USED_U, fd & PEN_U, y + 1 < H ? p + Wd : p, 1, 2);
+      uint64_t i3 = item(f & USED_R, f & PEN_R, p, 0, 3);
+      cswap(i0, i1); cswap(i2, i3); cswap(i0, i2); cswap(i1, i3); cswap(i1, i2);
+      const uint64_t deg = (uint64_t)((f & USED_U) != 0) + ((fl & USED_R) != 0) + ((fd & USED_U) != 0) + ((f & USED_R) != 0);
+      rec[p] = deg | ((i0 >> 8) & 3) << 8 | ((i1 >> 8) & 3) << 10 | ((i2 >> 8) & 3) << 12 | ((i3 >> 8) & 3) << 14 |
+               (i0 & 255) << 32 | (i1 & 255) << 40 | (i2 & 255) << 48 | (i3 & 255) << 56;
+    }
+  // ---- ordered tree: breadth-first from pixel 0 (SegmentTree.cpp:97-131)
+  // (branch-free body: all four slots of a record are written, `end` only moves past the real children; the arrays
+  // carry 4 spare entries for the writes past the last node)
+  t.order.resize(n + 4); t.father.resize(n + 4); t.father_id.resize(n + 4); t.fdist.resize(n + 4);
+  t.child0.resize(n); t.nchild.resize(n); t.level_off.clear();
+  int* order = t.order.data();
+  int* father = t.father.data();
+  int* father_id = t.father_id.data();
+  uint8_t* fdist = t.fdist.data();
+  const int delta[4] = {-Wd, -1, Wd, 1};
+  order[0] = 0; father[0] = -1; father_id[0] = 0; fdist[0] = 0;
+  t.level_off.push_back(0);
+  int end = 1, level_end = 1;
+  for (int pos = 0; pos < n; ++pos) {
+    if (pos == level_end) { t.level_off.push_back(pos); level_end = end; }
+    if (pos + 8 < end) __builtin_prefetch(&rec[order[pos + 8]]);
+    const int id = order[pos], fid = pos ? father_id[pos] : -1;
+    const uint64_t r = rec[id];
+    const int deg = (int)(r & 7), e0 = end;
+    for (int j = 0; j < 4; ++j) {
+      const int c = id + delta[(r >> (8 + 2 * j)) & 3];
+      order[end] = c;
+      father[end] = pos;
+      father_id[end] = id;
+      fdist[end] = (uint8_t)(r >> (32 + 8 * j));
+      end += (int)((j < deg) & (c != fid));
+    }
+    t.child0[pos] = e0;
+    t.nchild[pos] = (uint8_t)(end - e0);
+  }
+  t.order.resize(n); t.father.resize(n); t.father_id.resize(n); t.fdist.resize(n);
+  t.level_off.push_back(n);
+}
 
-struct Edge {
-  int a, b;
-  float w;
-};
-
-inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float scale, Tree& t);
+}  // namespace detail
 
 // wr[p]: weight of edge (p, p+1) for x < W-1; wu[p]: weight of edge (p, p-W) for y >= 1 (st_edge_weight_kernel).
 // tau: the constant c of the threshold function c / size (TAU = 1200 in Toolkit.h:33); scale: CWeightProvider::GetScale().
 inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t) {
-  const int n = H * W;
-  // ---- edges in the reference's sorted order: by weight, then by b, then by a (segment-graph.h:33-41)
-  static thread_local std::vector<Edge> e;  // work space reused across calls: fresh 4 MB allocations page-fault every time
-  std::vector<int> cnt(257, 0);
-  for (int y = 0; y < H; ++y)
-    for (int x = 0; x < W; ++x) {
-      const int p = y * W + x;
+  detail::Work& k = detail::work();
+  // ---- edges in the reference's sorted order: by weight, then by b, then by a (segment-graph.h:33-41): a counting
+  // sort whose buckets are filled in (b, a) order by construction
+  int cnt[257] = {0};
+  for (int y = 0, p = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x, ++p) {
       if (x < W - 1) cnt[wr[p] + 1]++;
       if (y >= 1) cnt[wu[p] + 1]++;
     }
   for (int i = 0; i < 256; ++i) cnt[i + 1] += cnt[i];
   const int m = cnt[256];
-  e.resize(m);
-  {
-    std::vector<int> at(cnt.begin(), cnt.begin() + 256);
-    for (int y = 0, b = 0; y < H; ++y)  // edges whose second endpoint is b, by increasing first endpoint a
-      for (int x = 0; x < W; ++x, ++b) {
-        if (x >= 1) { const int a = b - 1; Edge& d = e[at[wr[a]]++]; d.a = a; d.b = b; d.w = (float)wr[a]; }          // (a, a+1)
-        if (y + 1 < H) { const int a = b + W; Edge& d = e[at[wu[a]]++]; d.a = a; d.b = b; d.w = (float)wu[a]; }       // (a, a-W)
-      }
-  }
-  finish_tree(e, H, W, tau, scale, t);
+  k.code.resize(m);
+  k.ws.resize(m);
+  uint32_t* code = k.code.data();
+  float* ws = k.ws.data();
+  for (int y = 0, b = 0; y < H; ++y)  // edges whose second endpoint is b, by increasing first endpoint a
+    for (int x = 0; x < W; ++x, ++b) {
+      if (x >= 1) { const int a = b - 1, i = cnt[wr[a]]++; code[i] = (uint32_t)a << 1; ws[i] = (float)wr[a]; }            // (a, a+1)
+      if (y + 1 < H) { const int a = b + W, i = cnt[wu[a]]++; code[i] = (uint32_t)a << 1 | 1u; ws[i] = (float)wu[a]; }   // (a, a-W)
+    }
+  detail::finish(H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
 }
 
-// The same for real-valued weights (CColorDepthWeight, SegmentTree.cpp:204-218): a comparison sort by (w, b, a).
+// The same for real-valued weights >= 0 (CColorDepthWeight, SegmentTree.cpp:204-218): the bit pattern of a non-negative
+// float orders like the float, so the sort is a stable least-significant-digit radix sort (3 passes of 11 bits) of the
+// edges enumerated in (b, a) order.
 inline void build_tree_f(const float* wr, const float* wu, int H, int W, float tau, float scale, Tree& t) {
-  std::vector<Edge> e;
-  e.reserve(2 * (size_t)H * W);
-  for (int y = 0; y < H; ++y)
-    for (int x = 0; x < W; ++x) {
-      const int p = y * W + x;
-      if (x < W - 1) e.push_back(Edge{p, p + 1, wr[p]});
-      if (y >= 1) e.push_back(Edge{p, p - W, wu[p]});
+  detail::Work& k = detail::work();
+  const int m = (W - 1) * H + (H - 1) * W;
+  k.code.resize(m); k.code2.resize(m); k.key.resize(m); k.key2.resize(m); k.ws.resize(m);
+  uint32_t *c0 = k.code.data(), *c1 = k.code2.data(), *k0 = k.key.data(), *k1 = k.key2.data();
+  int e = 0;
+  auto bits = [](float f) { if (f == 0.f) f = 0.f; uint32_t u; std::memcpy(&u, &f, 4); return u; };  // -0 -> +0
+  for (int y = 0, b = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x, ++b) {
+      if (x >= 1) { c0[e] = (uint32_t)(b - 1) << 1; k0[e++] = bits(wr[b - 1]); }
+      if (y + 1 < H) { c0[e] = (uint32_t)(b + W) << 1 | 1u; k0[e++] = bits(wu[b + W]); }
     }
-  std::sort(e.begin(), e.end(), [](const Edge& x, const Edge& y) {
-    if (x.w != y.w) return x.w < y.w;
-    if (x.b != y.b) return x.b < y.b;
-    return x.a < y.a;
-  });
-  finish_tree(e, H, W, tau, scale, t);
-}
-
-inline void finish_tree(std::vector<Edge>& e, int H, int W, float tau, float scale, Tree& t) {
-  const int n = H * W;
-  const int m = (int)e.size();
-  // ---- segment_graph (segment-graph.h:48-101): adaptive-threshold Kruskal, then the remaining edges in the same order
-  // join the segments into ONE tree; an edge between two segments of more than MIN_SIZE_SEG pixels is penalised
-  static thread_local std::vector<uint8_t> used, adjd, deg, seen;
-  static thread_local std::vector<int> adj, depth;
-  used.assign(m, 0);
-  {
-    DisjointSets u(n, tau / 1.0f);
-    int sets = n;
+  std::vector<int> cnt(2049);
+  for (int pass = 0; pass < 3; ++pass) {
+    const int sh = 11 * pass;
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (int i = 0; i < m; ++i) cnt[((k0[i] >> sh) & 2047u) + 1]++;
+    for (int i = 0; i < 2048; ++i) cnt[i + 1] += cnt[i];
     for (int i = 0; i < m; ++i) {
-      const int a = u.find(e[i].a), b = u.find(e[i].b);
-      if (a != b && e[i].w <= u.info[a].thr && e[i].w <= u.info[b].thr) {
-        used[i] = 1;
-        const int r = u.join(a, b);
-        u.info[r].thr = e[i].w + tau / (float)u.info[r].size;
-        --sets;
-      }
+      const int j = cnt[(k0[i] >> sh) & 2047u]++;
+      k1[j] = k0[i];
+      c1[j] = c0[i];
     }
-    for (int i = 0; i < m && sets > 1; ++i) {  // once one component is left no further edge can join anything
-      if (used[i]) continue;                   // its endpoints are already connected
-      const int a = u.find(e[i].a), b = u.find(e[i].b);
-      if (a != b) {
-        const int size_min = std::min(u.info[a].size, u.info[b].size);
-        u.join(a, b);
-        used[i] = 1;
-        --sets;
-        if (size_min > 50) e[i].w += 5.0f;  // MIN_SIZE_SEG, PENALTY_CROSS_SEG
-      }
-    }
+    std::swap(k0, k1);
+    std::swap(c0, c1);
   }
-  // ---- adjacency in edge order (SegmentTree.cpp:70-94): at most 4 neighbours per pixel
-  adj.resize(4 * (size_t)n);
-  adjd.resize(4 * (size_t)n);
-  deg.assign(n, 0);
-  for (int i = 0; i < m; ++i) {
-    if (!used[i]) continue;
-    const int dis = std::min((int)(e[i].w * scale + 0.5f), 255);
-    const int a = e[i].a, b = e[i].b;
-    adj[4 * (size_t)a + deg[a]] = b; adjd[4 * (size_t)a + deg[a]++] = (uint8_t)dis;
-    adj[4 * (size_t)b + deg[b]] = a; adjd[4 * (size_t)b + deg[b]++] = (uint8_t)dis;
-  }
-  // ---- ordered tree: breadth-first from pixel 0 (SegmentTree.cpp:97-131)
-  t.order.assign(n, 0); t.father.assign(n, -1); t.father_id.assign(n, 0); t.fdist.assign(n, 0);
-  t.child0.assign(n, 0); t.nchild.assign(n, 0); t.level_off.clear();
-  depth.assign(n, 0);
-  seen.assign(n, 0);
-  seen[0] = 1;
-  int start = 0, end = 1;
-  while (start < end) {
-    const int pos = start++, id = t.order[pos];
-    t.child0[pos] = end;
-    for (int k = 0; k < deg[id]; ++k) {
-      const int c = adj[4 * (size_t)id + k];
-      if (seen[c]) continue;  // the father
-      seen[c] = 1;
-      t.order[end] = c;
-      t.father[end] = pos;
-      t.father_id[end] = id;
-      t.fdist[end] = adjd[4 * (size_t)id + k];
-      depth[end] = depth[pos] + 1;
-      ++end;
-    }
-    t.nchild[pos] = (uint8_t)(end - t.child0[pos]);
-  }
-  for (int i = 0; i < n; ++i)
-    if (i == 0 || depth[i] != depth[i - 1]) t.level_off.push_back(i);
-  t.level_off.push_back(n);
+  if (c0 != k.code.data()) std::memcpy(k.code.data(), c0, 4 * (size_t)m);  // 3 passes: the result is in the second pair
+  std::memcpy(k.ws.data(), k0, 4 * (size_t)m);
+  detail::finish(H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
 }
 
 // m_table of CSegmentTree::UpdateTable (SegmentTree.cpp:141-146): exp(-i / (255 sigma)) in float, sigma >= 0.01
