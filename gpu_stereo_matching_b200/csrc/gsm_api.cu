@@ -1316,9 +1316,11 @@ bool st_filter_ring_try(gsm_ctx* c, float* buf, float* fin, const StTree& dt, in
   return true;
 }
 int st_filter_launch(gsm_ctx* c, float* buf, float* fin, const StTree& dt, int D, cudaStream_t s) {
-  static const int force_plain = getenv("GSM_ST_PLAIN_FILTER") ? atoi(getenv("GSM_ST_PLAIN_FILTER")) : 0;
-  if (force_plain || !(st_filter_ring_try<16>(c, buf, fin, dt, D, s, 0) || st_filter_ring_try<8>(c, buf, fin, dt, D, s, 1) ||
-                       st_filter_ring_try<4>(c, buf, fin, dt, D, s, 2)))
+  // GSM_ST_RING = 16 / 8 / 4 caps the ring depth, 0 forces the plain kernel (tests run every variant); default: deepest that fits
+  const char* e = getenv("GSM_ST_RING");
+  const int maxr = e ? atoi(e) : 16;
+  if (!((maxr >= 16 && st_filter_ring_try<16>(c, buf, fin, dt, D, s, 0)) || (maxr >= 8 && st_filter_ring_try<8>(c, buf, fin, dt, D, s, 1)) ||
+        (maxr >= 4 && st_filter_ring_try<4>(c, buf, fin, dt, D, s, 2))))
     st_filter_kernel<<<D, 256, 0, s>>>(buf, fin, dt);
   c->launches++;
   return GSM_OK;

@@ -71,6 +71,10 @@ inline Work& work() {
   static thread_local Work w;
   return w;
 }
+// the cache is for streams of ordinary frames (tens of bytes per pixel); past 4 Mpx it is given back after the call
+inline void release_if_large(int n) {
+  if (n > (1 << 22)) work() = Work();
+}
 
 enum : uint8_t { USED_R = 1, USED_U = 2, PEN_R = 4, PEN_U = 8 };
 
@@ -223,6 +227,7 @@ inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float
       if (y + 1 < H) { const int a = b + W, i = cnt[wu[a]]++; code[i] = (uint32_t)a << 1 | 1u; ws[i] = (float)wu[a]; }   // (a, a-W)
     }
   detail::finish(H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
+  detail::release_if_large(H * W);
 }
 
 // The same for real-valued weights >= 0 (CColorDepthWeight, SegmentTree.cpp:204-218): the bit pattern of a non-negative
@@ -257,6 +262,7 @@ inline void build_tree_f(const float* wr, const float* wu, int H, int W, float t
   if (c0 != k.code.data()) std::memcpy(k.code.data(), c0, 4 * (size_t)m);  // 3 passes: the result is in the second pair
   std::memcpy(k.ws.data(), k0, 4 * (size_t)m);
   detail::finish(H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
+  detail::release_if_large(H * W);
 }
 
 // m_table of CSegmentTree::UpdateTable (SegmentTree.cpp:141-146): exp(-i / (255 sigma)) in float, sigma >= 0.01

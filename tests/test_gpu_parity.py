@@ -598,6 +598,27 @@ def test_segment_tree_stereo_bit_exact(ctx, orc):
         ctx.segment_tree_stereo(L[:, :, 0], R[:, :, 0], 16)
 
 
+def test_segment_tree_filter_kernel_variants(ctx, orc, monkeypatch):
+    """The tree filter has four code paths -- the on-chip ring kernel with 16, 8 or 4 level slots (whichever the widest
+    level of the tree allows) and the plain level-synchronous kernel: all four give the reference's volume bit for bit
+    (SegmentTree.cpp:148-181), on the demo pair and on a 640x480 pair whose levels are several hundred nodes wide."""
+    L, R = _art_demo_bgr()
+    Lb, Rb = gdata.synthetic_color_pair(480, 640, 23, dmax=24)
+    for name, (a, b), D in (("art_demo", (L, R), 32), ("vga", (Lb, Rb), 16)):
+        cost = ctx.st_matching_cost(a, b, D)
+        vols = {}
+        for ring in ("0", "4", "8", "16"):
+            monkeypatch.setenv("GSM_ST_RING", ring)
+            vols[ring], order, _, _ = ctx.st_filter(a, cost, 0.1, 1200.0)
+        monkeypatch.delenv("GSM_ST_RING")
+        for ring in ("4", "8", "16"):
+            assert np.array_equal(vols[ring], vols["0"]), (name, ring, float(np.abs(vols[ring] - vols["0"]).max()))
+        if orc.have_segref():
+            vref, oref, _, _ = orc.ref_st_filter(a, cost, 0.1, 1200.0)
+            assert np.array_equal(order, oref), name
+            assert np.array_equal(vols["16"], vref), (name, float(np.abs(vols["16"] - vref).max()))
+
+
 def test_errors_are_reported(ctx):
     z = np.zeros((16, 16), np.uint8)
     with pytest.raises(g.GsmError):
