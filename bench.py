@@ -262,6 +262,37 @@ def _sad_record(torch, ctx, g, stream, sh, flush, Ld, Rd, Dd, Lh, Rh, Dh, n, ste
     return {"ms": ms, "e2e_ms": e2e_ms, "kernel_ms": kernel_ms, "radius": r}
 
 
+def _segment_tree_record(ctx, gdata, with_reference):
+    """SURVEY 8f row 4 beside the headline: the reference's second pipeline (STMatching stereo_disparity_normal) through
+    gsm_segment_tree_stereo from HOST buffers (wall clock: upload, GPU stages, host tree build, read-back), and -- the
+    cpu_baseline leg -- the reference's own code (oracle/_ref/libsegref.so, one core) on the same pair."""
+    import time
+    h, w, D = 370, 463, 64  # the Middlebury third-size format of the reference's data sets
+    L, R = gdata.synthetic_color_pair(h, w, 7, dmax=D - 8)
+    for _ in range(2):
+        disp = ctx.segment_tree_stereo(L, R, D, scale=1)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        ctx.segment_tree_stereo(L, R, D, scale=1)
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    rec = {"what": "STMatching stereo_disparity_normal (cost, segment tree, tree filter, WTA, 7x7 median) from host buffers",
+           "workload": f"synthetic colour pair {w}x{h} x {D} d", "ms_per_pair": ms, "pairs_per_s": 1e3 / ms,
+           "value": h * w * D / ms / 1e3, "unit": "MDE/s"}
+    if with_reference:
+        from oracle import oracle as O
+        if O.have_segref():
+            with O.quiet_stdout():
+                ref = O.ref_st_routine(L, R, D, 1, 0.1)
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    O.ref_st_routine(L, R, D, 1, 0.1)
+                rms = (time.perf_counter() - t0) / 2 * 1e3
+            rec["cpu_reference"] = {"ms_per_pair": rms, "kind": "reference", "cores": 1,
+                                    "identical_to_product": bool(np.array_equal(ref, disp))}
+    return rec
+
+
 def _dsplit_record(args, torch, dist, g, gdata, rank, world, local_rank):
     """BASELINE config 5 in front of the driver (N > 1): one 3840x2160 pair, 256 disparities, GF r=9, split by disparity
     range over the ranks; packed (cost, d) planes combined over NVLink peer memory (gsm_reduce_keys_p2p), one cross-rank
@@ -731,6 +762,8 @@ def main():
         }
         if dsplit is not None:
             line["dsplit"] = dsplit
+        if world == 1:
+            line["segment_tree"] = _segment_tree_record(ctx, gdata, with_reference=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             with O.quiet_stdout():

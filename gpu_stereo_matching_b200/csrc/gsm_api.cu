@@ -14,6 +14,7 @@
 #include "gsm_sad.cuh"
 #include "gsm_st.cuh"
 #include "gsm_st_host.hpp"
+#include <thread>
 #include "gsm_util.cuh"
 
 using namespace gsm;
@@ -1215,8 +1216,8 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
     bytes = o;
   }
 };
-int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol) {
-  const size_t pin = StTreeBlock(n).bytes + 8 * n;  // + two float weight planes (or two u8 ones)
+int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol, int pin_slots = 1) {
+  const size_t pin = pin_slots * ((StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256);  // see StPinSlot
   if (c->st_pin_bytes < pin) {
     if (c->st_pin) cudaFreeHost(c->st_pin);
     c->st_pin = nullptr;
@@ -1240,45 +1241,55 @@ int st_check(const gsm_ctx* c, int rows, int cols, int D) {
   if (D < 1 || D > MAX_DISP) return fail(GSM_ERR_INVALID, "num_disp %d not in 1..256", D);
   return GSM_OK;
 }
-// image (device, interleaved 3-channel) -> the ordered tree on the device; fills t (host) as well.  With disp / mask
-// (device u8 maps) the edge weights are CColorDepthWeight's (SegmentTree.cpp:197-218, scale 255), else CColorWeight's.
-int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, float sigma, float tau, gsm_st::Tree& t,
-            StTree* dt, cudaStream_t s, const u8* disp = nullptr, const u8* mask = nullptr, int level = 0) {
+// ---- the tree of one view, in three phases (ST-2 builds the trees of its two views on two host threads) -------------
+// Pinned slot k of gsm_ctx::st_pin: [StTreeBlock mirror][weight read-back: two planes of n floats (or n bytes)]
+struct StPinSlot {
+  char *tree, *w;
+  StPinSlot(const gsm_ctx* c, size_t n, int k) {
+    const size_t stride = (StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256;
+    tree = (char*)c->st_pin + k * stride;
+    w = tree + StTreeBlock(n).bytes;
+  }
+};
+// phase 1 (GPU, asynchronous on s): 3x3 median of the image, edge weights, read-back into pw.  With disp / mask (device
+// u8 maps) the weights are CColorDepthWeight's (SegmentTree.cpp:197-218, float), else CColorWeight's (u8).
+int st_weights_async(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, char* pw, cudaStream_t s,
+                     const u8* disp = nullptr, const u8* mask = nullptr, int level = 0) {
   const size_t n = (size_t)rows * cols;
   const dim3 blk(128), grd((cols + 127) / 128, rows);
-  const StTreeBlock tb(n);
-  char* pin = (char*)c->st_pin;
-  char* pw = pin + tb.bytes;  // weight read-back area
   st_median3_kernel<<<grd, blk, 0, s>>>(img3, a.med, rows, cols);
-  c->launches++;
   if (disp) {
     st_edge_weight_depth_kernel<<<grd, blk, 0, s>>>(a.med, disp, mask, (float)level, a.wrf, a.wuf, rows, cols);
-    c->launches++;
     CK(cudaGetLastError());
-    float *wr = (float*)pw, *wu = wr + n;
-    CK(cudaMemcpyAsync(wr, a.wrf, 4 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(wu, a.wuf, 4 * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    gsm_st::build_tree_f(wr, wu, rows, cols, tau, /*CColorDepthWeight::GetScale*/ 255.0f, t);
+    CK(cudaMemcpyAsync(pw, a.wrf, 4 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(pw + 4 * n, a.wuf, 4 * n, cudaMemcpyDeviceToHost, s));
   } else {
     st_edge_weight_kernel<<<grd, blk, 0, s>>>(a.med, a.wr, a.wu, rows, cols);
-    c->launches++;
     CK(cudaGetLastError());
-    u8 *wr = (u8*)pw, *wu = wr + n;
-    CK(cudaMemcpyAsync(wr, a.wr, n, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(wu, a.wu, n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    gsm_st::build_tree(wr, wu, rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t);
+    CK(cudaMemcpyAsync(pw, a.wr, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(pw + n, a.wu, n, cudaMemcpyDeviceToHost, s));
   }
-  // the device form of the tree, written into the pinned mirror of the arena's tree block and sent as one copy
+  c->launches += 2;
+  return GSM_OK;
+}
+// phase 2 (host only; safe to run concurrently for different t / k / pin_tree): the ordered tree from the weights in pw,
+// then its device form written into the pinned mirror of the arena's tree block.  Fills dt except the device pointers.
+void st_build_pack(const char* pw, bool float_weights, int rows, int cols, float sigma, float tau, gsm_st::Tree& t,
+                   gsm_st::detail::Work& k, char* pin_tree, StTree* dt) {
+  const size_t n = (size_t)rows * cols;
+  if (float_weights)
+    gsm_st::build_tree_f((const float*)pw, (const float*)pw + n, rows, cols, tau, /*CColorDepthWeight::GetScale*/ 255.0f, t, k);
+  else
+    gsm_st::build_tree((const u8*)pw, (const u8*)pw + n, rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t, k);
+  const StTreeBlock tb(n);
   float table[256];
   gsm_st::weight_table(sigma, table);
   int tbits[256];
   memcpy(tbits, table, sizeof(tbits));
-  int2* up = (int2*)(pin + tb.o_up);
-  int2* down = (int2*)(pin + tb.o_down);
-  int* order = (int*)(pin + tb.o_order);
-  int* pos = (int*)(pin + tb.o_pos);
+  int2* up = (int2*)(pin_tree + tb.o_up);
+  int2* down = (int2*)(pin_tree + tb.o_down);
+  int* order = (int*)(pin_tree + tb.o_order);
+  int* pos = (int*)(pin_tree + tb.o_pos);
   for (size_t i = 0; i < n; ++i) {
     const int id = t.order[i];
     order[i] = id;
@@ -1286,15 +1297,28 @@ int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, fl
     up[i] = make_int2(t.child0[i], (int)t.nchild[i]);
     down[i] = make_int2(t.father[i], tbits[t.fdist[i]]);
   }
-  memcpy(pin + tb.o_level, t.level_off.data(), 4 * t.level_off.size());
-  CK(cudaMemcpyAsync(a.tree, pin, tb.o_level + 4 * t.level_off.size(), cudaMemcpyHostToDevice, s));
-  // (the pinned block is next written by the next st_tree call, which first synchronises on the weight read-back)
-  dt->up = a.up; dt->down = a.down; dt->level_off = a.level_off;
+  memcpy(pin_tree + tb.o_level, t.level_off.data(), 4 * t.level_off.size());
   dt->levels = (int)t.level_off.size() - 1;
   dt->n = (int)n;
   dt->max_width = 0;
   for (size_t l = 0; l + 1 < t.level_off.size(); ++l) dt->max_width = std::max(dt->max_width, t.level_off[l + 1] - t.level_off[l]);
+}
+// phase 3: the packed tree to the device as one copy (asynchronous on s; pin_tree stays untouched until s passes it)
+int st_upload(const StArena& a, const char* pin_tree, StTree* dt, cudaStream_t s) {
+  const StTreeBlock tb((size_t)dt->n);
+  CK(cudaMemcpyAsync(a.tree, pin_tree, tb.o_level + 4 * ((size_t)dt->levels + 1), cudaMemcpyHostToDevice, s));
+  dt->up = a.up; dt->down = a.down; dt->level_off = a.level_off;
   return GSM_OK;
+}
+// all three for one image: image (device, interleaved 3-channel) -> the ordered tree on the device; fills t (host) too
+int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, float sigma, float tau, gsm_st::Tree& t,
+            StTree* dt, cudaStream_t s, const u8* disp = nullptr, const u8* mask = nullptr, int level = 0) {
+  const StPinSlot pin(c, (size_t)rows * cols, 0);
+  int rc;
+  if ((rc = st_weights_async(c, a, img3, rows, cols, pin.w, s, disp, mask, level))) return rc;
+  CK(cudaStreamSynchronize(s));  // (also: every earlier upload from this pinned slot has been consumed)
+  st_build_pack(pin.w, disp != nullptr, rows, cols, sigma, tau, t, gsm_st::detail::work(), pin.tree, dt);
+  return st_upload(a, pin.tree, dt, s);
 }
 // the tree filter over D channels: the on-chip ring kernel with the deepest ring the widest level allows, else the plain one
 template <int RING>
@@ -1411,7 +1435,7 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   if ((rc = gsm_sync(c))) return rc;
   const size_t n = (size_t)rows * cols;
   const int D = p->num_disp;
-  if ((rc = st_reserve(c, n, D, false))) return rc;
+  if ((rc = st_reserve(c, n, D, false, p->refined ? 2 : 1))) return rc;
   const StArena a(c->st_buf, n, D, false);
   cudaStream_t s = c->stream;
   CK(cudaMemcpyAsync(a.L3, left3, 3 * n, cudaMemcpyHostToDevice, s));
@@ -1424,13 +1448,12 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   StTree dt;
   const float tau = p->tau > 0.f ? p->tau : 1200.f;
   const unsigned gn = (unsigned)((n + 255) / 256);
-  // aggregate the cost of one view over the tree of `img` and take the winner (+ median): -> a.disp / a.disp2
-  auto view = [&](const u8* img, int right, float sigma, const u8* tdisp, const u8* tmask, u8** out) -> int {
-    int r;
-    if ((r = st_tree(c, a, img, rows, cols, sigma, tau, t, &dt, s, tdisp, tmask, D))) return r;
+  // with the tree of a view on the device (dt): its cost, aggregated over the tree, winner (+ median) -> a.disp / a.disp2
+  auto view_gpu = [&](int right, u8** out) -> int {
     // the cost kernel writes straight into the [D][BFS position] layout the filter works on
     if (right) st_cost_right_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
     else st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
+    int r;
     if ((r = st_filter_launch(c, a.buf, a.fin, dt, D, s))) return r;
     st_wta_kernel<<<gn, 256, 0, s>>>(a.fin, a.order, a.disp, (int)n, D);
     c->launches += 2;
@@ -1442,6 +1465,11 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
     CK(cudaGetLastError());
     return GSM_OK;
   };
+  auto view = [&](const u8* img, int right, float sigma, const u8* tdisp, const u8* tmask, u8** out) -> int {
+    int r;
+    if ((r = st_tree(c, a, img, rows, cols, sigma, tau, t, &dt, s, tdisp, tmask, D))) return r;
+    return view_gpu(right, out);
+  };
   u8* out = nullptr;
   if (!p->refined) {
     if ((rc = view(a.L3, 0, p->sigma, nullptr, nullptr, &out))) return rc;
@@ -1450,9 +1478,31 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
     // (:128-147), then a second left pass over the tree of CColorDepthWeight(left image, left disparity, mask)
     if (D > cols) return fail(GSM_ERR_INVALID, "refined segment-tree stereo needs num_disp <= cols (StereoHelper.cpp:162-177)");
     const float SIGMA_ONE = 0.08f;
-    if ((rc = view(a.L3, 0, SIGMA_ONE, nullptr, nullptr, &out))) return rc;
-    CK(cudaMemcpyAsync(a.dispL, out, n, cudaMemcpyDeviceToDevice, s));
-    if ((rc = view(a.R3, 1, SIGMA_ONE, nullptr, nullptr, &out))) return rc;
+    // the trees of the two views are independent and host-bound: the right one is built on a second thread while this
+    // one builds the left one; the GPU takes the left view as soon as its tree is up
+    static thread_local gsm_st::Tree t2;
+    static thread_local gsm_st::detail::Work work2;  // owned here, lent to the short-lived builder thread
+    const StPinSlot pinL(c, n, 0), pinR(c, n, 1);
+    if ((rc = st_weights_async(c, a, a.L3, rows, cols, pinL.w, s))) return rc;
+    if ((rc = st_weights_async(c, a, a.R3, rows, cols, pinR.w, s))) return rc;
+    CK(cudaStreamSynchronize(s));
+    StTree dtR;
+    auto build_right = [&] { st_build_pack(pinR.w, false, rows, cols, SIGMA_ONE, tau, t2, work2, pinR.tree, &dtR); };
+    std::thread right_builder;
+    try {
+      right_builder = std::thread(build_right);
+    } catch (...) {  // no thread to be had: build it here, after the left one
+    }
+    st_build_pack(pinL.w, false, rows, cols, SIGMA_ONE, tau, t, gsm_st::detail::work(), pinL.tree, &dt);
+    rc = st_upload(a, pinL.tree, &dt, s);
+    if (!rc) rc = view_gpu(0, &out);
+    if (!rc && cudaMemcpyAsync(a.dispL, out, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(GSM_ERR_CUDA, "copy of the left disparity");
+    if (right_builder.joinable()) right_builder.join();  // (before any return: the thread references this frame)
+    else build_right();
+    if (rc) return rc;
+    dt = dtR;
+    if ((rc = st_upload(a, pinR.tree, &dt, s))) return rc;
+    if ((rc = view_gpu(1, &out))) return rc;
     CK(cudaMemcpyAsync(a.dispR, out, n, cudaMemcpyDeviceToDevice, s));
     lr_check_kernel<<<dim3((cols + 255) / 256, rows, 1), 256, 0, s>>>(a.dispL, a.dispR, nullptr, a.mask, nullptr, rows, cols, 1,
                                                                         nullptr);

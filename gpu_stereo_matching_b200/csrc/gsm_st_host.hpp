@@ -72,16 +72,15 @@ inline Work& work() {
   return w;
 }
 // the cache is for streams of ordinary frames (tens of bytes per pixel); past 4 Mpx it is given back after the call
-inline void release_if_large(int n) {
-  if (n > (1 << 22)) work() = Work();
+inline void release_if_large(Work& k, int n) {
+  if (n > (1 << 22)) k = Work();
 }
 
 enum : uint8_t { USED_R = 1, USED_U = 2, PEN_R = 4, PEN_U = 8 };
 
 // code[i] (sorted by (w, b, a)), ws[i] = the edge's weight.  wgt(p, dir) = weight of pixel p's right (0) / up (1) edge.
 template <class W>
-inline void finish(int H, int Wd, int m, float tau, float scale, const W& wgt, Tree& t) {
-  Work& k = work();
+inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const W& wgt, Tree& t) {
   const int n = H * Wd;
   const uint32_t* code = k.code.data();
   const float* ws = k.ws.data();
@@ -205,8 +204,9 @@ inline void finish(int H, int Wd, int m, float tau, float scale, const W& wgt, T
 
 // wr[p]: weight of edge (p, p+1) for x < W-1; wu[p]: weight of edge (p, p-W) for y >= 1 (st_edge_weight_kernel).
 // tau: the constant c of the threshold function c / size (TAU = 1200 in Toolkit.h:33); scale: CWeightProvider::GetScale().
-inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t) {
-  detail::Work& k = detail::work();
+// k: the builder's work space (default: one per calling thread; callers that build on short-lived threads pass their own).
+inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t,
+                       detail::Work& k = detail::work()) {
   // ---- edges in the reference's sorted order: by weight, then by b, then by a (segment-graph.h:33-41): a counting
   // sort whose buckets are filled in (b, a) order by construction
   int cnt[257] = {0};
@@ -226,15 +226,15 @@ inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float
       if (x >= 1) { const int a = b - 1, i = cnt[wr[a]]++; code[i] = (uint32_t)a << 1; ws[i] = (float)wr[a]; }            // (a, a+1)
       if (y + 1 < H) { const int a = b + W, i = cnt[wu[a]]++; code[i] = (uint32_t)a << 1 | 1u; ws[i] = (float)wu[a]; }   // (a, a-W)
     }
-  detail::finish(H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
-  detail::release_if_large(H * W);
+  detail::finish(k, H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
+  detail::release_if_large(k, H * W);
 }
 
 // The same for real-valued weights >= 0 (CColorDepthWeight, SegmentTree.cpp:204-218): the bit pattern of a non-negative
 // float orders like the float, so the sort is a stable least-significant-digit radix sort (3 passes of 11 bits) of the
 // edges enumerated in (b, a) order.
-inline void build_tree_f(const float* wr, const float* wu, int H, int W, float tau, float scale, Tree& t) {
-  detail::Work& k = detail::work();
+inline void build_tree_f(const float* wr, const float* wu, int H, int W, float tau, float scale, Tree& t,
+                         detail::Work& k = detail::work()) {
   const int m = (W - 1) * H + (H - 1) * W;
   k.code.resize(m); k.code2.resize(m); k.key.resize(m); k.key2.resize(m); k.ws.resize(m);
   uint32_t *c0 = k.code.data(), *c1 = k.code2.data(), *k0 = k.key.data(), *k1 = k.key2.data();
@@ -261,8 +261,8 @@ inline void build_tree_f(const float* wr, const float* wu, int H, int W, float t
   }
   if (c0 != k.code.data()) std::memcpy(k.code.data(), c0, 4 * (size_t)m);  // 3 passes: the result is in the second pair
   std::memcpy(k.ws.data(), k0, 4 * (size_t)m);
-  detail::finish(H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
-  detail::release_if_large(H * W);
+  detail::finish(k, H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
+  detail::release_if_large(k, H * W);
 }
 
 // m_table of CSegmentTree::UpdateTable (SegmentTree.cpp:141-146): exp(-i / (255 sigma)) in float, sigma >= 0.01

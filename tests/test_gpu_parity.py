@@ -605,7 +605,9 @@ def test_segment_tree_filter_kernel_variants(ctx, orc, monkeypatch):
     (SegmentTree.cpp:148-181), on the demo pair and on a 640x480 pair whose levels are several hundred nodes wide."""
     L, R = _art_demo_bgr()
     Lb, Rb = gdata.synthetic_color_pair(480, 640, 23, dmax=24)
-    for name, (a, b), D in (("art_demo", (L, R), 32), ("vga", (Lb, Rb), 16)):
+    tiny = lambda h, w: (L[40:40 + h, 60:60 + w].copy(), R[40:40 + h, 60:60 + w].copy())  # trees shallower than the ring
+    for name, (a, b), D in (("art_demo", (L, R), 32), ("vga", (Lb, Rb), 16), ("3x3", tiny(3, 3), 3), ("5x4", tiny(5, 4), 4),
+                            ("1 row of levels", tiny(3, 40), 5)):
         cost = ctx.st_matching_cost(a, b, D)
         vols = {}
         for ring in ("0", "4", "8", "16"):

@@ -24,10 +24,17 @@ for (h, w, D) in ((256, 320, 64), (370, 463, 64), (720, 1280, 128)):
         for _ in range(5):
             ctx.segment_tree_stereo(L, R, D, scale=1)
         ms = (time.perf_counter() - t0) / 5 * 1e3
+        ms2 = None
+        if D <= w and h * w < 500000:  # ST-2 (stereo_disparity_iteration): three trees, both views
+            ctx.segment_tree_stereo(L, R, D, scale=1, refined=True)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.segment_tree_stereo(L, R, D, scale=1, refined=True)
+            ms2 = (time.perf_counter() - t0) / 3 * 1e3
     wr, wu = weights(L)
     t0 = time.perf_counter()
     for _ in range(5):
         _, _, _, levels = g.st_build_tree_host(wr, wu)
     tms = (time.perf_counter() - t0) / 5 * 1e3
     print(f"{w}x{h} x{D}: whole call {ms:8.2f} ms ({h * w * D / ms / 1e3:8.1f} MDE/s), host tree builder {tms:7.2f} ms, "
-          f"tree depth {levels} levels", flush=True)
+          f"tree depth {levels} levels" + (f", ST-2 whole call {ms2:8.2f} ms" if ms2 else ""), flush=True)
