@@ -279,6 +279,14 @@ def _segment_tree_record(ctx, gdata, with_reference):
     rec = {"what": "STMatching stereo_disparity_normal (cost, segment tree, tree filter, WTA, 7x7 median) from host buffers",
            "workload": f"synthetic colour pair {w}x{h} x {D} d", "ms_per_pair": ms, "pairs_per_s": 1e3 / ms,
            "value": h * w * D / ms / 1e3, "unit": "MDE/s"}
+    nb = 16  # a batch: the per-frame trees are built concurrently on the host threads, two frames share the GPU
+    Lb, Rb = np.stack([L] * nb), np.stack([R] * nb)
+    ctx.segment_tree_stereo_batch(Lb, Rb, D)
+    t0 = time.perf_counter()
+    bd = ctx.segment_tree_stereo_batch(Lb, Rb, D)
+    bms = (time.perf_counter() - t0) * 1e3 / nb
+    rec["batch"] = {"pairs_per_call": nb, "ms_per_pair": bms, "pairs_per_s": 1e3 / bms, "host_threads": os.cpu_count(),
+                    "identical_to_single_calls": bool(all(np.array_equal(bd[i], disp) for i in range(nb)))}
     if with_reference:
         from oracle import oracle as O
         if O.have_segref():

@@ -312,6 +312,26 @@ class StereoContext:
         _l.check(self._lib.gsm_segment_tree_stereo(self._h, C.byref(p), _ptr(L), _ptr(R), _ptr(out), L.shape[0], L.shape[1]))
         return out
 
+    def segment_tree_stereo_batch(self, lefts_bgr, rights_bgr, num_disp: int, sigma: float = 0.1, tau: float = 1200.0,
+                                  median_radius: int = 3, scale: int = 1, host_threads: int = 0) -> np.ndarray:
+        """n pairs of one size ([n, rows, cols, 3] u8 each) through stereo_disparity_normal in one call: the trees of the
+        frames are built concurrently on host threads (0 = one per hardware thread) while the GPU aggregates each frame as
+        soon as its tree is ready; u8 [n, rows, cols], every map identical to segment_tree_stereo on that pair."""
+        L, R = np.asarray(lefts_bgr), np.asarray(rights_bgr)
+        for name, a in (("lefts_bgr", L), ("rights_bgr", R)):
+            if a.dtype != np.uint8:
+                raise TypeError(f"{name}: expected uint8, got {a.dtype}")
+            if a.ndim != 4 or a.shape[3] != 3:
+                raise ValueError(f"{name}: expected [n, rows, cols, 3], got {a.shape}")
+        if L.shape != R.shape:
+            raise ValueError("lefts / rights differ in shape")
+        L, R = np.ascontiguousarray(L), np.ascontiguousarray(R)
+        out = np.empty(L.shape[:3], np.uint8)
+        p = GsmStParams(int(num_disp), float(sigma), float(tau), int(median_radius), int(scale), 0)
+        _l.check(self._lib.gsm_segment_tree_stereo_batch(self._h, C.byref(p), _ptr(L), _ptr(R), _ptr(out), L.shape[0],
+                                                         L.shape[1], L.shape[2], int(host_threads)))
+        return out
+
     def st_matching_cost(self, left_bgr, right_bgr, num_disp: int) -> np.ndarray:
         """== GetMatchingCost (StereoHelper.cpp:75-129): float32 [rows, cols, num_disp]."""
         L, R = self._bgr(left_bgr, "left_bgr"), self._bgr(right_bgr, "right_bgr")

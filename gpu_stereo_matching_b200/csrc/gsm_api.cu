@@ -14,6 +14,9 @@
 #include "gsm_sad.cuh"
 #include "gsm_st.cuh"
 #include "gsm_st_host.hpp"
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include "gsm_util.cuh"
 
@@ -55,6 +58,8 @@ struct gsm_ctx {
   struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
   // segment-tree stereo (gsm_st.cuh): one device arena, grown on demand
   void* st_buf = nullptr;
+  struct StWorker;                      // host work space of one tree-builder thread (gsm_segment_tree_stereo_batch)
+  std::vector<StWorker*> st_workers;
   void* st_pin = nullptr;  // pinned host mirror of the arena's tree block + the weight / disparity read-back
   size_t st_pin_bytes = 0;
   size_t st_bytes = 0;
@@ -74,6 +79,10 @@ struct gsm_ctx {
   bool timing = false;
   std::vector<cudaEvent_t> ev;  // (start, stop) pairs of the fused kernels of the last device call
   size_t ev_used = 0;
+};
+struct gsm_ctx::StWorker {
+  gsm_st::Tree t;
+  gsm_st::detail::Work k;
 };
 
 // strip halo (columns) a fused kernel needs on each side of its output columns
@@ -147,6 +156,7 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (c->st_pin) cudaFreeHost(c->st_pin);
+  for (gsm_ctx::StWorker* w : c->st_workers) delete w;
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
@@ -1216,7 +1226,7 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
     bytes = o;
   }
 };
-int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol, int pin_slots = 1) {
+int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol, int pin_slots = 1, int arenas = 1) {
   const size_t pin = pin_slots * ((StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256);  // see StPinSlot
   if (c->st_pin_bytes < pin) {
     if (c->st_pin) cudaFreeHost(c->st_pin);
@@ -1225,7 +1235,7 @@ int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol, int pin_slots = 1) {
     CK(cudaHostAlloc(&c->st_pin, pin, cudaHostAllocDefault));
     c->st_pin_bytes = pin;
   }
-  const size_t need = StArena(nullptr, n, D, with_vol).bytes;
+  const size_t need = arenas * StArena(nullptr, n, D, with_vol).bytes;
   if (c->st_bytes >= need) return GSM_OK;
   if (c->st_buf) cudaFree(c->st_buf);
   c->st_buf = nullptr;
@@ -1516,6 +1526,126 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(disparity, out, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return GSM_OK;
+}
+
+// A batch of pairs (frames of one size): the host-bound part of the pipeline -- one tree per frame -- is data parallel
+// across frames, so the trees are built concurrently on host threads while the GPU takes each frame as soon as its tree
+// is packed.  Per frame the stages and their results are those of gsm_segment_tree_stereo (ST-1).
+extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p, const uint8_t* left3, const uint8_t* right3,
+                                             uint8_t* disparity, int nframes, int rows, int cols, int host_threads) {
+  if (!p) return fail(GSM_ERR_INVALID, "null params");
+  int rc;
+  if ((rc = st_check(c, rows, cols, p->num_disp))) return rc;
+  if (!left3 || !right3 || !disparity) return fail(GSM_ERR_INVALID, "null pointer");
+  if (nframes < 1) return fail(GSM_ERR_INVALID, "nframes %d", nframes);
+  if (p->refined) return fail(GSM_ERR_UNSUPPORTED, "gsm_segment_tree_stereo_batch runs ST-1 (refined = 0); call gsm_segment_tree_stereo per pair for ST-2");
+  if (p->median_radius < 0 || p->median_radius > MED_MAXR) return fail(GSM_ERR_INVALID, "median_radius %d", p->median_radius);
+  if (p->scale < 1) return fail(GSM_ERR_INVALID, "scale %d", p->scale);
+  CK(cudaSetDevice(c->device));
+  if ((rc = gsm_sync(c))) return rc;
+  const size_t n = (size_t)rows * cols;
+  const int D = p->num_disp;
+  const float tau = p->tau > 0.f ? p->tau : 1200.f;
+  int T = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
+  T = std::max(1, std::min(std::min(T, 64), nframes));
+  // frames in flight: two per builder thread, within 256 MB of pinned host memory (a slot mirrors one frame's tree)
+  const size_t slot_bytes = (StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256;
+  const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(2 * (size_t)T, (size_t)nframes), std::max<size_t>(2, ((size_t)256 << 20) / slot_bytes)));
+  // two device arenas on two streams: a tree filter occupies one CTA per disparity, so for num_disp <= half the SMs
+  // two frames aggregate side by side
+  if ((rc = st_reserve(c, n, D, false, K, 2))) return rc;
+  while ((int)c->st_workers.size() < T) c->st_workers.push_back(new gsm_ctx::StWorker());
+  const StArena a(c->st_buf, n, D, false);
+  const StArena arena[2] = {a, StArena((char*)c->st_buf + a.bytes, n, D, false)};
+  cudaStream_t s = c->stream;
+  cudaStream_t streams[2] = {c->stream, c->s_h2d};  // (the host-path upload stream is idle during this call)
+  const dim3 blk(128), grd((cols + 127) / 128, rows);
+  const unsigned gn = (unsigned)((n + 255) / 256);
+
+  for (int f0 = 0; f0 < nframes; f0 += K) {
+    const int kc = std::min(K, nframes - f0);
+    // ---- phase A (GPU): edge weights of every frame of the chunk into its pinned slot
+    for (int i = 0; i < kc; ++i) {
+      CK(cudaMemcpyAsync(a.L3, left3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
+      if ((rc = st_weights_async(c, a, a.L3, rows, cols, StPinSlot(c, n, i).w, s))) return rc;
+    }
+    CK(cudaStreamSynchronize(s));
+    // ---- phase B (host threads): trees, in frame order off a shared counter
+    std::vector<StTree> dts(kc);
+    std::vector<char> done(kc, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<int> next{0};
+    auto builder = [&](int w) {
+      for (;;) {
+        const int i = next.fetch_add(1);
+        if (i >= kc) break;
+        const StPinSlot pin(c, n, i);
+        st_build_pack(pin.w, false, rows, cols, p->sigma, tau, c->st_workers[w]->t, c->st_workers[w]->k, pin.tree, &dts[i]);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          done[i] = 1;
+        }
+        cv.notify_all();
+      }
+    };
+    std::vector<std::thread> threads;
+    for (int w = 0; w < std::min(T, kc); ++w) {
+      try {
+        threads.emplace_back(builder, w);
+      } catch (...) {
+        break;  // fewer threads than asked for
+      }
+    }
+    if (threads.empty()) builder(0);  // none at all: build here, then run the GPU stages
+    // ---- phase C (GPU): each frame as soon as its tree is packed; the disparity comes back through the frame's slot
+    auto frame_gpu = [&](int i) -> int {
+      const StPinSlot pin(c, n, i);
+      const StArena& a = arena[i & 1];
+      cudaStream_t s = streams[i & 1];
+      CK(cudaMemcpyAsync(a.L3, left3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(a.R3, right3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
+      st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
+      st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.R3, a.gR, rows, cols);
+      int r;
+      if ((r = st_upload(a, pin.tree, &dts[i], s))) return r;
+      st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
+      if ((r = st_filter_launch(c, a.buf, a.fin, dts[i], D, s))) return r;
+      st_wta_kernel<<<gn, 256, 0, s>>>(a.fin, a.order, a.disp, (int)n, D);
+      c->launches += 4;
+      u8* out = a.disp;
+      if (p->median_radius > 0) {
+        if ((r = median_launch(c, a.disp, a.disp2, 1, rows, cols, p->median_radius, s))) return r;
+        out = a.disp2;
+      }
+      if (p->scale != 1) {
+        st_scale_kernel<<<gn, 256, 0, s>>>(out, n, p->scale);
+        c->launches++;
+      }
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(pin.w, out, n, cudaMemcpyDeviceToHost, s));  // the weights in pin.w have been consumed by the builder
+      return GSM_OK;
+    };
+    rc = GSM_OK;
+    for (int i = 0; i < kc && !rc; ++i) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done[i] != 0; });
+      }
+      rc = frame_gpu(i);
+    }
+    next.store(kc);  // (on an error: no further frames are started)
+    for (std::thread& th : threads) th.join();
+    if (rc) {
+      cudaStreamSynchronize(streams[0]);
+      cudaStreamSynchronize(streams[1]);
+      return rc;
+    }
+    CK(cudaStreamSynchronize(streams[0]));
+    CK(cudaStreamSynchronize(streams[1]));
+    for (int i = 0; i < kc; ++i) memcpy(disparity + (size_t)(f0 + i) * n, StPinSlot(c, n, i).w, n);
+  }
   return GSM_OK;
 }
 

@@ -76,6 +76,7 @@ SYMBOLS = {
     "gsm_disparity_to_depth": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float]),
     "gsm_set_rectification": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "gsm_segment_tree_stereo": (C.c_int, [_P, C.POINTER(GsmStParams), _P, _P, _P, C.c_int, C.c_int]),
+    "gsm_segment_tree_stereo_batch": (C.c_int, [_P, C.POINTER(GsmStParams), _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gsm_st_matching_cost": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "gsm_st_filter": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, _P, _P]),
     "gsm_st_build_tree_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, C.POINTER(C.c_int)]),

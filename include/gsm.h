@@ -225,6 +225,13 @@ typedef struct gsm_st_params {
 } gsm_st_params;
 int gsm_segment_tree_stereo(gsm_ctx* ctx, const gsm_st_params* p, const uint8_t* left3, const uint8_t* right3,
                             uint8_t* disparity, int rows, int cols);
+/* nframes pairs of one size in one call (left3 / right3: [nframes][rows][cols][3], disparity: [nframes][rows][cols]).
+ * The reference's STMatching processes one pair per process (main.cpp:60); its host-bound stage -- one tree per frame --
+ * is independent across frames, so the trees are built concurrently on host_threads host threads (0 = one per
+ * hardware thread, at most nframes) while the GPU aggregates each frame as soon as its tree is packed.  ST-1 only
+ * (p->refined must be 0).  Every frame's map is identical to gsm_segment_tree_stereo on that pair. */
+int gsm_segment_tree_stereo_batch(gsm_ctx* ctx, const gsm_st_params* p, const uint8_t* left3, const uint8_t* right3,
+                                  uint8_t* disparity, int nframes, int rows, int cols, int host_threads);
 /* Stage exports (parity with the reference stage by stage).  GetMatchingCost: float [rows][cols][num_disp]. */
 int gsm_st_matching_cost(gsm_ctx* ctx, const uint8_t* left3, const uint8_t* right3, float* cost, int rows, int cols,
                          int num_disp);

@@ -622,6 +622,26 @@ def test_segment_tree_filter_kernel_variants(ctx, orc, monkeypatch):
             assert np.array_equal(vols["16"], vref), (name, float(np.abs(vols["16"] - vref).max()))
 
 
+def test_segment_tree_stereo_batch_equals_single_calls(ctx):
+    """gsm_segment_tree_stereo_batch (trees of the frames built concurrently on host threads, GPU stages per frame as the
+    trees arrive) returns, frame for frame, the map gsm_segment_tree_stereo returns for that pair -- for any number of
+    builder threads, for more frames than pinned slots are in flight, and repeatably."""
+    n = 7
+    Ls = np.stack([gdata.synthetic_color_pair(96, 150, 100 + i, dmax=28)[0] for i in range(n)])
+    Rs = np.stack([gdata.synthetic_color_pair(96, 150, 100 + i, dmax=28)[1] for i in range(n)])
+    single = np.stack([ctx.segment_tree_stereo(Ls[i], Rs[i], 32, scale=4) for i in range(n)])
+    assert len({single[i].tobytes() for i in range(n)}) == n  # the frames really differ
+    for threads in (1, 2, 3, 0):
+        batch = ctx.segment_tree_stereo_batch(Ls, Rs, 32, scale=4, host_threads=threads)
+        assert batch.shape == single.shape and np.array_equal(batch, single), threads
+    one = ctx.segment_tree_stereo_batch(Ls[:1], Rs[:1], 32, scale=4)
+    assert np.array_equal(one[0], single[0])
+    with pytest.raises(ValueError):
+        ctx.segment_tree_stereo_batch(Ls, Rs[:3], 32)
+    with pytest.raises(ValueError):
+        ctx.segment_tree_stereo_batch(Ls[0], Rs[0], 32)
+
+
 def test_errors_are_reported(ctx):
     z = np.zeros((16, 16), np.uint8)
     with pytest.raises(g.GsmError):

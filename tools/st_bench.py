@@ -31,10 +31,18 @@ for (h, w, D) in ((256, 320, 64), (370, 463, 64), (720, 1280, 128)):
             for _ in range(3):
                 ctx.segment_tree_stereo(L, R, D, scale=1, refined=True)
             ms2 = (time.perf_counter() - t0) / 3 * 1e3
+        nb = 32 if h * w < 500000 else 8  # a batch: the trees of the frames are built on all host threads
+        Lb, Rb = np.stack([L] * nb), np.stack([R] * nb)
+        ctx.segment_tree_stereo_batch(Lb, Rb, D)
+        t0 = time.perf_counter()
+        bd = ctx.segment_tree_stereo_batch(Lb, Rb, D)
+        bms = (time.perf_counter() - t0) * 1e3 / nb
+        assert all(np.array_equal(bd[i], d) for i in range(nb))
     wr, wu = weights(L)
     t0 = time.perf_counter()
     for _ in range(5):
         _, _, _, levels = g.st_build_tree_host(wr, wu)
     tms = (time.perf_counter() - t0) / 5 * 1e3
     print(f"{w}x{h} x{D}: whole call {ms:8.2f} ms ({h * w * D / ms / 1e3:8.1f} MDE/s), host tree builder {tms:7.2f} ms, "
-          f"tree depth {levels} levels" + (f", ST-2 whole call {ms2:8.2f} ms" if ms2 else ""), flush=True)
+          f"tree depth {levels} levels" + (f", ST-2 whole call {ms2:8.2f} ms" if ms2 else "")
+          + f", batch of {nb}: {bms:6.2f} ms per pair ({1e3 / bms:6.1f} pairs/s)", flush=True)
