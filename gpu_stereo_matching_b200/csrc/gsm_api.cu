@@ -58,6 +58,7 @@ struct gsm_ctx {
   struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
   // segment-tree stereo (gsm_st.cuh): one device arena, grown on demand
   void* st_buf = nullptr;
+  cudaStream_t st_streams[4] = {};      // gsm_segment_tree_stereo_batch: one per device arena (created on first use)
   struct StWorker;                      // host work space of one tree-builder thread (gsm_segment_tree_stereo_batch)
   std::vector<StWorker*> st_workers;
   void* st_pin = nullptr;  // pinned host mirror of the arena's tree block + the weight / disparity read-back
@@ -157,6 +158,8 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
     if (b) cudaFree(b);
   if (c->st_pin) cudaFreeHost(c->st_pin);
   for (gsm_ctx::StWorker* w : c->st_workers) delete w;
+  for (cudaStream_t st : c->st_streams)
+    if (st) cudaStreamDestroy(st);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
@@ -1552,14 +1555,20 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
   // frames in flight: two per builder thread, within 256 MB of pinned host memory (a slot mirrors one frame's tree)
   const size_t slot_bytes = (StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256;
   const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(2 * (size_t)T, (size_t)nframes), std::max<size_t>(2, ((size_t)256 << 20) / slot_bytes)));
-  // two device arenas on two streams: a tree filter occupies one CTA per disparity, so for num_disp <= half the SMs
-  // two frames aggregate side by side
-  if ((rc = st_reserve(c, n, D, false, K, 2))) return rc;
+  // Several device arenas, each on its own stream: a tree filter is one CTA per disparity and latency-bound (a quarter
+  // of its SM's issue slots), so the filters of several frames run side by side -- on different SMs while there are
+  // free ones, co-resident after that.
+  constexpr int NA = 4;
+  if ((rc = st_reserve(c, n, D, false, K, NA))) return rc;
   while ((int)c->st_workers.size() < T) c->st_workers.push_back(new gsm_ctx::StWorker());
-  const StArena a(c->st_buf, n, D, false);
-  const StArena arena[2] = {a, StArena((char*)c->st_buf + a.bytes, n, D, false)};
-  cudaStream_t s = c->stream;
-  cudaStream_t streams[2] = {c->stream, c->s_h2d};  // (the host-path upload stream is idle during this call)
+  std::vector<StArena> arena;
+  for (int k = 0; k < NA; ++k) {
+    arena.emplace_back((char*)c->st_buf + k * StArena(nullptr, n, D, false).bytes, n, D, false);
+    if (!c->st_streams[k]) CK(cudaStreamCreateWithFlags(&c->st_streams[k], cudaStreamNonBlocking));
+  }
+  cudaStream_t* streams = c->st_streams;
+  const StArena& a = arena[0];
+  cudaStream_t s = streams[0];
   const dim3 blk(128), grd((cols + 127) / 128, rows);
   const unsigned gn = (unsigned)((n + 255) / 256);
 
@@ -1602,8 +1611,8 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
     // ---- phase C (GPU): each frame as soon as its tree is packed; the disparity comes back through the frame's slot
     auto frame_gpu = [&](int i) -> int {
       const StPinSlot pin(c, n, i);
-      const StArena& a = arena[i & 1];
-      cudaStream_t s = streams[i & 1];
+      const StArena& a = arena[i % NA];
+      cudaStream_t s = streams[i % NA];
       CK(cudaMemcpyAsync(a.L3, left3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
       CK(cudaMemcpyAsync(a.R3, right3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
       st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
@@ -1638,12 +1647,10 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
     next.store(kc);  // (on an error: no further frames are started)
     for (std::thread& th : threads) th.join();
     if (rc) {
-      cudaStreamSynchronize(streams[0]);
-      cudaStreamSynchronize(streams[1]);
+      for (int k = 0; k < NA; ++k) cudaStreamSynchronize(streams[k]);
       return rc;
     }
-    CK(cudaStreamSynchronize(streams[0]));
-    CK(cudaStreamSynchronize(streams[1]));
+    for (int k = 0; k < NA; ++k) CK(cudaStreamSynchronize(streams[k]));
     for (int i = 0; i < kc; ++i) memcpy(disparity + (size_t)(f0 + i) * n, StPinSlot(c, n, i).w, n);
   }
   return GSM_OK;
