@@ -279,7 +279,7 @@ def _segment_tree_record(ctx, gdata, with_reference):
     rec = {"what": "STMatching stereo_disparity_normal (cost, segment tree, tree filter, WTA, 7x7 median) from host buffers",
            "workload": f"synthetic colour pair {w}x{h} x {D} d", "ms_per_pair": ms, "pairs_per_s": 1e3 / ms,
            "value": h * w * D / ms / 1e3, "unit": "MDE/s"}
-    nb = 16  # a batch: the per-frame trees are built concurrently on the host threads, two frames share the GPU
+    nb = 32  # a batch: the per-frame trees are built concurrently on the host threads, two frames share the GPU
     Lb, Rb = np.stack([L] * nb), np.stack([R] * nb)
     ctx.segment_tree_stereo_batch(Lb, Rb, D)
     t0 = time.perf_counter()

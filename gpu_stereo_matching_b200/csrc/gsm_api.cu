@@ -1558,12 +1558,13 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
   // Several device arenas, each on its own stream: a tree filter is one CTA per disparity and latency-bound (a quarter
   // of its SM's issue slots), so the filters of several frames run side by side -- on different SMs while there are
   // free ones, co-resident after that.
-  constexpr int NA = 4;
+  const size_t arena_bytes = StArena(nullptr, n, D, false).bytes;
+  const int NA = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)16 << 30) / arena_bytes));  // within 16 GB of device memory
   if ((rc = st_reserve(c, n, D, false, K, NA))) return rc;
   while ((int)c->st_workers.size() < T) c->st_workers.push_back(new gsm_ctx::StWorker());
   std::vector<StArena> arena;
   for (int k = 0; k < NA; ++k) {
-    arena.emplace_back((char*)c->st_buf + k * StArena(nullptr, n, D, false).bytes, n, D, false);
+    arena.emplace_back((char*)c->st_buf + k * arena_bytes, n, D, false);
     if (!c->st_streams[k]) CK(cudaStreamCreateWithFlags(&c->st_streams[k], cudaStreamNonBlocking));
   }
   cudaStream_t* streams = c->st_streams;
