@@ -84,6 +84,9 @@ struct gsm_ctx {
 struct gsm_ctx::StWorker {
   gsm_st::Tree t;
   gsm_st::detail::Work k;
+  cudaStream_t s = nullptr;  // the builder's own stream and device scratch (records phase)
+  void* dev = nullptr;
+  size_t dev_bytes = 0;
 };
 
 // strip halo (columns) a fused kernel needs on each side of its output columns
@@ -157,7 +160,11 @@ extern "C" void gsm_destroy(gsm_ctx* c) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   if (c->st_pin) cudaFreeHost(c->st_pin);
-  for (gsm_ctx::StWorker* w : c->st_workers) delete w;
+  for (gsm_ctx::StWorker* w : c->st_workers) {
+    if (w->s) cudaStreamDestroy(w->s);
+    if (w->dev) cudaFree(w->dev);
+    delete w;
+  }
   for (cudaStream_t st : c->st_streams)
     if (st) cudaStreamDestroy(st);
   for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
@@ -1195,13 +1202,15 @@ extern "C" int gsm_set_rectification(gsm_ctx* c, const float* mxl, const float* 
 
 // ---- segment-tree stereo (kernels in gsm_st.cuh, tree in gsm_st_host.hpp) --------------------------
 namespace {
-// The ordered tree as the device wants it, one contiguous block (same layout in the pinned host mirror: ONE copy).
+// The ordered tree as the host's breadth-first pass leaves it, one contiguous block with the same layout in the pinned
+// host slot and on the device: ONE copy, then st_pack_kernel forms the words the filter reads.
 struct StTreeBlock {
-  size_t o_up, o_down, o_order, o_pos, o_level, bytes;
+  size_t o_order, o_level, o_father, o_child0, o_fdist, o_nchild, o_wtab, bytes;
   explicit StTreeBlock(size_t n) {
     size_t o = 0;
     auto take = [&](size_t b) { const size_t at = o; o += (b + 255) / 256 * 256; return at; };
-    o_up = take(8 * n); o_down = take(8 * n); o_order = take(4 * n); o_pos = take(4 * n); o_level = take(4 * (n + 2));
+    o_order = take(4 * n); o_level = take(4 * (n + 2)); o_father = take(4 * n); o_child0 = take(4 * n);
+    o_fdist = take(n); o_nchild = take(n); o_wtab = take(4 * 256);
     bytes = o;
   }
 };
@@ -1222,15 +1231,27 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
     wrf = (float*)take(4 * n); wuf = (float*)take(4 * n);
     const StTreeBlock tb(n);
     tree = (char*)take(tb.bytes);
-    up = (int2*)(tree + tb.o_up); down = (int2*)(tree + tb.o_down); order = (int*)(tree + tb.o_order);
-    pos = (int*)(tree + tb.o_pos); level_off = (int*)(tree + tb.o_level);
+    order = (int*)(tree + tb.o_order); level_off = (int*)(tree + tb.o_level);
+    up = (int2*)take(8 * n); down = (int2*)take(8 * n); pos = (int*)take(4 * n);
     buf = (float*)take(4 * n * D); fin = (float*)take(4 * n * D);
     vol = with_vol ? (float*)take(4 * n * D) : nullptr;
     bytes = o;
   }
 };
+// Pinned slot k of gsm_ctx::st_pin: [StTreeBlock mirror][weight read-back: two planes of n floats (or of n bytes)]
+// [kept-edge flags, n bytes][per-pixel records, 8 n bytes]
+struct StPinSlot {
+  char *tree, *w, *flags, *rec;
+  static size_t stride(size_t n) { return (StTreeBlock(n).bytes + 8 * n + (n + 255) / 256 * 256 + 8 * n + 255) / 256 * 256; }
+  StPinSlot(const gsm_ctx* c, size_t n, int k) {
+    tree = (char*)c->st_pin + k * stride(n);
+    w = tree + StTreeBlock(n).bytes;
+    flags = w + 8 * n;
+    rec = flags + (n + 255) / 256 * 256;
+  }
+};
 int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol, int pin_slots = 1, int arenas = 1) {
-  const size_t pin = pin_slots * ((StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256);  // see StPinSlot
+  const size_t pin = pin_slots * StPinSlot::stride(n);
   if (c->st_pin_bytes < pin) {
     if (c->st_pin) cudaFreeHost(c->st_pin);
     c->st_pin = nullptr;
@@ -1254,16 +1275,24 @@ int st_check(const gsm_ctx* c, int rows, int cols, int D) {
   if (D < 1 || D > MAX_DISP) return fail(GSM_ERR_INVALID, "num_disp %d not in 1..256", D);
   return GSM_OK;
 }
-// ---- the tree of one view, in three phases (ST-2 builds the trees of its two views on two host threads) -------------
-// Pinned slot k of gsm_ctx::st_pin: [StTreeBlock mirror][weight read-back: two planes of n floats (or n bytes)]
-struct StPinSlot {
-  char *tree, *w;
-  StPinSlot(const gsm_ctx* c, size_t n, int k) {
-    const size_t stride = (StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256;
-    tree = (char*)c->st_pin + k * stride;
-    w = tree + StTreeBlock(n).bytes;
+// A tree builder: host work space + its own stream and device scratch for the data-parallel middle phase.  One per
+// thread that builds trees (the calling thread uses builder 0).
+int st_worker(gsm_ctx* c, int k, size_t n, gsm_ctx::StWorker** out) {
+  while ((int)c->st_workers.size() <= k) c->st_workers.push_back(new gsm_ctx::StWorker());
+  gsm_ctx::StWorker* w = c->st_workers[k];
+  if (!w->s) CK(cudaStreamCreateWithFlags(&w->s, cudaStreamNonBlocking));
+  const size_t need = 8 * n + (n + 255) / 256 * 256 + 8 * n;  // weights (two float planes at most), flags, records
+  if (w->dev_bytes < need) {
+    if (w->dev) cudaFree(w->dev);
+    w->dev = nullptr;
+    w->dev_bytes = 0;
+    CK(cudaMalloc(&w->dev, need));
+    w->dev_bytes = need;
   }
-};
+  *out = w;
+  return GSM_OK;
+}
+// ---- the tree of one view, in three phases ---------------------------------------------------------------------------
 // phase 1 (GPU, asynchronous on s): 3x3 median of the image, edge weights, read-back into pw.  With disp / mask (device
 // u8 maps) the weights are CColorDepthWeight's (SegmentTree.cpp:197-218, float), else CColorWeight's (u8).
 int st_weights_async(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, char* pw, cudaStream_t s,
@@ -1285,53 +1314,83 @@ int st_weights_async(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int
   c->launches += 2;
   return GSM_OK;
 }
-// phase 2 (host only; safe to run concurrently for different t / k / pin_tree): the ordered tree from the weights in pw,
-// then its device form written into the pinned mirror of the arena's tree block.  Fills dt except the device pointers.
-void st_build_pack(const char* pw, bool float_weights, int rows, int cols, float sigma, float tau, gsm_st::Tree& t,
-                   gsm_st::detail::Work& k, char* pin_tree, StTree* dt) {
+// phase 2 (safe to run concurrently on different builders / pinned slots; the calling thread must have the context's
+// device current): the ordered tree from the weights in pin.w, left in the pinned mirror of the arena's tree block.
+//   host: edges sorted, the two Kruskal passes -> kept-edge flags          (sequential by definition)
+//   GPU (the builder's stream): per-pixel records from flags + weights     (data parallel: st_records_kernel)
+//   host: breadth-first ordering                                           (sequential, one record per node)
+// Fills dt except the device pointers.
+int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int rows, int cols, float sigma, float tau,
+             StTree* dt, long long* launches) {
   const size_t n = (size_t)rows * cols;
+  const size_t wb = float_weights ? 4 : 1;
+  int m;
+  if (float_weights) m = gsm_st::sort_edges_f((const float*)pin.w, (const float*)pin.w + n, rows, cols, w.k);
+  else m = gsm_st::sort_edges((const u8*)pin.w, (const u8*)pin.w + n, rows, cols, w.k);
+  gsm_st::detail::kruskal(w.k, rows, cols, m, tau);
+  memcpy(pin.flags, w.k.flags.data(), n);
+  char* dw = (char*)w.dev;
+  u8* dflags = (u8*)(dw + 8 * n);
+  unsigned long long* drec = (unsigned long long*)(dw + 8 * n + (n + 255) / 256 * 256);
+  CK(cudaMemcpyAsync(dw, pin.w, 2 * n * wb, cudaMemcpyHostToDevice, w.s));
+  CK(cudaMemcpyAsync(dflags, pin.flags, n, cudaMemcpyHostToDevice, w.s));
+  const dim3 blk(128), grd((cols + 127) / 128, rows);
   if (float_weights)
-    gsm_st::build_tree_f((const float*)pw, (const float*)pw + n, rows, cols, tau, /*CColorDepthWeight::GetScale*/ 255.0f, t, k);
+    st_records_kernel<float><<<grd, blk, 0, w.s>>>(dflags, (const float*)dw, (const float*)dw + n, drec, rows, cols,
+                                                   /*CColorDepthWeight::GetScale*/ 255.0f);
   else
-    gsm_st::build_tree((const u8*)pw, (const u8*)pw + n, rows, cols, tau, /*CColorWeight::GetScale*/ 1.0f, t, k);
+    st_records_kernel<u8><<<grd, blk, 0, w.s>>>(dflags, (const u8*)dw, (const u8*)dw + n, drec, rows, cols,
+                                                /*CColorWeight::GetScale*/ 1.0f);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(pin.rec, drec, 8 * n, cudaMemcpyDeviceToHost, w.s));
+  CK(cudaStreamSynchronize(w.s));
+  ++*launches;
+  gsm_st::Tree& t = w.t;
+  gsm_st::detail::bfs((const uint64_t*)pin.rec, rows, cols, t);
+  gsm_st::detail::release_if_large(w.k, rows * cols);
   const StTreeBlock tb(n);
+  memcpy(pin.tree + tb.o_order, t.order.data(), 4 * n);
+  memcpy(pin.tree + tb.o_level, t.level_off.data(), 4 * t.level_off.size());
+  memcpy(pin.tree + tb.o_father, t.father.data(), 4 * n);
+  memcpy(pin.tree + tb.o_child0, t.child0.data(), 4 * n);
+  memcpy(pin.tree + tb.o_fdist, t.fdist.data(), n);
+  memcpy(pin.tree + tb.o_nchild, t.nchild.data(), n);
   float table[256];
   gsm_st::weight_table(sigma, table);
-  int tbits[256];
-  memcpy(tbits, table, sizeof(tbits));
-  int2* up = (int2*)(pin_tree + tb.o_up);
-  int2* down = (int2*)(pin_tree + tb.o_down);
-  int* order = (int*)(pin_tree + tb.o_order);
-  int* pos = (int*)(pin_tree + tb.o_pos);
-  for (size_t i = 0; i < n; ++i) {
-    const int id = t.order[i];
-    order[i] = id;
-    pos[id] = (int)i;
-    up[i] = make_int2(t.child0[i], (int)t.nchild[i]);
-    down[i] = make_int2(t.father[i], tbits[t.fdist[i]]);
-  }
-  memcpy(pin_tree + tb.o_level, t.level_off.data(), 4 * t.level_off.size());
+  memcpy(pin.tree + tb.o_wtab, table, sizeof(table));
   dt->levels = (int)t.level_off.size() - 1;
   dt->n = (int)n;
   dt->max_width = 0;
   for (size_t l = 0; l + 1 < t.level_off.size(); ++l) dt->max_width = std::max(dt->max_width, t.level_off[l + 1] - t.level_off[l]);
+  return GSM_OK;
 }
-// phase 3: the packed tree to the device as one copy (asynchronous on s; pin_tree stays untouched until s passes it)
-int st_upload(const StArena& a, const char* pin_tree, StTree* dt, cudaStream_t s) {
-  const StTreeBlock tb((size_t)dt->n);
-  CK(cudaMemcpyAsync(a.tree, pin_tree, tb.o_level + 4 * ((size_t)dt->levels + 1), cudaMemcpyHostToDevice, s));
+// phase 3 (asynchronous on s; pin.tree stays untouched until s has passed it): the tree block to the device as one copy,
+// then the words the filter kernels read
+int st_upload(gsm_ctx* c, const StArena& a, const StPinSlot& pin, StTree* dt, cudaStream_t s) {
+  const size_t n = (size_t)dt->n;
+  const StTreeBlock tb(n);
+  CK(cudaMemcpyAsync(a.tree, pin.tree, tb.bytes, cudaMemcpyHostToDevice, s));
+  st_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.order, (const int*)(a.tree + tb.o_father), (const int*)(a.tree + tb.o_child0),
+                                                           (const u8*)(a.tree + tb.o_fdist), (const u8*)(a.tree + tb.o_nchild),
+                                                           (const int*)(a.tree + tb.o_wtab), a.up, a.down, a.pos, (int)n);
+  c->launches++;
+  CK(cudaGetLastError());
   dt->up = a.up; dt->down = a.down; dt->level_off = a.level_off;
   return GSM_OK;
 }
-// all three for one image: image (device, interleaved 3-channel) -> the ordered tree on the device; fills t (host) too
-int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, float sigma, float tau, gsm_st::Tree& t,
-            StTree* dt, cudaStream_t s, const u8* disp = nullptr, const u8* mask = nullptr, int level = 0) {
-  const StPinSlot pin(c, (size_t)rows * cols, 0);
+// all three for one image on the calling thread: image (device, interleaved 3-channel) -> the ordered tree on the device;
+// the host form of the tree is left in builder 0 (c->st_workers[0]->t)
+int st_tree(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int cols, float sigma, float tau, StTree* dt,
+            cudaStream_t s, const u8* disp = nullptr, const u8* mask = nullptr, int level = 0) {
+  const size_t n = (size_t)rows * cols;
+  const StPinSlot pin(c, n, 0);
+  gsm_ctx::StWorker* w;
   int rc;
+  if ((rc = st_worker(c, 0, n, &w))) return rc;
   if ((rc = st_weights_async(c, a, img3, rows, cols, pin.w, s, disp, mask, level))) return rc;
   CK(cudaStreamSynchronize(s));  // (also: every earlier upload from this pinned slot has been consumed)
-  st_build_pack(pin.w, disp != nullptr, rows, cols, sigma, tau, t, gsm_st::detail::work(), pin.tree, dt);
-  return st_upload(a, pin.tree, dt, s);
+  if ((rc = st_build(*w, pin, disp != nullptr, rows, cols, sigma, tau, dt, &c->launches))) return rc;
+  return st_upload(c, a, pin, dt, s);
 }
 // the tree filter over D channels: the on-chip ring kernel with the deepest ring the widest level allows, else the plain one
 template <int RING>
@@ -1416,9 +1475,9 @@ extern "C" int gsm_st_filter(gsm_ctx* c, const uint8_t* image3, float* cost, int
   const StArena a(c->st_buf, n, num_disp, true);
   cudaStream_t s = c->stream;
   CK(cudaMemcpyAsync(a.L3, image3, 3 * n, cudaMemcpyHostToDevice, s));
-  static thread_local gsm_st::Tree t;  // its arrays are reused: fresh ones page-fault on every call
   StTree dt;
-  if ((rc = st_tree(c, a, a.L3, rows, cols, sigma, tau, t, &dt, s))) return rc;
+  if ((rc = st_tree(c, a, a.L3, rows, cols, sigma, tau, &dt, s))) return rc;
+  const gsm_st::Tree& t = c->st_workers[0]->t;
   if (order) memcpy(order, t.order.data(), 4 * n);
   if (father_id) memcpy(father_id, t.father_id.data(), 4 * n);
   if (father_dist) memcpy(father_dist, t.fdist.data(), n);
@@ -1457,7 +1516,6 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
   st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.R3, a.gR, rows, cols);
   c->launches += 2;
-  static thread_local gsm_st::Tree t;  // its arrays are reused: fresh ones page-fault on every call
   StTree dt;
   const float tau = p->tau > 0.f ? p->tau : 1200.f;
   const unsigned gn = (unsigned)((n + 255) / 256);
@@ -1480,7 +1538,7 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   };
   auto view = [&](const u8* img, int right, float sigma, const u8* tdisp, const u8* tmask, u8** out) -> int {
     int r;
-    if ((r = st_tree(c, a, img, rows, cols, sigma, tau, t, &dt, s, tdisp, tmask, D))) return r;
+    if ((r = st_tree(c, a, img, rows, cols, sigma, tau, &dt, s, tdisp, tmask, D))) return r;
     return view_gpu(right, out);
   };
   u8* out = nullptr;
@@ -1493,28 +1551,36 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
     const float SIGMA_ONE = 0.08f;
     // the trees of the two views are independent and host-bound: the right one is built on a second thread while this
     // one builds the left one; the GPU takes the left view as soon as its tree is up
-    static thread_local gsm_st::Tree t2;
-    static thread_local gsm_st::detail::Work work2;  // owned here, lent to the short-lived builder thread
     const StPinSlot pinL(c, n, 0), pinR(c, n, 1);
+    gsm_ctx::StWorker *wL, *wR;
+    if ((rc = st_worker(c, 0, n, &wL)) || (rc = st_worker(c, 1, n, &wR))) return rc;
     if ((rc = st_weights_async(c, a, a.L3, rows, cols, pinL.w, s))) return rc;
     if ((rc = st_weights_async(c, a, a.R3, rows, cols, pinR.w, s))) return rc;
     CK(cudaStreamSynchronize(s));
     StTree dtR;
-    auto build_right = [&] { st_build_pack(pinR.w, false, rows, cols, SIGMA_ONE, tau, t2, work2, pinR.tree, &dtR); };
+    int rcR = GSM_OK;
+    long long launchesR = 0;
+    const int dev = c->device;
+    auto build_right = [&] {
+      if (cudaSetDevice(dev) != cudaSuccess) { rcR = GSM_ERR_CUDA; return; }
+      rcR = st_build(*wR, pinR, false, rows, cols, SIGMA_ONE, tau, &dtR, &launchesR);
+    };
     std::thread right_builder;
     try {
       right_builder = std::thread(build_right);
     } catch (...) {  // no thread to be had: build it here, after the left one
     }
-    st_build_pack(pinL.w, false, rows, cols, SIGMA_ONE, tau, t, gsm_st::detail::work(), pinL.tree, &dt);
-    rc = st_upload(a, pinL.tree, &dt, s);
+    rc = st_build(*wL, pinL, false, rows, cols, SIGMA_ONE, tau, &dt, &c->launches);
+    if (!rc) rc = st_upload(c, a, pinL, &dt, s);
     if (!rc) rc = view_gpu(0, &out);
     if (!rc && cudaMemcpyAsync(a.dispL, out, n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(GSM_ERR_CUDA, "copy of the left disparity");
     if (right_builder.joinable()) right_builder.join();  // (before any return: the thread references this frame)
     else build_right();
+    c->launches += launchesR;
     if (rc) return rc;
+    if (rcR) return rcR;
     dt = dtR;
-    if ((rc = st_upload(a, pinR.tree, &dt, s))) return rc;
+    if ((rc = st_upload(c, a, pinR, &dt, s))) return rc;
     if ((rc = view_gpu(1, &out))) return rc;
     CK(cudaMemcpyAsync(a.dispR, out, n, cudaMemcpyDeviceToDevice, s));
     lr_check_kernel<<<dim3((cols + 255) / 256, rows, 1), 256, 0, s>>>(a.dispL, a.dispR, nullptr, a.mask, nullptr, rows, cols, 1,
@@ -1553,7 +1619,7 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
   int T = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
   T = std::max(1, std::min(std::min(T, 64), nframes));
   // frames in flight: two per builder thread, within 256 MB of pinned host memory (a slot mirrors one frame's tree)
-  const size_t slot_bytes = (StTreeBlock(n).bytes + 8 * n + 255) / 256 * 256;
+  const size_t slot_bytes = StPinSlot::stride(n);
   const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(2 * (size_t)T, (size_t)nframes), std::max<size_t>(2, ((size_t)256 << 20) / slot_bytes)));
   // Several device arenas, each on its own stream: a tree filter is one CTA per disparity and latency-bound (a quarter
   // of its SM's issue slots), so the filters of several frames run side by side -- on different SMs while there are
@@ -1561,7 +1627,10 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
   const size_t arena_bytes = StArena(nullptr, n, D, false).bytes;
   const int NA = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)16 << 30) / arena_bytes));  // within 16 GB of device memory
   if ((rc = st_reserve(c, n, D, false, K, NA))) return rc;
-  while ((int)c->st_workers.size() < T) c->st_workers.push_back(new gsm_ctx::StWorker());
+  for (int k = 0; k < T; ++k) {
+    gsm_ctx::StWorker* unused;
+    if ((rc = st_worker(c, k, n, &unused))) return rc;
+  }
   std::vector<StArena> arena;
   for (int k = 0; k < NA; ++k) {
     arena.emplace_back((char*)c->st_buf + k * arena_bytes, n, D, false);
@@ -1587,12 +1656,16 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<int> next{0};
+    std::vector<int> brc(kc, GSM_OK);
+    std::vector<long long> blaunches(kc, 0);
+    const int dev = c->device;
     auto builder = [&](int w) {
+      const bool dev_ok = cudaSetDevice(dev) == cudaSuccess;
       for (;;) {
         const int i = next.fetch_add(1);
         if (i >= kc) break;
         const StPinSlot pin(c, n, i);
-        st_build_pack(pin.w, false, rows, cols, p->sigma, tau, c->st_workers[w]->t, c->st_workers[w]->k, pin.tree, &dts[i]);
+        brc[i] = dev_ok ? st_build(*c->st_workers[w], pin, false, rows, cols, p->sigma, tau, &dts[i], &blaunches[i]) : GSM_ERR_CUDA;
         {
           std::lock_guard<std::mutex> lk(mu);
           done[i] = 1;
@@ -1619,7 +1692,8 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
       st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
       st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.R3, a.gR, rows, cols);
       int r;
-      if ((r = st_upload(a, pin.tree, &dts[i], s))) return r;
+      if (brc[i]) return brc[i];
+      if ((r = st_upload(c, a, pin, &dts[i], s))) return r;
       st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
       if ((r = st_filter_launch(c, a.buf, a.fin, dts[i], D, s))) return r;
       st_wta_kernel<<<gn, 256, 0, s>>>(a.fin, a.order, a.disp, (int)n, D);
@@ -1647,6 +1721,7 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
     }
     next.store(kc);  // (on an error: no further frames are started)
     for (std::thread& th : threads) th.join();
+    for (int i = 0; i < kc; ++i) c->launches += blaunches[i];
     if (rc) {
       for (int k = 0; k < NA; ++k) cudaStreamSynchronize(streams[k]);
       return rc;

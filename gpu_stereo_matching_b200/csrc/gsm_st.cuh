@@ -145,6 +145,51 @@ __global__ void st_edge_weight_depth_kernel(const u8* __restrict__ img, const u8
   wu[p] = y >= 1 ? wgt(p - W) : 0.f;
 }
 
+// The middle, data-parallel phase of the tree builder (gsm_st_host.hpp: kruskal -> RECORDS -> bfs) on the GPU: per pixel
+// its kept grid edges in edge-list order (SegmentTree.cpp:70-94), i.e. sorted by (w, b, a): by weight, ties in the order
+// up, left, down, right.  flags[p]: bit 0 / 1 = p's right / up edge is in the tree, bit 2 / 3 = that edge carries the
+// cross-segment penalty (segment-graph.h: w += 5).  wr[p] / wu[p] = weight of p's right / up edge (u8: CColorWeight,
+// float: CColorDepthWeight).  rec[p] = deg | direction codes (2 bits each) << 8 | quantised distances
+// min((int)(w * scale + 0.5f), 255) << 32 -- the same words detail::records() produces on the host.
+template <typename WT>
+__global__ void st_records_kernel(const u8* __restrict__ flags, const WT* __restrict__ wr, const WT* __restrict__ wu,
+                                  unsigned long long* __restrict__ rec, int H, int W, float scale) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int p = y * W + x;
+  typedef unsigned long long u64;
+  const int f = flags[p], fl = x > 0 ? flags[p - 1] : 0, fd = y + 1 < H ? flags[p + W] : 0;
+  auto item = [&](int used, int pen, WT wq, u64 dcode) -> u64 {
+    float w = (float)wq;
+    const u64 key = sizeof(WT) == 1 ? (u64)wq : (u64)__float_as_uint(w);  // weights >= 0: the bits order like the value
+    if (pen) w = __fadd_rn(w, 5.0f);
+    const u64 dq = (u64)min((int)__fadd_rn(__fmul_rn(w, scale), 0.5f), 255);
+    return used ? (key << 12 | dcode << 10 | dcode << 8 | dq) : ~0ull;
+  };
+  u64 i0 = item(f & 2, f & 8, wu[p], 0);
+  u64 i1 = item(fl & 1, fl & 4, x > 0 ? wr[p - 1] : wr[p], 1);
+  u64 i2 = item(fd & 2, fd & 8, y + 1 < H ? wu[p + W] : wu[p], 2);
+  u64 i3 = item(f & 1, f & 4, wr[p], 3);
+  auto cswap = [](u64& a, u64& b) { const u64 lo = min(a, b), hi = max(a, b); a = lo; b = hi; };
+  cswap(i0, i1); cswap(i2, i3); cswap(i0, i2); cswap(i1, i3); cswap(i1, i2);
+  const u64 deg = (u64)((f & 2) != 0) + ((fl & 1) != 0) + ((fd & 2) != 0) + ((f & 1) != 0);
+  rec[p] = deg | ((i0 >> 8) & 3) << 8 | ((i1 >> 8) & 3) << 10 | ((i2 >> 8) & 3) << 12 | ((i3 >> 8) & 3) << 14 |
+           (i0 & 255) << 32 | (i1 & 255) << 40 | (i2 & 255) << 48 | (i3 & 255) << 56;
+}
+
+// The ordered tree as the host's breadth-first pass leaves it (per BFS position: pixel, father, first child, number of
+// children, quantised weight of the edge to the father) -> the words the filter kernels read + the pixel -> position map.
+// wtab[q] = float bits of m_table[q] = exp(-q / (255 sigma)) (CSegmentTree::UpdateTable, computed on the host).
+__global__ void st_pack_kernel(const int* __restrict__ order, const int* __restrict__ father, const int* __restrict__ child0,
+                               const u8* __restrict__ fdist, const u8* __restrict__ nchild, const int* __restrict__ wtab,
+                               int2* __restrict__ up, int2* __restrict__ down, int* __restrict__ pos, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pos[order[i]] = i;
+  up[i] = make_int2(child0[i], (int)nchild[i]);
+  down[i] = make_int2(father[i], wtab[fdist[i]]);
+}
+
 // The ordered tree (breadth-first from pixel 0, SegmentTree.cpp:97-131) as arrays indexed by BFS position:
 //   father[i]  BFS position of the father (root: -1)      fw[i]  m_table[father.dist] = exp(-dist / (255 sigma))
 //   child0[i]  BFS position of the first child             nchild[i]  number of children

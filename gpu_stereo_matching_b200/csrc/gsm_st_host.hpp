@@ -78,9 +78,12 @@ inline void release_if_large(Work& k, int n) {
 
 enum : uint8_t { USED_R = 1, USED_U = 2, PEN_R = 4, PEN_U = 8 };
 
-// code[i] (sorted by (w, b, a)), ws[i] = the edge's weight.  wgt(p, dir) = weight of pixel p's right (0) / up (1) edge.
-template <class W>
-inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const W& wgt, Tree& t) {
+// The builder runs in three phases so that the middle one -- per-pixel, data parallel -- can run on the GPU
+// (st_records_kernel in gsm_st.cuh computes the same records from the same inputs):
+//   kruskal()  edges in k.code / k.ws (sorted by (w, b, a))  ->  k.flags, four bits per pixel
+//   records()  flags + weights                               ->  k.rec, per pixel its kept edges in edge-list order
+//   bfs()      records                                       ->  the ordered tree
+inline void kruskal(Work& k, int H, int Wd, int m, float tau) {
   const int n = H * Wd;
   const uint32_t* code = k.code.data();
   const float* ws = k.ws.data();
@@ -127,6 +130,13 @@ inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const 
       }
     }
   }
+}
+
+// wgt(p, dir) = weight of pixel p's right (0) / up (1) edge.
+template <class W>
+inline void records(Work& k, int H, int Wd, float scale, const W& wgt) {
+  const int n = H * Wd;
+  const uint8_t* flags = k.flags.data();
   // ---- per pixel: its kept edges in edge-list order (SegmentTree.cpp:70-94).  Ties in w are ordered by (b, a): the
   // up neighbour (b = p - W), the left one (b = p, a = p - 1), the one below (b = p, a = p + W), the right one (b = p + 1).
   // rec = deg | dir codes (2 bits each) << 8 | quantised distances << 32
@@ -166,6 +176,11 @@ inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const 
       rec[p] = deg | ((i0 >> 8) & 3) << 8 | ((i1 >> 8) & 3) << 10 | ((i2 >> 8) & 3) << 12 | ((i3 >> 8) & 3) << 14 |
                (i0 & 255) << 32 | (i1 & 255) << 40 | (i2 & 255) << 48 | (i3 & 255) << 56;
     }
+}
+
+// rec[p] = deg | dir codes (2 bits each, U L D R = 0 1 2 3) << 8 | quantised distances << 32 (records() / st_records_kernel)
+inline void bfs(const uint64_t* rec, int H, int Wd, Tree& t) {
+  const int n = H * Wd;
   // ---- ordered tree: breadth-first from pixel 0 (SegmentTree.cpp:97-131)
   // (branch-free body: all four slots of a record are written, `end` only moves past the real children; the arrays
   // carry 4 spare entries for the writes past the last node)
@@ -200,13 +215,20 @@ inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const 
   t.level_off.push_back(n);
 }
 
+template <class W>
+inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const W& wgt, Tree& t) {
+  kruskal(k, H, Wd, m, tau);
+  records(k, H, Wd, scale, wgt);
+  bfs(k.rec.data(), H, Wd, t);
+}
+
 }  // namespace detail
 
 // wr[p]: weight of edge (p, p+1) for x < W-1; wu[p]: weight of edge (p, p-W) for y >= 1 (st_edge_weight_kernel).
 // tau: the constant c of the threshold function c / size (TAU = 1200 in Toolkit.h:33); scale: CWeightProvider::GetScale().
 // k: the builder's work space (default: one per calling thread; callers that build on short-lived threads pass their own).
-inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t,
-                       detail::Work& k = detail::work()) {
+// edges of the grid in the reference's sorted order -> k.code / k.ws; returns their number
+inline int sort_edges(const uint8_t* wr, const uint8_t* wu, int H, int W, detail::Work& k) {
   // ---- edges in the reference's sorted order: by weight, then by b, then by a (segment-graph.h:33-41): a counting
   // sort whose buckets are filled in (b, a) order by construction
   int cnt[257] = {0};
@@ -226,6 +248,11 @@ inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float
       if (x >= 1) { const int a = b - 1, i = cnt[wr[a]]++; code[i] = (uint32_t)a << 1; ws[i] = (float)wr[a]; }            // (a, a+1)
       if (y + 1 < H) { const int a = b + W, i = cnt[wu[a]]++; code[i] = (uint32_t)a << 1 | 1u; ws[i] = (float)wu[a]; }   // (a, a-W)
     }
+  return m;
+}
+inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t,
+                       detail::Work& k = detail::work()) {
+  const int m = sort_edges(wr, wu, H, W, k);
   detail::finish(k, H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
   detail::release_if_large(k, H * W);
 }
@@ -233,8 +260,7 @@ inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float
 // The same for real-valued weights >= 0 (CColorDepthWeight, SegmentTree.cpp:204-218): the bit pattern of a non-negative
 // float orders like the float, so the sort is a stable least-significant-digit radix sort (3 passes of 11 bits) of the
 // edges enumerated in (b, a) order.
-inline void build_tree_f(const float* wr, const float* wu, int H, int W, float tau, float scale, Tree& t,
-                         detail::Work& k = detail::work()) {
+inline int sort_edges_f(const float* wr, const float* wu, int H, int W, detail::Work& k) {
   const int m = (W - 1) * H + (H - 1) * W;
   k.code.resize(m); k.code2.resize(m); k.key.resize(m); k.key2.resize(m); k.ws.resize(m);
   uint32_t *c0 = k.code.data(), *c1 = k.code2.data(), *k0 = k.key.data(), *k1 = k.key2.data();
@@ -261,6 +287,11 @@ inline void build_tree_f(const float* wr, const float* wu, int H, int W, float t
   }
   if (c0 != k.code.data()) std::memcpy(k.code.data(), c0, 4 * (size_t)m);  // 3 passes: the result is in the second pair
   std::memcpy(k.ws.data(), k0, 4 * (size_t)m);
+  return m;
+}
+inline void build_tree_f(const float* wr, const float* wu, int H, int W, float tau, float scale, Tree& t,
+                         detail::Work& k = detail::work()) {
+  const int m = sort_edges_f(wr, wu, H, W, k);
   detail::finish(k, H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
   detail::release_if_large(k, H * W);
 }
