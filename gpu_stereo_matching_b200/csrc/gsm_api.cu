@@ -14,6 +14,7 @@
 #include "gsm_sad.cuh"
 #include "gsm_st.cuh"
 #include "gsm_st_host.hpp"
+#include <cub/device/device_radix_sort.cuh>
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
@@ -86,7 +87,7 @@ struct gsm_ctx::StWorker {
   gsm_st::detail::Work k;
   cudaStream_t s = nullptr;  // the builder's own stream and device scratch (records phase)
   void* dev = nullptr;
-  size_t dev_bytes = 0;
+  size_t dev_bytes = 0, sort_temp = 0, scratch_n = 0;
 };
 
 // strip halo (columns) a fused kernel needs on each side of its output columns
@@ -1239,14 +1240,16 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
   }
 };
 // Pinned slot k of gsm_ctx::st_pin: [StTreeBlock mirror][weight read-back: two planes of n floats (or of n bytes)]
-// [kept-edge flags, n bytes][per-pixel records, 8 n bytes]
+// [sorted edge codes, <= 2n words][sorted edge weights, <= 2n floats][kept-edge flags, n bytes][per-pixel records, 8 n bytes]
 struct StPinSlot {
-  char *tree, *w, *flags, *rec;
-  static size_t stride(size_t n) { return (StTreeBlock(n).bytes + 8 * n + (n + 255) / 256 * 256 + 8 * n + 255) / 256 * 256; }
+  char *tree, *w, *code, *ws, *flags, *rec;
+  static size_t stride(size_t n) { return (StTreeBlock(n).bytes + 8 * n * 3 + (n + 255) / 256 * 256 + 8 * n + 255) / 256 * 256; }
   StPinSlot(const gsm_ctx* c, size_t n, int k) {
     tree = (char*)c->st_pin + k * stride(n);
     w = tree + StTreeBlock(n).bytes;
-    flags = w + 8 * n;
+    code = w + 8 * n;
+    ws = code + 8 * n;
+    flags = ws + 8 * n;
     rec = flags + (n + 255) / 256 * 256;
   }
 };
@@ -1280,14 +1283,28 @@ int st_check(const gsm_ctx* c, int rows, int cols, int D) {
 int st_worker(gsm_ctx* c, int k, size_t n, gsm_ctx::StWorker** out) {
   while ((int)c->st_workers.size() <= k) c->st_workers.push_back(new gsm_ctx::StWorker());
   gsm_ctx::StWorker* w = c->st_workers[k];
-  if (!w->s) CK(cudaStreamCreateWithFlags(&w->s, cudaStreamNonBlocking));
-  const size_t need = 8 * n + (n + 255) / 256 * 256 + 8 * n;  // weights (two float planes at most), flags, records
-  if (w->dev_bytes < need) {
-    if (w->dev) cudaFree(w->dev);
-    w->dev = nullptr;
-    w->dev_bytes = 0;
-    CK(cudaMalloc(&w->dev, need));
-    w->dev_bytes = need;
+  if (!w->s) {  // high priority: a builder's small kernels must not queue behind the tree filters of other frames
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&w->s, cudaStreamNonBlocking, hi));
+  }
+  // weights (two float planes at most) | flags | records | edge keys in/out, codes in/out, sorted weights (<= 2n words each) | sort temp
+  if (w->scratch_n != n) {  // (the size query walks the sort's dispatch: not something to repeat per call and builder)
+    size_t temp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const u32*)nullptr, (u32*)nullptr, (const u32*)nullptr, (u32*)nullptr,
+                                       (int)(2 * n), 0, 32));
+    temp = (temp + 255) / 256 * 256;
+    const size_t need = 7 * ((8 * n + 255) / 256 * 256) + (n + 255) / 256 * 256 + temp;
+    if (w->dev_bytes < need) {
+      if (w->dev) cudaFree(w->dev);
+      w->dev = nullptr;
+      w->dev_bytes = 0;
+      w->scratch_n = 0;
+      CK(cudaMalloc(&w->dev, need));
+      w->dev_bytes = need;
+    }
+    w->sort_temp = temp;
+    w->scratch_n = n;
   }
   *out = w;
   return GSM_OK;
@@ -1316,25 +1333,60 @@ int st_weights_async(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int
 }
 // phase 2 (safe to run concurrently on different builders / pinned slots; the calling thread must have the context's
 // device current): the ordered tree from the weights in pin.w, left in the pinned mirror of the arena's tree block.
-//   host: edges sorted, the two Kruskal passes -> kept-edge flags          (sequential by definition)
-//   GPU (the builder's stream): per-pixel records from flags + weights     (data parallel: st_records_kernel)
+//   GPU (the builder's stream): edges enumerated and sorted by weight      (stable radix sort)
+//   host: the two Kruskal passes -> kept-edge flags                        (sequential by definition)
+//   GPU: per-pixel records from flags + weights                            (data parallel: st_records_kernel)
 //   host: breadth-first ordering                                           (sequential, one record per node)
 // Fills dt except the device pointers.
 int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int rows, int cols, float sigma, float tau,
-             StTree* dt, long long* launches) {
+             StTree* dt, long long* launches, bool gpu_sort = true) {
   const size_t n = (size_t)rows * cols;
   const size_t wb = float_weights ? 4 : 1;
-  int m;
-  if (float_weights) m = gsm_st::sort_edges_f((const float*)pin.w, (const float*)pin.w + n, rows, cols, w.k);
-  else m = gsm_st::sort_edges((const u8*)pin.w, (const u8*)pin.w + n, rows, cols, w.k);
-  gsm_st::detail::kruskal(w.k, rows, cols, m, tau);
-  memcpy(pin.flags, w.k.flags.data(), n);
+  const int m = (cols - 1) * rows + (rows - 1) * cols;  // edges of the grid
+  const size_t r8 = (8 * n + 255) / 256 * 256, r1 = (n + 255) / 256 * 256;  // (the carve-up st_worker sized)
   char* dw = (char*)w.dev;
-  u8* dflags = (u8*)(dw + 8 * n);
-  unsigned long long* drec = (unsigned long long*)(dw + 8 * n + (n + 255) / 256 * 256);
-  CK(cudaMemcpyAsync(dw, pin.w, 2 * n * wb, cudaMemcpyHostToDevice, w.s));
-  CK(cudaMemcpyAsync(dflags, pin.flags, n, cudaMemcpyHostToDevice, w.s));
+  u8* dflags = (u8*)(dw + r8);
+  unsigned long long* drec = (unsigned long long*)(dw + r8 + r1);
+  u32* key_in = (u32*)(dw + 2 * r8 + r1);
+  u32* key_out = (u32*)(dw + 3 * r8 + r1);
+  u32* code_in = (u32*)(dw + 4 * r8 + r1);
+  u32* code_out = (u32*)(dw + 5 * r8 + r1);
+  float* dws = (float*)(dw + 6 * r8 + r1);
+  void* temp = dw + 7 * r8 + r1;
   const dim3 blk(128), grd((cols + 127) / 128, rows);
+  // ---- the edges in the reference's sorted order (GPU: enumerate in (b, a) order, stable radix sort by weight)
+  CK(cudaMemcpyAsync(dw, pin.w, 2 * n * wb, cudaMemcpyHostToDevice, w.s));
+  const uint32_t* code;
+  const float* ws;
+  if (gpu_sort) {
+    size_t temp_bytes = w.sort_temp;
+    if (float_weights) {
+      st_enumerate_edges_kernel<float><<<grd, blk, 0, w.s>>>((const float*)dw, (const float*)dw + n, key_in, code_in, rows, cols);
+      CK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const u32*)key_in, key_out, (const u32*)code_in, code_out, m, 0, 32, w.s));
+      st_edge_weights_from_keys_kernel<float><<<(m + 255) / 256, 256, 0, w.s>>>(key_out, dws, m);
+    } else {
+      st_enumerate_edges_kernel<u8><<<grd, blk, 0, w.s>>>((const u8*)dw, (const u8*)dw + n, key_in, code_in, rows, cols);
+      CK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const u32*)key_in, key_out, (const u32*)code_in, code_out, m, 0, 8, w.s));
+      st_edge_weights_from_keys_kernel<u8><<<(m + 255) / 256, 256, 0, w.s>>>(key_out, dws, m);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pin.code, code_out, 4 * (size_t)m, cudaMemcpyDeviceToHost, w.s));
+    CK(cudaMemcpyAsync(pin.ws, dws, 4 * (size_t)m, cudaMemcpyDeviceToHost, w.s));
+    CK(cudaStreamSynchronize(w.s));
+    *launches += 3;  // + the sort's own kernels
+    code = (const uint32_t*)pin.code;
+    ws = (const float*)pin.ws;
+  } else {  // the same order on the host (counting / radix sort of gsm_st_host.hpp; measured 4 % slower even in batches)
+    if (float_weights) gsm_st::sort_edges_f((const float*)pin.w, (const float*)pin.w + n, rows, cols, w.k);
+    else gsm_st::sort_edges((const u8*)pin.w, (const u8*)pin.w + n, rows, cols, w.k);
+    code = w.k.code.data();
+    ws = w.k.ws.data();
+  }
+  // ---- the two Kruskal passes (host: sequential by definition) -> kept-edge flags
+  gsm_st::detail::kruskal(w.k, code, ws, rows, cols, m, tau);
+  memcpy(pin.flags, w.k.flags.data(), n);
+  // ---- per-pixel records (GPU)
+  CK(cudaMemcpyAsync(dflags, pin.flags, n, cudaMemcpyHostToDevice, w.s));
   if (float_weights)
     st_records_kernel<float><<<grd, blk, 0, w.s>>>(dflags, (const float*)dw, (const float*)dw + n, drec, rows, cols,
                                                    /*CColorDepthWeight::GetScale*/ 255.0f);
@@ -1618,9 +1670,12 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
   const float tau = p->tau > 0.f ? p->tau : 1200.f;
   int T = host_threads > 0 ? host_threads : (int)std::thread::hardware_concurrency();
   T = std::max(1, std::min(std::min(T, 64), nframes));
-  // frames in flight: two per builder thread, within 256 MB of pinned host memory (a slot mirrors one frame's tree)
+  // frames in flight: two per builder thread, within 512 MB of pinned host memory (a slot mirrors one frame's tree),
+  // and chunks of equal size (a short last chunk costs a whole round of tree builds)
   const size_t slot_bytes = StPinSlot::stride(n);
-  const int K = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(2 * (size_t)T, (size_t)nframes), std::max<size_t>(2, ((size_t)256 << 20) / slot_bytes)));
+  const int kmax = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(2 * (size_t)T, (size_t)nframes), std::max<size_t>(2, ((size_t)512 << 20) / slot_bytes)));
+  const int chunks = (nframes + kmax - 1) / kmax;
+  const int K = (nframes + chunks - 1) / chunks;
   // Several device arenas, each on its own stream: a tree filter is one CTA per disparity and latency-bound (a quarter
   // of its SM's issue slots), so the filters of several frames run side by side -- on different SMs while there are
   // free ones, co-resident after that.

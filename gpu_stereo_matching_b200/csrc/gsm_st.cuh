@@ -2,8 +2,10 @@
 // stereo_disparity_normal (STMatching/StereoDisparity.cpp:58-90), on the GPU wherever it is data parallel:
 //   GetMatchingCost (StereoHelper.cpp:75-129)           st_gray_grad_kernel + st_cost_kernel
 //   CColorWeight (SegmentTree.cpp:183-195)              st_median3_kernel (3x3 median per channel) + st_edge_weight_kernel
-//   BuildSegmentTree (SegmentTree.cpp:38-139)           HOST (gsm_st_host.hpp): Kruskal with Felzenszwalb's adaptive threshold
-//                                                       is defined by its sequential edge order; O(N) here (counting sort)
+//   BuildSegmentTree (SegmentTree.cpp:38-139)           edge sort: st_enumerate_edges_kernel + radix sort; Kruskal with Felzenszwalb's
+//                                                       adaptive threshold (defined by its sequential edge order) and the
+//                                                       breadth-first ordering: HOST (gsm_st_host.hpp); between them
+//                                                       st_records_kernel, after them st_pack_kernel
 //   Filter (SegmentTree.cpp:148-181)                    st_filter_kernel: two level-synchronous passes over the ordered tree
 //   GetDisparity_WTA (StereoHelper.cpp:131-154)         st_wta_kernel
 //   MeanFilter(disparity, 3), disparity *= scale        median_kernel (gsm_util.cuh) + st_scale_kernel
@@ -143,6 +145,30 @@ __global__ void st_edge_weight_depth_kernel(const u8* __restrict__ img, const u8
   };
   wr[p] = x + 1 < W ? wgt(p + 1) : 0.f;
   wu[p] = y >= 1 ? wgt(p - W) : 0.f;
+}
+
+// The first phase of the tree builder on the GPU: the grid's edges enumerated in (b, a) order -- for every pixel b in
+// raster order the edge from its left neighbour, then the edge from the pixel below (segment-graph.h:33-41 sorts by
+// (w, b, a); a stable sort by weight of this enumeration is that order).  code = (lower / left pixel a) << 1 | direction
+// (0: (a, a+1), 1: (a, a-W)), key = the weight (u8 value, or the bits of the non-negative float).
+template <typename WT>
+__global__ void st_enumerate_edges_kernel(const WT* __restrict__ wr, const WT* __restrict__ wu, u32* __restrict__ key,
+                                          u32* __restrict__ code, int H, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const int b = y * W + x;
+  const bool down = y + 1 < H;
+  // edges of the pixels before b: rows above have W - 1 left edges and W down edges each
+  int e = y * (2 * W - 1) + (x > 0 ? x - 1 : 0) + (down ? x : 0);
+  auto bits = [](WT v) -> u32 { return sizeof(WT) == 1 ? (u32)v : __float_as_uint((float)v + 0.0f); };  // (-0 -> +0)
+  if (x > 0) { key[e] = bits(wr[b - 1]); code[e] = (u32)(b - 1) << 1; ++e; }
+  if (down) { key[e] = bits(wu[b + W]); code[e] = (u32)(b + W) << 1 | 1u; }
+}
+// sorted keys -> the float weights the Kruskal passes compare
+template <typename WT>
+__global__ void st_edge_weights_from_keys_kernel(const u32* __restrict__ key, float* __restrict__ ws, int m) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) ws[i] = sizeof(WT) == 1 ? (float)key[i] : __uint_as_float(key[i]);
 }
 
 // The middle, data-parallel phase of the tree builder (gsm_st_host.hpp: kruskal -> RECORDS -> bfs) on the GPU: per pixel

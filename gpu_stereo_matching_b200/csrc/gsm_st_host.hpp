@@ -80,13 +80,11 @@ enum : uint8_t { USED_R = 1, USED_U = 2, PEN_R = 4, PEN_U = 8 };
 
 // The builder runs in three phases so that the middle one -- per-pixel, data parallel -- can run on the GPU
 // (st_records_kernel in gsm_st.cuh computes the same records from the same inputs):
-//   kruskal()  edges in k.code / k.ws (sorted by (w, b, a))  ->  k.flags, four bits per pixel
+//   kruskal()  edges (code[i], ws[i]) sorted by (w, b, a)    ->  k.flags, four bits per pixel
 //   records()  flags + weights                               ->  k.rec, per pixel its kept edges in edge-list order
 //   bfs()      records                                       ->  the ordered tree
-inline void kruskal(Work& k, int H, int Wd, int m, float tau) {
+inline void kruskal(Work& k, const uint32_t* code, const float* ws, int H, int Wd, int m, float tau) {
   const int n = H * Wd;
-  const uint32_t* code = k.code.data();
-  const float* ws = k.ws.data();
   k.p.resize(n); k.size.resize(n); k.thr.resize(n);
   k.flags.assign(n, 0);
   uint8_t* flags = k.flags.data();
@@ -217,7 +215,7 @@ inline void bfs(const uint64_t* rec, int H, int Wd, Tree& t) {
 
 template <class W>
 inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const W& wgt, Tree& t) {
-  kruskal(k, H, Wd, m, tau);
+  kruskal(k, k.code.data(), k.ws.data(), H, Wd, m, tau);
   records(k, H, Wd, scale, wgt);
   bfs(k.rec.data(), H, Wd, t);
 }
