@@ -59,7 +59,7 @@ struct gsm_ctx {
   struct StatGeom { int rows = -1, cols = -1, xoff = -1, n = -1; } stat_geom[2];  // geometry the statistic planes were zeroed for
   // segment-tree stereo (gsm_st.cuh): one device arena, grown on demand
   void* st_buf = nullptr;
-  cudaStream_t st_streams[4] = {};      // gsm_segment_tree_stereo_batch: one per device arena (created on first use)
+  cudaStream_t st_streams[8] = {};      // gsm_segment_tree_stereo_batch: one per device arena (created on first use)
   struct StWorker;                      // host work space of one tree-builder thread (gsm_segment_tree_stereo_batch)
   std::vector<StWorker*> st_workers;
   void* st_pin = nullptr;  // pinned host mirror of the arena's tree block + the weight / disparity read-back
@@ -1241,9 +1241,12 @@ struct StArena {  // carve-up of gsm_ctx::st_buf for one rows x cols x D problem
 };
 // Pinned slot k of gsm_ctx::st_pin: [StTreeBlock mirror][weight read-back: two planes of n floats (or of n bytes)]
 // [sorted edge codes, <= 2n words][sorted edge weights, <= 2n floats][kept-edge flags, n bytes][per-pixel records, 8 n bytes]
+// [batches: the frame's two images, 3n bytes each]
 struct StPinSlot {
-  char *tree, *w, *code, *ws, *flags, *rec;
-  static size_t stride(size_t n) { return (StTreeBlock(n).bytes + 8 * n * 3 + (n + 255) / 256 * 256 + 8 * n + 255) / 256 * 256; }
+  char *tree, *w, *code, *ws, *flags, *rec, *img;
+  static size_t stride(size_t n) {
+    return (StTreeBlock(n).bytes + 8 * n * 3 + (n + 255) / 256 * 256 + 8 * n + 2 * ((3 * n + 255) / 256 * 256) + 255) / 256 * 256;
+  }
   StPinSlot(const gsm_ctx* c, size_t n, int k) {
     tree = (char*)c->st_pin + k * stride(n);
     w = tree + StTreeBlock(n).bytes;
@@ -1251,6 +1254,7 @@ struct StPinSlot {
     ws = code + 8 * n;
     flags = ws + 8 * n;
     rec = flags + (n + 255) / 256 * 256;
+    img = rec + 8 * n;
   }
 };
 int st_reserve(gsm_ctx* c, size_t n, int D, bool with_vol, int pin_slots = 1, int arenas = 1) {
@@ -1294,7 +1298,7 @@ int st_worker(gsm_ctx* c, int k, size_t n, gsm_ctx::StWorker** out) {
     CK(cub::DeviceRadixSort::SortPairs(nullptr, temp, (const u32*)nullptr, (u32*)nullptr, (const u32*)nullptr, (u32*)nullptr,
                                        (int)(2 * n), 0, 32));
     temp = (temp + 255) / 256 * 256;
-    const size_t need = 7 * ((8 * n + 255) / 256 * 256) + (n + 255) / 256 * 256 + temp;
+    const size_t need = 7 * ((8 * n + 255) / 256 * 256) + (n + 255) / 256 * 256 + temp + 2 * ((3 * n + 255) / 256 * 256);
     if (w->dev_bytes < need) {
       if (w->dev) cudaFree(w->dev);
       w->dev = nullptr;
@@ -1339,7 +1343,8 @@ int st_weights_async(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int
 //   host: breadth-first ordering                                           (sequential, one record per node)
 // Fills dt except the device pointers.
 int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int rows, int cols, float sigma, float tau,
-             StTree* dt, long long* launches, bool gpu_sort = true) {
+             StTree* dt, long long* launches, bool gpu_sort = true, const u8* left_host = nullptr,
+             const u8* right_host = nullptr) {
   const size_t n = (size_t)rows * cols;
   const size_t wb = float_weights ? 4 : 1;
   const int m = (cols - 1) * rows + (rows - 1) * cols;  // edges of the grid
@@ -1354,8 +1359,23 @@ int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int
   float* dws = (float*)(dw + 6 * r8 + r1);
   void* temp = dw + 7 * r8 + r1;
   const dim3 blk(128), grd((cols + 127) / 128, rows);
+  if (left_host) {
+    // batches: the builder stages its frame itself (the copies out of pageable memory run on all builder threads) and
+    // computes the edge weights on its own stream -- they never leave the device
+    const size_t r3 = (3 * n + 255) / 256 * 256;
+    u8* dimg = (u8*)temp + w.sort_temp;
+    u8* dmed = dimg + r3;
+    memcpy(pin.img, left_host, 3 * n);
+    memcpy(pin.img + r3, right_host, 3 * n);
+    CK(cudaMemcpyAsync(dimg, pin.img, 3 * n, cudaMemcpyHostToDevice, w.s));
+    st_median3_kernel<<<grd, blk, 0, w.s>>>(dimg, dmed, rows, cols);
+    st_edge_weight_kernel<<<grd, blk, 0, w.s>>>(dmed, (u8*)dw, (u8*)dw + n, rows, cols);
+    *launches += 2;
+    gpu_sort = true;  // (the weights are not on the host)
+  } else {
+    CK(cudaMemcpyAsync(dw, pin.w, 2 * n * wb, cudaMemcpyHostToDevice, w.s));
+  }
   // ---- the edges in the reference's sorted order (GPU: enumerate in (b, a) order, stable radix sort by weight)
-  CK(cudaMemcpyAsync(dw, pin.w, 2 * n * wb, cudaMemcpyHostToDevice, w.s));
   const uint32_t* code;
   const float* ws;
   if (gpu_sort) {
@@ -1680,7 +1700,7 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
   // of its SM's issue slots), so the filters of several frames run side by side -- on different SMs while there are
   // free ones, co-resident after that.
   const size_t arena_bytes = StArena(nullptr, n, D, false).bytes;
-  const int NA = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)16 << 30) / arena_bytes));  // within 16 GB of device memory
+  const int NA = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)16 << 30) / arena_bytes));  // within 16 GB; 8 arenas measured no faster
   if ((rc = st_reserve(c, n, D, false, K, NA))) return rc;
   for (int k = 0; k < T; ++k) {
     gsm_ctx::StWorker* unused;
@@ -1699,13 +1719,8 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
 
   for (int f0 = 0; f0 < nframes; f0 += K) {
     const int kc = std::min(K, nframes - f0);
-    // ---- phase A (GPU): edge weights of every frame of the chunk into its pinned slot
-    for (int i = 0; i < kc; ++i) {
-      CK(cudaMemcpyAsync(a.L3, left3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
-      if ((rc = st_weights_async(c, a, a.L3, rows, cols, StPinSlot(c, n, i).w, s))) return rc;
-    }
-    CK(cudaStreamSynchronize(s));
-    // ---- phase B (host threads): trees, in frame order off a shared counter
+    // ---- builder threads: frames in order off a shared counter; each stages its frame in its pinned slot, computes the
+    // edge weights on its own stream and builds the tree (st_build)
     std::vector<StTree> dts(kc);
     std::vector<char> done(kc, 0);
     std::mutex mu;
@@ -1720,7 +1735,9 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
         const int i = next.fetch_add(1);
         if (i >= kc) break;
         const StPinSlot pin(c, n, i);
-        brc[i] = dev_ok ? st_build(*c->st_workers[w], pin, false, rows, cols, p->sigma, tau, &dts[i], &blaunches[i]) : GSM_ERR_CUDA;
+        brc[i] = dev_ok ? st_build(*c->st_workers[w], pin, false, rows, cols, p->sigma, tau, &dts[i], &blaunches[i], true,
+                                   left3 + (size_t)(f0 + i) * 3 * n, right3 + (size_t)(f0 + i) * 3 * n)
+                        : GSM_ERR_CUDA;
         {
           std::lock_guard<std::mutex> lk(mu);
           done[i] = 1;
@@ -1737,17 +1754,18 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
       }
     }
     if (threads.empty()) builder(0);  // none at all: build here, then run the GPU stages
-    // ---- phase C (GPU): each frame as soon as its tree is packed; the disparity comes back through the frame's slot
+    // ---- the calling thread: each frame to the GPU as soon as its tree is packed (asynchronous copies and launches
+    // only); the disparity comes back through the frame's slot
     auto frame_gpu = [&](int i) -> int {
       const StPinSlot pin(c, n, i);
       const StArena& a = arena[i % NA];
       cudaStream_t s = streams[i % NA];
-      CK(cudaMemcpyAsync(a.L3, left3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(a.R3, right3 + (size_t)(f0 + i) * 3 * n, 3 * n, cudaMemcpyHostToDevice, s));
+      if (brc[i]) return brc[i];
+      CK(cudaMemcpyAsync(a.L3, pin.img, 3 * n, cudaMemcpyHostToDevice, s));  // staged by the builder
+      CK(cudaMemcpyAsync(a.R3, pin.img + (3 * n + 255) / 256 * 256, 3 * n, cudaMemcpyHostToDevice, s));
       st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
       st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.R3, a.gR, rows, cols);
       int r;
-      if (brc[i]) return brc[i];
       if ((r = st_upload(c, a, pin, &dts[i], s))) return r;
       st_cost_kernel<<<grd, blk, 0, s>>>(a.L3, a.R3, a.gL, a.gR, a.buf, a.pos, n, rows, cols, D);
       if ((r = st_filter_launch(c, a.buf, a.fin, dts[i], D, s))) return r;
