@@ -1343,8 +1343,7 @@ int st_weights_async(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int
 //   host: breadth-first ordering                                           (sequential, one record per node)
 // Fills dt except the device pointers.
 int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int rows, int cols, float sigma, float tau,
-             StTree* dt, long long* launches, bool gpu_sort = true, const u8* left_host = nullptr,
-             const u8* right_host = nullptr) {
+             StTree* dt, long long* launches, const u8* left_host = nullptr, const u8* right_host = nullptr) {
   const size_t n = (size_t)rows * cols;
   const size_t wb = float_weights ? 4 : 1;
   const int m = (cols - 1) * rows + (rows - 1) * cols;  // edges of the grid
@@ -1371,37 +1370,27 @@ int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int
     st_median3_kernel<<<grd, blk, 0, w.s>>>(dimg, dmed, rows, cols);
     st_edge_weight_kernel<<<grd, blk, 0, w.s>>>(dmed, (u8*)dw, (u8*)dw + n, rows, cols);
     *launches += 2;
-    gpu_sort = true;  // (the weights are not on the host)
   } else {
     CK(cudaMemcpyAsync(dw, pin.w, 2 * n * wb, cudaMemcpyHostToDevice, w.s));
   }
   // ---- the edges in the reference's sorted order (GPU: enumerate in (b, a) order, stable radix sort by weight)
-  const uint32_t* code;
-  const float* ws;
-  if (gpu_sort) {
-    size_t temp_bytes = w.sort_temp;
-    if (float_weights) {
-      st_enumerate_edges_kernel<float><<<grd, blk, 0, w.s>>>((const float*)dw, (const float*)dw + n, key_in, code_in, rows, cols);
-      CK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const u32*)key_in, key_out, (const u32*)code_in, code_out, m, 0, 32, w.s));
-      st_edge_weights_from_keys_kernel<float><<<(m + 255) / 256, 256, 0, w.s>>>(key_out, dws, m);
-    } else {
-      st_enumerate_edges_kernel<u8><<<grd, blk, 0, w.s>>>((const u8*)dw, (const u8*)dw + n, key_in, code_in, rows, cols);
-      CK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const u32*)key_in, key_out, (const u32*)code_in, code_out, m, 0, 8, w.s));
-      st_edge_weights_from_keys_kernel<u8><<<(m + 255) / 256, 256, 0, w.s>>>(key_out, dws, m);
-    }
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(pin.code, code_out, 4 * (size_t)m, cudaMemcpyDeviceToHost, w.s));
-    CK(cudaMemcpyAsync(pin.ws, dws, 4 * (size_t)m, cudaMemcpyDeviceToHost, w.s));
-    CK(cudaStreamSynchronize(w.s));
-    *launches += 3;  // + the sort's own kernels
-    code = (const uint32_t*)pin.code;
-    ws = (const float*)pin.ws;
-  } else {  // the same order on the host (counting / radix sort of gsm_st_host.hpp; measured 4 % slower even in batches)
-    if (float_weights) gsm_st::sort_edges_f((const float*)pin.w, (const float*)pin.w + n, rows, cols, w.k);
-    else gsm_st::sort_edges((const u8*)pin.w, (const u8*)pin.w + n, rows, cols, w.k);
-    code = w.k.code.data();
-    ws = w.k.ws.data();
+  size_t temp_bytes = w.sort_temp;
+  if (float_weights) {
+    st_enumerate_edges_kernel<float><<<grd, blk, 0, w.s>>>((const float*)dw, (const float*)dw + n, key_in, code_in, rows, cols);
+    CK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const u32*)key_in, key_out, (const u32*)code_in, code_out, m, 0, 32, w.s));
+    st_edge_weights_from_keys_kernel<float><<<(m + 255) / 256, 256, 0, w.s>>>(key_out, dws, m);
+  } else {
+    st_enumerate_edges_kernel<u8><<<grd, blk, 0, w.s>>>((const u8*)dw, (const u8*)dw + n, key_in, code_in, rows, cols);
+    CK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const u32*)key_in, key_out, (const u32*)code_in, code_out, m, 0, 8, w.s));
+    st_edge_weights_from_keys_kernel<u8><<<(m + 255) / 256, 256, 0, w.s>>>(key_out, dws, m);
   }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(pin.code, code_out, 4 * (size_t)m, cudaMemcpyDeviceToHost, w.s));
+  CK(cudaMemcpyAsync(pin.ws, dws, 4 * (size_t)m, cudaMemcpyDeviceToHost, w.s));
+  CK(cudaStreamSynchronize(w.s));
+  *launches += 3;  // + the sort's own kernels
+  const uint32_t* code = (const uint32_t*)pin.code;
+  const float* ws = (const float*)pin.ws;
   // ---- the two Kruskal passes (host: sequential by definition) -> kept-edge flags
   gsm_st::detail::kruskal(w.k, code, ws, rows, cols, m, tau);
   memcpy(pin.flags, w.k.flags.data(), n);
@@ -1735,7 +1724,7 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
         const int i = next.fetch_add(1);
         if (i >= kc) break;
         const StPinSlot pin(c, n, i);
-        brc[i] = dev_ok ? st_build(*c->st_workers[w], pin, false, rows, cols, p->sigma, tau, &dts[i], &blaunches[i], true,
+        brc[i] = dev_ok ? st_build(*c->st_workers[w], pin, false, rows, cols, p->sigma, tau, &dts[i], &blaunches[i],
                                    left3 + (size_t)(f0 + i) * 3 * n, right3 + (size_t)(f0 + i) * 3 * n)
                         : GSM_ERR_CUDA;
         {

@@ -3,10 +3,14 @@
 // CSegmentTree::BuildSegmentTree (STMatching/SegmentTree.cpp:38-139) with segment_graph (segment-graph.h:48-101) is
 // Kruskal's algorithm with Felzenszwalb's adaptive merge threshold: whether an edge joins two components depends on
 // the sizes of the components all lighter edges have formed, i.e. on the sequential order of the sorted edge list.
-// It is therefore built on the host -- in O(N), and around the fact that the graph is the pixel GRID:
+// That sequential core -- the two Kruskal passes -- and the breadth-first ordering are the host's part; the sort before
+// them and the per-pixel step between them are data parallel and, in the product pipeline (st_build in gsm_api.cu), run
+// on the GPU (gsm_st.cuh: st_enumerate_edges_kernel + radix sort, st_records_kernel).  This header holds the two host
+// phases plus host versions of the other two (build_tree: the host-only gsm_st_build_tree_host, which the CPU tests
+// compare with the reference's tree).  Everything is O(N) and built around the fact that the graph is the pixel GRID:
 //   * an edge is one 32-bit word (lower/left pixel << 1 | direction); the reference's std::sort by (w, b, a)
-//     (segment-graph.h:33-41) is a stable counting sort (integer weights of CColorWeight) or a stable 3-pass radix sort
-//     (float weights of CColorDepthWeight) of the edges enumerated in (b, a) order;
+//     (segment-graph.h:33-41) is a stable sort by weight of the edges enumerated in (b, a) order (here: a counting sort
+//     over CColorWeight's integer weights);
 //   * which edges the two Kruskal passes keep (and which the second one penalises) is four bits per pixel;
 //   * the reference's adjacency lists "in edge order" (SegmentTree.cpp:70-94) are, per pixel, its <= 4 kept grid edges
 //     sorted by (w, b, a) -- a local sort done in one raster pass, no scattered list building;
@@ -59,9 +63,8 @@ struct Sets {
 };
 
 struct Work {  // reused across calls: fresh multi-megabyte allocations page-fault every time
-  std::vector<uint32_t> code, code2;
+  std::vector<uint32_t> code;
   std::vector<float> ws;
-  std::vector<uint32_t> key, key2;
   std::vector<int> p, size;
   std::vector<float> thr;
   std::vector<uint8_t> flags;
@@ -251,45 +254,6 @@ inline int sort_edges(const uint8_t* wr, const uint8_t* wu, int H, int W, detail
 inline void build_tree(const uint8_t* wr, const uint8_t* wu, int H, int W, float tau, float scale, Tree& t,
                        detail::Work& k = detail::work()) {
   const int m = sort_edges(wr, wu, H, W, k);
-  detail::finish(k, H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
-  detail::release_if_large(k, H * W);
-}
-
-// The same for real-valued weights >= 0 (CColorDepthWeight, SegmentTree.cpp:204-218): the bit pattern of a non-negative
-// float orders like the float, so the sort is a stable least-significant-digit radix sort (3 passes of 11 bits) of the
-// edges enumerated in (b, a) order.
-inline int sort_edges_f(const float* wr, const float* wu, int H, int W, detail::Work& k) {
-  const int m = (W - 1) * H + (H - 1) * W;
-  k.code.resize(m); k.code2.resize(m); k.key.resize(m); k.key2.resize(m); k.ws.resize(m);
-  uint32_t *c0 = k.code.data(), *c1 = k.code2.data(), *k0 = k.key.data(), *k1 = k.key2.data();
-  int e = 0;
-  auto bits = [](float f) { if (f == 0.f) f = 0.f; uint32_t u; std::memcpy(&u, &f, 4); return u; };  // -0 -> +0
-  for (int y = 0, b = 0; y < H; ++y)
-    for (int x = 0; x < W; ++x, ++b) {
-      if (x >= 1) { c0[e] = (uint32_t)(b - 1) << 1; k0[e++] = bits(wr[b - 1]); }
-      if (y + 1 < H) { c0[e] = (uint32_t)(b + W) << 1 | 1u; k0[e++] = bits(wu[b + W]); }
-    }
-  std::vector<int> cnt(2049);
-  for (int pass = 0; pass < 3; ++pass) {
-    const int sh = 11 * pass;
-    std::fill(cnt.begin(), cnt.end(), 0);
-    for (int i = 0; i < m; ++i) cnt[((k0[i] >> sh) & 2047u) + 1]++;
-    for (int i = 0; i < 2048; ++i) cnt[i + 1] += cnt[i];
-    for (int i = 0; i < m; ++i) {
-      const int j = cnt[(k0[i] >> sh) & 2047u]++;
-      k1[j] = k0[i];
-      c1[j] = c0[i];
-    }
-    std::swap(k0, k1);
-    std::swap(c0, c1);
-  }
-  if (c0 != k.code.data()) std::memcpy(k.code.data(), c0, 4 * (size_t)m);  // 3 passes: the result is in the second pair
-  std::memcpy(k.ws.data(), k0, 4 * (size_t)m);
-  return m;
-}
-inline void build_tree_f(const float* wr, const float* wu, int H, int W, float tau, float scale, Tree& t,
-                         detail::Work& k = detail::work()) {
-  const int m = sort_edges_f(wr, wu, H, W, k);
   detail::finish(k, H, W, m, tau, scale, [&](int p, int dir) { return dir ? wu[p] : wr[p]; }, t);
   detail::release_if_large(k, H * W);
 }
