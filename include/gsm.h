@@ -210,8 +210,9 @@ int gsm_set_rectification(gsm_ctx* ctx, const float* mapx_left, const float* map
  * SegmentTree.cpp:38-195) -> winner-take-all (StereoHelper.cpp:131-154) -> (2m+1)^2 median (Toolkit.cpp:33-48) ->
  * disparity * scale.  Images: interleaved 3-channel u8, rows x cols, channel order as cv::imread gives it (B, G, R);
  * at least 3 x 3 pixels (the reference's median asserts below that).  Host pointers, blocking.  Every stage is bit-exact to the reference compiled without FP contraction.
- * The tree itself (Kruskal with an adaptive threshold: defined by its sequential edge order) is built on the host,
- * in O(pixels); cost, tree filter, WTA and median run on the GPU. */
+ * Of the tree construction only what is sequential by definition runs on the host, in O(pixels): the two Kruskal
+ * passes (adaptive threshold: the outcome depends on the sorted edge order) and the breadth-first ordering; the edge
+ * sort, the per-pixel adjacency, cost, tree filter, WTA and median run on the GPU. */
 typedef struct gsm_st_params {
   int num_disp;      /* max_dis_level, 1..256 */
   float sigma;       /* range parameter of the edge-weight table exp(-dist / (255 sigma)) (SegmentTree.cpp:141-146) */
