@@ -18,6 +18,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
+#include <string>
 #include <thread>
 #include "gsm_util.cuh"
 
@@ -1620,11 +1621,13 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
     CK(cudaStreamSynchronize(s));
     StTree dtR;
     int rcR = GSM_OK;
+    std::string errR;
     long long launchesR = 0;
     const int dev = c->device;
     auto build_right = [&] {
-      if (cudaSetDevice(dev) != cudaSuccess) { rcR = GSM_ERR_CUDA; return; }
+      if (cudaSetDevice(dev) != cudaSuccess) { rcR = GSM_ERR_CUDA; errR = "cudaSetDevice failed on the builder thread"; return; }
       rcR = st_build(*wR, pinR, false, rows, cols, SIGMA_ONE, tau, &dtR, &launchesR);
+      if (rcR) errR = g_err;  // (thread-local text)
     };
     std::thread right_builder;
     try {
@@ -1639,7 +1642,7 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
     else build_right();
     c->launches += launchesR;
     if (rc) return rc;
-    if (rcR) return rcR;
+    if (rcR) return fail(rcR, "tree builder, right view: %s", errR.c_str());
     dt = dtR;
     if ((rc = st_upload(c, a, pinR, &dt, s))) return rc;
     if ((rc = view_gpu(1, &out))) return rc;
@@ -1716,6 +1719,7 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
     std::condition_variable cv;
     std::atomic<int> next{0};
     std::vector<int> brc(kc, GSM_OK);
+    std::vector<std::string> berr(kc);  // (the error text is thread-local: carried over by hand)
     std::vector<long long> blaunches(kc, 0);
     const int dev = c->device;
     auto builder = [&](int w) {
@@ -1727,6 +1731,7 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
         brc[i] = dev_ok ? st_build(*c->st_workers[w], pin, false, rows, cols, p->sigma, tau, &dts[i], &blaunches[i],
                                    left3 + (size_t)(f0 + i) * 3 * n, right3 + (size_t)(f0 + i) * 3 * n)
                         : GSM_ERR_CUDA;
+        if (brc[i]) berr[i] = dev_ok ? g_err : "cudaSetDevice failed on a builder thread";
         {
           std::lock_guard<std::mutex> lk(mu);
           done[i] = 1;
@@ -1749,7 +1754,7 @@ extern "C" int gsm_segment_tree_stereo_batch(gsm_ctx* c, const gsm_st_params* p,
       const StPinSlot pin(c, n, i);
       const StArena& a = arena[i % NA];
       cudaStream_t s = streams[i % NA];
-      if (brc[i]) return brc[i];
+      if (brc[i]) return fail(brc[i], "tree builder, frame %d: %s", f0 + i, berr[i].c_str());
       CK(cudaMemcpyAsync(a.L3, pin.img, 3 * n, cudaMemcpyHostToDevice, s));  // staged by the builder
       CK(cudaMemcpyAsync(a.R3, pin.img + (3 * n + 255) / 256 * 256, 3 * n, cudaMemcpyHostToDevice, s));
       st_gray_grad_kernel<<<grd, blk, 0, s>>>(a.L3, a.gL, rows, cols);
