@@ -607,7 +607,7 @@ def test_segment_tree_filter_kernel_variants(ctx, orc, monkeypatch):
     Lb, Rb = gdata.synthetic_color_pair(480, 640, 23, dmax=24)
     tiny = lambda h, w: (L[40:40 + h, 60:60 + w].copy(), R[40:40 + h, 60:60 + w].copy())  # trees shallower than the ring
     for name, (a, b), D in (("art_demo", (L, R), 32), ("vga", (Lb, Rb), 16), ("3x3", tiny(3, 3), 3), ("5x4", tiny(5, 4), 4),
-                            ("1 row of levels", tiny(3, 40), 5)):
+                            ("wide strip", tiny(3, 40), 5), ("tall strip", tiny(40, 3), 3)):
         cost = ctx.st_matching_cost(a, b, D)
         vols = {}
         for ring in ("0", "4", "8", "16"):
