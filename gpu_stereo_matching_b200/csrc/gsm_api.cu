@@ -16,6 +16,7 @@
 #include "gsm_st_host.hpp"
 #include <cub/device/device_radix_sort.cuh>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -1336,6 +1337,23 @@ int st_weights_async(gsm_ctx* c, const StArena& a, const u8* img3, int rows, int
   c->launches += 2;
   return GSM_OK;
 }
+// GSM_ST_TIMING=1: wall-clock milliseconds of the builder's phases on stderr (dev aid; the GPU phases include their syncs)
+struct StPhaseClock {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  char line[256];
+  int len = 0;
+  StPhaseClock() : on(getenv("GSM_ST_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) { line[0] = 0; }
+  void mark(const char* name) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    len += snprintf(line + len, sizeof(line) - len, " %s %.3f", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+  void print(const char* what) {
+    if (on) fprintf(stderr, "[gsm st] %s:%s ms\n", what, line);
+  }
+};
 // phase 2 (safe to run concurrently on different builders / pinned slots; the calling thread must have the context's
 // device current): the ordered tree from the weights in pin.w, left in the pinned mirror of the arena's tree block.
 //   GPU (the builder's stream): edges enumerated and sorted by weight      (stable radix sort)
@@ -1348,6 +1366,7 @@ int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int
   const size_t n = (size_t)rows * cols;
   const size_t wb = float_weights ? 4 : 1;
   const int m = (cols - 1) * rows + (rows - 1) * cols;  // edges of the grid
+  StPhaseClock clk;
   const size_t r8 = (8 * n + 255) / 256 * 256, r1 = (n + 255) / 256 * 256;  // (the carve-up st_worker sized)
   char* dw = (char*)w.dev;
   u8* dflags = (u8*)(dw + r8);
@@ -1390,11 +1409,13 @@ int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int
   CK(cudaMemcpyAsync(pin.ws, dws, 4 * (size_t)m, cudaMemcpyDeviceToHost, w.s));
   CK(cudaStreamSynchronize(w.s));
   *launches += 3;  // + the sort's own kernels
+  clk.mark("weights+sort(gpu)");
   const uint32_t* code = (const uint32_t*)pin.code;
   const float* ws = (const float*)pin.ws;
   // ---- the two Kruskal passes (host: sequential by definition) -> kept-edge flags
   gsm_st::detail::kruskal(w.k, code, ws, rows, cols, m, tau);
   memcpy(pin.flags, w.k.flags.data(), n);
+  clk.mark("kruskal(host)");
   // ---- per-pixel records (GPU)
   CK(cudaMemcpyAsync(dflags, pin.flags, n, cudaMemcpyHostToDevice, w.s));
   if (float_weights)
@@ -1407,8 +1428,10 @@ int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int
   CK(cudaMemcpyAsync(pin.rec, drec, 8 * n, cudaMemcpyDeviceToHost, w.s));
   CK(cudaStreamSynchronize(w.s));
   ++*launches;
+  clk.mark("records(gpu)");
   gsm_st::Tree& t = w.t;
   gsm_st::detail::bfs((const uint64_t*)pin.rec, rows, cols, t);
+  clk.mark("bfs(host)");
   gsm_st::detail::release_if_large(w.k, rows * cols);
   const StTreeBlock tb(n);
   memcpy(pin.tree + tb.o_order, t.order.data(), 4 * n);
@@ -1424,6 +1447,8 @@ int st_build(gsm_ctx::StWorker& w, const StPinSlot& pin, bool float_weights, int
   dt->n = (int)n;
   dt->max_width = 0;
   for (size_t l = 0; l + 1 < t.level_off.size(); ++l) dt->max_width = std::max(dt->max_width, t.level_off[l + 1] - t.level_off[l]);
+  clk.mark("stage");
+  clk.print("tree builder");
   return GSM_OK;
 }
 // phase 3 (asynchronous on s; pin.tree stays untouched until s has passed it): the tree block to the device as one copy,
@@ -1565,6 +1590,7 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   if (!left3 || !right3 || !disparity) return fail(GSM_ERR_INVALID, "null pointer");
   if (p->median_radius < 0 || p->median_radius > MED_MAXR) return fail(GSM_ERR_INVALID, "median_radius %d", p->median_radius);
   if (p->scale < 1) return fail(GSM_ERR_INVALID, "scale %d", p->scale);
+  StPhaseClock clk;
   CK(cudaSetDevice(c->device));
   if ((rc = gsm_sync(c))) return rc;
   const size_t n = (size_t)rows * cols;
@@ -1600,7 +1626,9 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   };
   auto view = [&](const u8* img, int right, float sigma, const u8* tdisp, const u8* tmask, u8** out) -> int {
     int r;
+    clk.mark("upload+launches");
     if ((r = st_tree(c, a, img, rows, cols, sigma, tau, &dt, s, tdisp, tmask, D))) return r;
+    clk.mark("tree(weights, builder, upload)");
     return view_gpu(right, out);
   };
   u8* out = nullptr;
@@ -1659,6 +1687,8 @@ extern "C" int gsm_segment_tree_stereo(gsm_ctx* c, const gsm_st_params* p, const
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(disparity, out, n, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  clk.mark("cost+filter+wta+median+download");
+  clk.print("gsm_segment_tree_stereo");
   return GSM_OK;
 }
 
