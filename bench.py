@@ -771,7 +771,10 @@ def main():
         if dsplit is not None:
             line["dsplit"] = dsplit
         if world == 1:
-            line["segment_tree"] = _segment_tree_record(ctx, gdata, with_reference=not args.no_cpu_baseline)
+            try:  # a side record: it must never cost the headline line
+                line["segment_tree"] = _segment_tree_record(ctx, gdata, with_reference=not args.no_cpu_baseline)
+            except Exception as e:  # noqa: BLE001
+                line["segment_tree"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             with O.quiet_stdout():
