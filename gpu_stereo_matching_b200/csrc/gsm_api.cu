@@ -1564,7 +1564,8 @@ extern "C" int gsm_st_filter(gsm_ctx* c, const uint8_t* image3, float* cost, int
   CK(cudaMemcpyAsync(a.L3, image3, 3 * n, cudaMemcpyHostToDevice, s));
   StTree dt;
   if ((rc = st_tree(c, a, a.L3, rows, cols, sigma, tau, &dt, s))) return rc;
-  const gsm_st::Tree& t = c->st_workers[0]->t;
+  gsm_st::Tree& t = c->st_workers[0]->t;
+  if (father_id) gsm_st::detail::father_ids(t);
   if (order) memcpy(order, t.order.data(), 4 * n);
   if (father_id) memcpy(father_id, t.father_id.data(), 4 * n);
   if (father_dist) memcpy(father_dist, t.fdist.data(), n);

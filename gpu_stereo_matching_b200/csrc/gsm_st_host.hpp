@@ -185,35 +185,40 @@ inline void bfs(const uint64_t* rec, int H, int Wd, Tree& t) {
   // ---- ordered tree: breadth-first from pixel 0 (SegmentTree.cpp:97-131)
   // (branch-free body: all four slots of a record are written, `end` only moves past the real children; the arrays
   // carry 4 spare entries for the writes past the last node)
-  t.order.resize(n + 4); t.father.resize(n + 4); t.father_id.resize(n + 4); t.fdist.resize(n + 4);
+  t.order.resize(n + 4); t.father.resize(n + 4); t.fdist.resize(n + 4);
   t.child0.resize(n); t.nchild.resize(n); t.level_off.clear();
   int* order = t.order.data();
   int* father = t.father.data();
-  int* father_id = t.father_id.data();
   uint8_t* fdist = t.fdist.data();
   const int delta[4] = {-Wd, -1, Wd, 1};
-  order[0] = 0; father[0] = -1; father_id[0] = 0; fdist[0] = 0;
+  order[0] = 0; father[0] = -1; fdist[0] = 0;
   t.level_off.push_back(0);
   int end = 1, level_end = 1;
   for (int pos = 0; pos < n; ++pos) {
     if (pos == level_end) { t.level_off.push_back(pos); level_end = end; }
     if (pos + 8 < end) __builtin_prefetch(&rec[order[pos + 8]]);
-    const int id = order[pos], fid = pos ? father_id[pos] : -1;
+    const int id = order[pos], fid = pos ? order[father[pos]] : -1;  // (the father was ordered long ago: a cache hit)
     const uint64_t r = rec[id];
     const int deg = (int)(r & 7), e0 = end;
     for (int j = 0; j < 4; ++j) {
       const int c = id + delta[(r >> (8 + 2 * j)) & 3];
       order[end] = c;
       father[end] = pos;
-      father_id[end] = id;
       fdist[end] = (uint8_t)(r >> (32 + 8 * j));
       end += (int)((j < deg) & (c != fid));
     }
     t.child0[pos] = e0;
     t.nchild[pos] = (uint8_t)(end - e0);
   }
-  t.order.resize(n); t.father.resize(n); t.father_id.resize(n); t.fdist.resize(n);
+  t.order.resize(n); t.father.resize(n); t.fdist.resize(n);
   t.level_off.push_back(n);
+}
+// m_tree[i].father.id for the callers that report it (the pipeline itself works on BFS positions)
+inline void father_ids(Tree& t) {
+  const size_t n = t.order.size();
+  t.father_id.resize(n);
+  if (n) t.father_id[0] = 0;
+  for (size_t i = 1; i < n; ++i) t.father_id[i] = t.order[t.father[i]];
 }
 
 template <class W>
@@ -221,6 +226,7 @@ inline void finish(Work& k, int H, int Wd, int m, float tau, float scale, const 
   kruskal(k, k.code.data(), k.ws.data(), H, Wd, m, tau);
   records(k, H, Wd, scale, wgt);
   bfs(k.rec.data(), H, Wd, t);
+  father_ids(t);
 }
 
 }  // namespace detail
